@@ -1,0 +1,115 @@
+/* include/hvapprox_b200.h — extended C-ABI of libmoocore_b200.so.
+ *
+ * Everything here is an ADDITION to the reference interface (the reference has none of it);
+ * the three drop-in entry points live in include/hvapprox.h.  The additions exist for
+ *   - multi-GPU sharding: a sample index range [i0, i1) of one estimate can be evaluated on
+ *     one device and combined later (the reference's loop c/hvapprox.c:235,676,851 is the
+ *     range [0, nsamples));
+ *   - measurement: keep the point set resident in HBM across calls, time the kernels;
+ *   - parity tests: per-sample values and the generated direction set.
+ * Plain C types only (no torch, no CUDA types; a CUDA stream is passed as void*).
+ *
+ * Every function returning int returns 0 on success and a negative code on failure;
+ * hvb200_last_error() then describes the failure (thread-local).
+ */
+#ifndef HVAPPROX_B200_H_
+#define HVAPPROX_B200_H_
+
+#include "hvapprox.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Direction-set generators; numbering follows c/main-hvapprox.c's -m option. */
+enum {
+    HVB200_METHOD_MC   = 1,   /* DZ2019-MC   hv_approx_normal                (c/hvapprox.c:221) */
+    HVB200_METHOD_HW   = 2,   /* DZ2019-HW   hv_approx_hua_wang              (c/hvapprox.c:656) */
+    HVB200_METHOD_RPHI = 3    /* Rphi-FWE+   hv_approx_rphi_fang_wang_plus   (c/hvapprox.c:834) */
+};
+
+/* Max-min kernel variants.  Both give bit-identical per-sample values. */
+enum {
+    HVB200_KERNEL_AUTO   = 0,
+    HVB200_KERNEL_EXACT  = 1, /* d DMUL + d min + 1 max per sample*point (the textbook loop)   */
+    HVB200_KERNEL_SCREEN = 2  /* exact threshold screen: 1 DSETP per element, products only for
+                                 candidates that can raise the running max                      */
+};
+
+/* Largest dimension the library accepts.  The reference stops at 31
+ * (MOOCORE_HVAPPROX_DIMENSION_MAX, c/config.h:28); 32..HVB200_DIMENSION_MAX is an extension
+ * (c_d from the closed form, generic square-and-multiply for s^d) offered for DZ2019-MC and
+ * Rphi-FWE+ only and only through this header, never through include/hvapprox.h. */
+#define HVB200_DIMENSION_MAX 64
+
+typedef struct hvb200_plan hvb200_plan;   /* opaque: transformed point set resident on one GPU */
+
+typedef struct hvb200_stats {
+    double maxmin_ms;      /* sum of device time of the max-min kernel launches of the last run */
+    double dirgen_ms;      /* same for the direction generators                                  */
+    double reduce_ms;      /* final reduction kernel                                             */
+    double h2d_ms;         /* host->device copies issued by the last run (MC/Rphi streams)       */
+    uint64_t maxmin_launches;
+    uint64_t dirgen_launches;
+    uint64_t reduce_launches;
+    uint64_t samples;      /* i1 - i0 of the last run                                            */
+    uint64_t npoints;      /* n' (points that strictly dominate ref)                             */
+    uint64_t newton_capped;/* DZ2019-HW Newton solves stopped by the iteration cap               */
+    uint64_t slow_path;    /* SCREEN kernel: candidate evaluations (diagnostic)                  */
+    uint64_t h2d_bytes;    /* bytes copied host->device by the last run                          */
+    int kernel;            /* HVB200_KERNEL_* actually used                                      */
+} hvb200_stats;
+
+MOOCORE_API const char *hvb200_last_error(void);
+MOOCORE_API int hvb200_device_count(void);
+MOOCORE_API const char *hvb200_version(void);
+
+/* transform_and_filter (c/hvapprox.c:30-66) + upload.  *plan_out is NULL (and 0 is returned)
+ * when no point strictly dominates ref — the caller then reports 0.0 like c/hvapprox.c:228. */
+MOOCORE_API int hvb200_plan_create(hvb200_plan **plan_out, const double *data, size_t npoints,
+                                   dimension_t nobjs, const double *ref, const boolvec *maximise,
+                                   int device);
+MOOCORE_API void hvb200_plan_destroy(hvb200_plan *plan);
+MOOCORE_API size_t hvb200_plan_npoints(const hvb200_plan *plan);
+MOOCORE_API int hvb200_plan_set_kernel(hvb200_plan *plan, int kernel);
+
+/* Sum over samples i in [i0, i1) of (max_p min_k p'_k r^(i)_k)^d for the direction set of
+ * `method` with `nsamples` directions in total, as a double-double (hi, lo).  `cuda_stream`
+ * is a cudaStream_t (NULL = the plan's own stream).  Synchronous: returns when the result is
+ * on the host. */
+MOOCORE_API int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint32_t seed,
+                                uint64_t i0, uint64_t i1, void *cuda_stream, double out_hilo[2]);
+MOOCORE_API int hvb200_plan_last_stats(const hvb200_plan *plan, hvb200_stats *out);
+
+/* (double)(c_d * (sum / (long double)nsamples)), c/hvapprox.c:256-257,691-692,863-864; the
+ * `npairs` (hi, lo) partial sums are added in index order in long double. */
+MOOCORE_API double hvb200_finalize(dimension_t nobjs, uint_fast32_t nsamples,
+                                   const double *hilo_pairs, int npairs);
+
+/* Parity/debug: per-sample values s_i^d for i in [i0, i0+count) copied to host memory. */
+MOOCORE_API int hvb200_plan_sample_values(hvb200_plan *plan, int method, uint_fast32_t nsamples,
+                                          uint32_t seed, uint64_t i0, uint64_t count, double *values_out);
+/* Parity/debug: the reciprocal directions r^(i) (count x nobjs, row-major) as generated on
+ * the device for method/nsamples/seed. */
+MOOCORE_API int hvb200_directions(int method, dimension_t nobjs, uint_fast32_t nsamples, uint32_t seed,
+                                  uint64_t i0, uint64_t count, double *r_out, int device);
+/* Max-min over caller-supplied reciprocal directions (count x nobjs, host memory):
+ * values_out (optional) gets s_i^d, out_hilo (optional) the sum. */
+MOOCORE_API int hvb200_plan_run_directions(hvb200_plan *plan, const double *r_host, uint64_t count,
+                                           double *values_out, double out_hilo[2]);
+
+/* Single-process multi-GPU: evaluate one estimate sharded over `ndevices` GPUs
+ * (devices 0..ndevices-1, contiguous index ranges, partial sums combined with one NCCL
+ * all-gather when libnccl can be loaded, else by per-device copies). */
+MOOCORE_API double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, dimension_t nobjs,
+                                          const double *ref, const boolvec *maximise,
+                                          uint_fast32_t nsamples, uint32_t seed, int ndevices);
+
+/* FP64 pipe micro-benchmark used for the roofline denominator: returns measured DFMA
+ * FLOP/s (2 flops per DFMA) of `device`, or a negative number on failure. */
+MOOCORE_API double hvb200_measure_fp64_flops(int device, double *dmul_per_s, double *dsetp_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,337 @@
+"""ctypes binding of libmoocore_b200.so and the Python surface on top of it."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Any, Literal, Sequence
+
+import numpy as np
+
+HVAPPROX_DIMENSION_MAX = 31  # MOOCORE_HVAPPROX_DIMENSION_MAX, c/config.h:28
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBNAME = "libmoocore_b200.so"
+
+METHOD_IDS = {"DZ2019-MC": 1, "DZ2019-HW": 2, "Rphi-FWE+": 3}
+KERNEL_IDS = {"auto": 0, "exact": 1, "screen": 2}
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+
+
+class Stats(ctypes.Structure):
+    """struct hvb200_stats (include/hvapprox_b200.h)."""
+
+    _fields_ = [
+        ("maxmin_ms", ctypes.c_double),
+        ("dirgen_ms", ctypes.c_double),
+        ("reduce_ms", ctypes.c_double),
+        ("h2d_ms", ctypes.c_double),
+        ("maxmin_launches", ctypes.c_uint64),
+        ("dirgen_launches", ctypes.c_uint64),
+        ("reduce_launches", ctypes.c_uint64),
+        ("samples", ctypes.c_uint64),
+        ("npoints", ctypes.c_uint64),
+        ("newton_capped", ctypes.c_uint64),
+        ("slow_path", ctypes.c_uint64),
+        ("h2d_bytes", ctypes.c_uint64),
+        ("kernel", ctypes.c_int),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, _LIBNAME)
+
+
+_lib = None
+
+
+def _load() -> ctypes.CDLL:
+    """Load the native library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C moocore_b200/csrc`. moocore_b200 has no CPU fallback."
+        )
+    L = ctypes.CDLL(path)
+    dim_t, size_t, u64, u32 = ctypes.c_uint8, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32
+    vp = ctypes.c_void_p
+    common = [_c_double_p, size_t, dim_t, _c_double_p, _c_u8_p, u64]
+    L.hv_approx_normal.restype = ctypes.c_double
+    L.hv_approx_normal.argtypes = common + [u32]
+    L.hv_approx_hua_wang.restype = ctypes.c_double
+    L.hv_approx_hua_wang.argtypes = common
+    L.hv_approx_rphi_fang_wang_plus.restype = ctypes.c_double
+    L.hv_approx_rphi_fang_wang_plus.argtypes = common
+    L.hvb200_last_error.restype = ctypes.c_char_p
+    L.hvb200_version.restype = ctypes.c_char_p
+    L.hvb200_device_count.restype = ctypes.c_int
+    L.hvb200_plan_create.restype = ctypes.c_int
+    L.hvb200_plan_create.argtypes = [ctypes.POINTER(vp), _c_double_p, size_t, dim_t, _c_double_p, _c_u8_p, ctypes.c_int]
+    L.hvb200_plan_destroy.restype = None
+    L.hvb200_plan_destroy.argtypes = [vp]
+    L.hvb200_plan_npoints.restype = size_t
+    L.hvb200_plan_npoints.argtypes = [vp]
+    L.hvb200_plan_set_kernel.restype = ctypes.c_int
+    L.hvb200_plan_set_kernel.argtypes = [vp, ctypes.c_int]
+    L.hvb200_plan_run.restype = ctypes.c_int
+    L.hvb200_plan_run.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, vp, _c_double_p]
+    L.hvb200_plan_last_stats.restype = ctypes.c_int
+    L.hvb200_plan_last_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.hvb200_finalize.restype = ctypes.c_double
+    L.hvb200_finalize.argtypes = [dim_t, u64, _c_double_p, ctypes.c_int]
+    L.hvb200_plan_sample_values.restype = ctypes.c_int
+    L.hvb200_plan_sample_values.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, _c_double_p]
+    L.hvb200_directions.restype = ctypes.c_int
+    L.hvb200_directions.argtypes = [ctypes.c_int, dim_t, u64, u32, u64, u64, _c_double_p, ctypes.c_int]
+    L.hvb200_plan_run_directions.restype = ctypes.c_int
+    L.hvb200_plan_run_directions.argtypes = [vp, _c_double_p, u64, _c_double_p, _c_double_p]
+    L.hvb200_hv_approx_multi.restype = ctypes.c_double
+    L.hvb200_hv_approx_multi.argtypes = [ctypes.c_int, _c_double_p, size_t, dim_t, _c_double_p, _c_u8_p, u64, u32, ctypes.c_int]
+    L.hvb200_measure_fp64_flops.restype = ctypes.c_double
+    L.hvb200_measure_fp64_flops.argtypes = [ctypes.c_int, _c_double_p, _c_double_p]
+    _lib = L
+    return L
+
+
+class _LazyLib:
+    def __getattr__(self, name):
+        return getattr(_load(), name)
+
+
+lib = _LazyLib()
+
+
+def device_count() -> int:
+    return int(_load().hvb200_device_count())
+
+
+def _last_error() -> str:
+    return (_load().hvb200_last_error() or b"").decode("utf-8", "replace")
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_c_double_p)
+
+
+# ---- argument handling: same rules and messages as python/src/moocore/_utils.py ------------
+def _array_1d_of_length_n(x: Any, n: int, name: str = "x") -> np.ndarray:
+    """_utils.py:64-72."""
+    x = np.ravel(x)
+    if len(x) == 1:
+        return np.full((n), x[0])
+    if x.shape[0] == n:
+        return x
+    raise ValueError(f"{name!r} must have length {n}, but it has length {x.shape[0]}")
+
+
+def _is_integer_value(n: Any) -> bool:
+    """_utils.py:75-86."""
+    if isinstance(n, (int, np.integer)):
+        return True
+    if n is None:
+        return False
+    try:
+        return int(n) == n
+    except (ValueError, TypeError):
+        return False
+
+
+def _get_seed_for_c(seed: Any) -> int:
+    """_utils.py:89-92: int -> as is; None / Generator -> draw from default_rng."""
+    if not _is_integer_value(seed):
+        seed = np.random.default_rng(seed).integers(2**32 - 2, dtype=np.uint32)
+    return int(seed)
+
+
+def _prepare(points, ref, maximise, nsamples, allow_extension=False):
+    points = np.asarray(points, dtype=float)
+    if points.ndim != 2:
+        raise ValueError("input points must be a 2-D array")
+    nobj = points.shape[1]
+    if nobj == 0:
+        raise ValueError("input points must have at least 1 column")
+    max_dim = 64 if allow_extension else HVAPPROX_DIMENSION_MAX
+    if nobj > max_dim:
+        raise ValueError(f"This function supports at most {max_dim} columns, but input has {nobj}")
+    ref = np.ascontiguousarray(_array_1d_of_length_n(np.asarray(ref, dtype=float), nobj, name="ref"), dtype=float)
+    if not _is_integer_value(nsamples) or nsamples <= 0 or nsamples > 2147483648:
+        raise ValueError(f"nsamples ({nsamples}) must be a positive integer value smaller than 2147483648")
+    maxi = np.ascontiguousarray(_array_1d_of_length_n(maximise, nobj, name="maximise").astype(bool)).view(np.uint8)
+    points = np.ascontiguousarray(points)
+    return points, ref, maxi, int(nsamples), nobj
+
+
+def _exact_hv_1d(points: np.ndarray, ref: np.ndarray, maximise: np.ndarray) -> float:
+    """nobj == 1: the reference returns hypervolume() (_moocore.py:1139-1141); in 1-D that is the
+    distance from ref to the best point (0 if none dominates ref)."""
+    x = points[:, 0]
+    if x.size == 0:
+        return 0.0
+    v = (x.max() - ref[0]) if maximise[0] else (ref[0] - x.min())
+    return float(max(v, 0.0))
+
+
+def hv_approx(
+    points,
+    /,
+    ref,
+    *,
+    maximise: bool | Sequence[bool] = False,
+    nsamples: int = 262_144,
+    seed: int | np.random.Generator | None = None,
+    method: Literal["DZ2019-HW", "DZ2019-MC", "Rphi-FWE+"] = "Rphi-FWE+",
+) -> float:
+    """Approximate the hypervolume indicator (drop-in for ``moocore.hv_approx``).
+
+    Same contract as python/src/moocore/_moocore.py:991-1177: ``points`` is (n, m) float,
+    ``ref`` a scalar or length-m vector, ``maximise`` a bool or length-m bools, ``nsamples`` a
+    positive integer value <= 2**31, ``seed`` only used by ``"DZ2019-MC"``.  Returns ``0.0`` when
+    no point strictly dominates ``ref``.  Raises ``ValueError`` for a non-integer ``nsamples``,
+    an unknown ``method``, a wrong-length ``ref`` or more than 31 columns, like the reference.
+    Raises ``RuntimeError`` if the CUDA path fails (the C entry point returned NaN).
+    """
+    if method not in METHOD_IDS:
+        # validated up front; the reference raises the same error from its match statement
+        pts = np.asarray(points, dtype=float)
+        if pts.ndim == 2 and pts.shape[1] >= 2:
+            _prepare(points, ref, maximise, nsamples)
+        raise ValueError(f"Unknown method = {method}")
+    points, ref, maxi, nsamples, nobj = _prepare(points, ref, maximise, nsamples)
+    if nobj == 1:
+        return _exact_hv_1d(points, ref, maxi)
+    L = _load()
+    args = (_dp(points), points.shape[0], nobj, _dp(ref), maxi.ctypes.data_as(_c_u8_p), nsamples)
+    if method == "DZ2019-MC":
+        hv = L.hv_approx_normal(*args, _get_seed_for_c(seed))
+    elif method == "DZ2019-HW":
+        hv = L.hv_approx_hua_wang(*args)
+    else:
+        hv = L.hv_approx_rphi_fang_wang_plus(*args)
+    if hv != hv:
+        raise RuntimeError(f"moocore_b200: CUDA hv_approx failed: {_last_error()}")
+    return float(hv)
+
+
+class Plan:
+    """A point set transformed, filtered and resident on one GPU (hvb200_plan)."""
+
+    def __init__(self, points, ref, maximise=False, device: int = 0, kernel: str = "auto", allow_extension: bool = False):
+        points, ref, maxi, _, nobj = _prepare(points, ref, maximise, 1, allow_extension)
+        if nobj < 2:
+            raise ValueError("Plan needs at least 2 objectives")
+        L = _load()
+        h = ctypes.c_void_p()
+        rc = L.hvb200_plan_create(ctypes.byref(h), _dp(points), points.shape[0], nobj, _dp(ref),
+                                  maxi.ctypes.data_as(_c_u8_p), device)
+        if rc != 0:
+            raise RuntimeError(f"hvb200_plan_create failed ({rc}): {_last_error()}")
+        self._h = h if h.value else None
+        self.nobj = nobj
+        self.device = device
+        if self._h is not None and kernel != "auto":
+            self.set_kernel(kernel)
+
+    @property
+    def empty(self) -> bool:
+        """True when no point strictly dominates ref (hv_approx is then 0)."""
+        return self._h is None
+
+    @property
+    def npoints(self) -> int:
+        return 0 if self._h is None else int(_load().hvb200_plan_npoints(self._h))
+
+    def set_kernel(self, kernel: str) -> None:
+        if _load().hvb200_plan_set_kernel(self._h, KERNEL_IDS[kernel]) != 0:
+            raise RuntimeError(_last_error())
+
+    def run(self, method: str, nsamples: int, seed: int = 0, i0: int = 0, i1: int | None = None, stream: int | None = None):
+        """Partial sum over samples [i0, i1) as a (hi, lo) pair."""
+        if self._h is None:
+            return (0.0, 0.0)
+        i1 = nsamples if i1 is None else i1
+        out = (ctypes.c_double * 2)()
+        rc = _load().hvb200_plan_run(self._h, METHOD_IDS[method], nsamples, seed, i0, i1,
+                                     ctypes.c_void_p(stream) if stream else None, out)
+        if rc != 0:
+            raise RuntimeError(f"hvb200_plan_run failed ({rc}): {_last_error()}")
+        return (out[0], out[1])
+
+    def stats(self) -> dict:
+        s = Stats()
+        if self._h is not None:
+            _load().hvb200_plan_last_stats(self._h, ctypes.byref(s))
+        return s.as_dict()
+
+    def sample_values(self, method: str, nsamples: int, seed: int = 0, i0: int = 0, count: int | None = None) -> np.ndarray:
+        count = nsamples - i0 if count is None else count
+        out = np.zeros(count, dtype=np.float64)
+        if self._h is None:
+            return out
+        rc = _load().hvb200_plan_sample_values(self._h, METHOD_IDS[method], nsamples, seed, i0, count, _dp(out))
+        if rc != 0:
+            raise RuntimeError(f"hvb200_plan_sample_values failed ({rc}): {_last_error()}")
+        return out
+
+    def run_directions(self, r: np.ndarray, want_values: bool = True):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        assert r.ndim == 2 and r.shape[1] == self.nobj
+        vals = np.zeros(r.shape[0], dtype=np.float64) if want_values else None
+        out = (ctypes.c_double * 2)()
+        rc = _load().hvb200_plan_run_directions(self._h, _dp(r), r.shape[0], _dp(vals) if want_values else None, out)
+        if rc != 0:
+            raise RuntimeError(f"hvb200_plan_run_directions failed ({rc}): {_last_error()}")
+        return vals, (out[0], out[1])
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            _load().hvb200_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def directions(method: str, nobj: int, nsamples: int, seed: int = 0, i0: int = 0, count: int | None = None, device: int = 0) -> np.ndarray:
+    """Reciprocal directions r^(i) generated on the device (parity/debug)."""
+    count = nsamples - i0 if count is None else count
+    out = np.zeros((count, nobj), dtype=np.float64)
+    rc = _load().hvb200_directions(METHOD_IDS[method], nobj, nsamples, seed, i0, count, _dp(out), device)
+    if rc != 0:
+        raise RuntimeError(f"hvb200_directions failed ({rc}): {_last_error()}")
+    return out
+
+
+def hv_approx_range(points, ref, *, maximise=False, nsamples: int, seed: int = 0, method: str, i0: int, i1: int,
+                    device: int = 0, stream: int | None = None):
+    """One shard of an estimate: the (hi, lo) partial sum over samples [i0, i1) on `device`."""
+    with Plan(points, ref, maximise, device=device) as plan:
+        return plan.run(method, nsamples, seed, i0, i1, stream)
+
+
+def hv_approx_finalize(nobj: int, nsamples: int, partials) -> float:
+    """c_d * (sum of partials) / nsamples in long double (c/hvapprox.c:691-692)."""
+    flat = np.ascontiguousarray(np.asarray(partials, dtype=np.float64).reshape(-1))
+    return float(_load().hvb200_finalize(nobj, nsamples, _dp(flat), flat.size // 2))
+
+
+def measure_fp64(device: int = 0) -> dict:
+    dmul, dsetp = ctypes.c_double(), ctypes.c_double()
+    flops = _load().hvb200_measure_fp64_flops(device, ctypes.byref(dmul), ctypes.byref(dsetp))
+    return {"dfma_flops": flops, "dmul_per_s": dmul.value, "dsetp_per_s": dsetp.value}

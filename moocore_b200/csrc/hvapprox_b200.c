@@ -1,0 +1,453 @@
+/* hvapprox_b200.c — host side (C99) of the B200 hv_approx path.
+ *
+ * Exports the three entry points of moocore's c/hvapprox.h:16-38 plus the extended API of
+ * include/hvapprox_b200.h.  This file does what c/hvapprox.c does on the host outside its hot
+ * loop — transform_and_filter (:30-66), construct_polar_a (:261-286), the final long double
+ * scaling (:256-257, 691-692, 863-864) — and produces the two inherently sequential input
+ * streams (MT19937+ziggurat normals for DZ2019-MC, the rounded Rphi recurrence) that are then
+ * uploaded; every per-sample x per-point operation runs in the CUDA kernels of
+ * hvb200_kernels.cu.  There is no CPU implementation of the max-min path here: if CUDA is not
+ * usable the entry points report the error and return NaN.
+ *
+ * All file:line citations are relative to /root/reference.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hvb200_tables.h"
+#include "hvb200_internal.h"
+
+#define TINY_WEIGHT 1e-20 /* ALMOST_ZERO_WEIGHT, c/hvapprox.c:9 */
+
+/* ------------------------------------------------------------------------------------------ */
+/* errors                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+static __thread char tls_error[512];
+
+void hvb200_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tls_error, sizeof tls_error, fmt, ap);
+    va_end(ap);
+}
+const char *hvb200_last_error(void) { return tls_error; }
+const char *hvb200_version(void) { return "moocore_b200 0.1 (hv_approx path of moocore 0.20, sm_100a)"; }
+int hvb200_device_count(void) { return hvb200cu_device_count(); }
+
+static double fail_nan(const char *where)
+{
+    fprintf(stderr, "moocore_b200: %s: %s\n", where, tls_error[0] ? tls_error : "unknown error");
+    return NAN;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* transform_and_filter (c/hvapprox.c:30-66)                                                  */
+/* ------------------------------------------------------------------------------------------ */
+static size_t transform_and_filter(const double *data, size_t n, int d, const double *ref,
+                                   const boolvec *maximise, double *out)
+{
+    size_t kept = 0;
+    for (size_t i = 0; i < n; i++) {
+        const double *src = data + i * (size_t)d;
+        double *dst = out + kept * (size_t)d;
+        int k;
+        for (k = 0; k < d; k++) {
+            const double v = maximise[k] ? src[k] - ref[k] : ref[k] - src[k];
+            if (!(v > 0)) break;          /* v <= 0 (or NaN) : does not strictly dominate ref */
+            dst[k] = v;
+        }
+        kept += (k == d);
+    }
+    return kept;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* plans                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+int hvb200_plan_create(hvb200_plan **plan_out, const double *data, size_t npoints, dimension_t nobjs,
+                       const double *ref, const boolvec *maximise, int device)
+{
+    *plan_out = NULL;
+    tls_error[0] = 0;
+    const int d = (int)nobjs;
+    if (d < 2 || d > HVB200_DIMENSION_MAX) {
+        hvb200_set_error("nobjs = %d outside [2, %d]", d, HVB200_DIMENSION_MAX);
+        return -2;
+    }
+    if (device < 0 || device >= hvb200cu_device_count()) {
+        hvb200_set_error("CUDA device %d not available (%d visible); this library has no CPU fallback",
+                         device, hvb200cu_device_count());
+        return -3;
+    }
+    double *pts = malloc((npoints ? npoints : 1) * (size_t)d * sizeof *pts);
+    if (!pts) { hvb200_set_error("out of host memory"); return -4; }
+    const size_t n = transform_and_filter(data, npoints, d, ref, maximise, pts);
+    if (n == 0) { free(pts); return 0; }         /* caller returns 0.0, c/hvapprox.c:228-229 */
+    hvb200_plan *plan = calloc(1, sizeof *plan);
+    if (!plan) { free(pts); hvb200_set_error("out of host memory"); return -4; }
+    plan->device = device;
+    plan->d = d;
+    plan->n = n;
+    plan->kernel = HVB200_KERNEL_AUTO;
+    const char *env = getenv("HVB200_KERNEL");
+    if (env && !strcmp(env, "exact")) plan->kernel = HVB200_KERNEL_EXACT;
+    if (env && !strcmp(env, "screen")) plan->kernel = HVB200_KERNEL_SCREEN;
+    const int rc = hvb200cu_plan_upload(plan, pts);
+    free(pts);
+    if (rc) { hvb200cu_plan_free(plan); free(plan); return -1; }
+    *plan_out = plan;
+    return 0;
+}
+void hvb200_plan_destroy(hvb200_plan *plan)
+{
+    if (!plan) return;
+    hvb200cu_plan_free(plan);
+    free(plan);
+}
+size_t hvb200_plan_npoints(const hvb200_plan *plan) { return plan ? plan->n : 0; }
+int hvb200_plan_set_kernel(hvb200_plan *plan, int kernel)
+{
+    if (kernel < HVB200_KERNEL_AUTO || kernel > HVB200_KERNEL_SCREEN) { hvb200_set_error("bad kernel id %d", kernel); return -2; }
+    plan->kernel = kernel;
+    return 0;
+}
+int hvb200_plan_last_stats(const hvb200_plan *plan, hvb200_stats *out)
+{
+    *out = plan->stats;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* DZ2019-HW host part: construct_polar_a (c/hvapprox.c:261-286)                              */
+/* ------------------------------------------------------------------------------------------ */
+static int lattice_prime(int ldim)
+{   /* smallest prime p with (p-1)/2 >= ldim; the reference tabulates it (:266-270) */
+    for (int p = 3;; p += 2) {
+        int prime = 1;
+        for (int q = 3; q * q <= p; q += 2) if (p % q == 0) { prime = 0; break; }
+        if (prime && (p - 1) / 2 >= ldim) return p;
+    }
+}
+static void hw_params_init(hvb200_hw_params *hw, int d, uint64_t nsamples)
+{
+    static const long double PI_L = 3.141592653589793238462643383279502884L;
+    memset(hw, 0, sizeof *hw);
+    hw->d = d;
+    hw->nsamples = nsamples;
+    const int ldim = d - 1;
+    const int p = lattice_prime(ldim);
+    hw->a[0] = 1;
+    for (int k = 1; k < ldim; k++) {
+        long double t = fabsl(2 * cosl(2 * PI_L * k / p));
+        t -= truncl(t);
+        hw->a[k] = (uint64_t)llroundl(nsamples * t);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* DZ2019-MC host part: the NumPy-legacy MT19937 stream + 256-layer ziggurat                   */
+/* (c/mt19937/mt19937.c:6-55, c/mt19937/mt19937.h:28-57, c/rng.c:71-99)                        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { uint32_t x[624]; int pos; } mt_stream;
+
+static void mt_seed(mt_stream *s, uint32_t seed)
+{
+    for (int i = 0; i < 624; i++) {
+        s->x[i] = seed;
+        seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)i + 1u;
+    }
+    s->pos = 624;
+}
+static void mt_twist(mt_stream *s)
+{
+    uint32_t *x = s->x;
+    int i;
+    for (i = 0; i < 624 - 397; i++) {
+        const uint32_t y = (x[i] & 0x80000000u) | (x[i + 1] & 0x7fffffffu);
+        x[i] = x[i + 397] ^ (y >> 1) ^ (-(y & 1u) & 0x9908b0dfu);
+    }
+    for (; i < 623; i++) {
+        const uint32_t y = (x[i] & 0x80000000u) | (x[i + 1] & 0x7fffffffu);
+        x[i] = x[i - 227] ^ (y >> 1) ^ (-(y & 1u) & 0x9908b0dfu);
+    }
+    const uint32_t y = (x[623] & 0x80000000u) | (x[0] & 0x7fffffffu);
+    x[623] = x[396] ^ (y >> 1) ^ (-(y & 1u) & 0x9908b0dfu);
+    s->pos = 0;
+}
+static inline uint32_t mt_u32(mt_stream *s)
+{
+    if (s->pos == 624) mt_twist(s);
+    uint32_t y = s->x[s->pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+static inline uint64_t mt_u64(mt_stream *s) { const uint64_t hi = mt_u32(s); return hi << 32 | mt_u32(s); }
+static inline double mt_unit(mt_stream *s)
+{
+    const int32_t a = (int32_t)(mt_u32(s) >> 5), b = (int32_t)(mt_u32(s) >> 6);
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+static inline double from_bits(uint64_t b) { double v; memcpy(&v, &b, sizeof v); return v; }
+
+static double zig_normal(mt_stream *s)
+{
+    const double R = from_bits(HVB200_ZIG_R_BITS), INV_R = from_bits(HVB200_ZIG_INV_R_BITS);
+    for (;;) {
+        const uint64_t r = mt_u64(s);
+        const int layer = (int)(r & 0xff);
+        const uint64_t mag = (r >> 9) & 0x000fffffffffffffull;
+        double x = (double)mag * from_bits(hvb200_zig_wi_bits[layer]);
+        if ((r >> 8) & 1) x = -x;
+        if (mag < hvb200_zig_ki[layer]) return x;          /* ~99.3 % */
+        if (layer == 0) {                                    /* tail */
+            for (;;) {
+                const double xx = -INV_R * log1p(-mt_unit(s));
+                const double yy = -log1p(-mt_unit(s));
+                if (yy + yy > xx * xx) return ((mag >> 8) & 1) ? -(R + xx) : R + xx;
+            }
+        } else {                                             /* wedge */
+            const double f_hi = from_bits(hvb200_zig_fi_bits[layer - 1]), f_lo = from_bits(hvb200_zig_fi_bits[layer]);
+            if ((f_hi - f_lo) * mt_unit(s) + f_lo < exp(-0.5 * x * x)) return x;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Rphi-FWE+ host part: Rphi_init / Rphi_next (c/hvapprox.c:695-747) in native long double     */
+/* ------------------------------------------------------------------------------------------ */
+static void rphi_alpha(long double *alpha, int ldim)
+{
+    alpha[0] = hvb200_rho[ldim];
+    for (int k = 1; k < ldim; k++) alpha[k] = alpha[k - 1] * hvb200_rho[ldim];
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* run                                                                                         */
+/* ------------------------------------------------------------------------------------------ */
+static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t seed, uint64_t i0, uint64_t i1,
+                     void *stream, double out_hilo[2], double *values_out, double *dirs_out)
+{
+    const int d = plan->d;
+    tls_error[0] = 0;
+    if (i1 < i0 || i1 > nsamples) { hvb200_set_error("bad sample range [%llu, %llu) of %llu",
+                                                     (unsigned long long)i0, (unsigned long long)i1, (unsigned long long)nsamples); return -2; }
+    if (method == HVB200_METHOD_HW && d > MOOCORE_HVAPPROX_DIMENSION_MAX + 1) {
+        hvb200_set_error("DZ2019-HW supports at most %d objectives", MOOCORE_HVAPPROX_DIMENSION_MAX + 1);
+        return -2;
+    }
+    uint64_t batch = 0;
+    uint64_t want = i1 - i0 ? i1 - i0 : 1;
+    if ((values_out || dirs_out) && want > (1u << 22)) want = 1u << 22;
+    if (method != HVB200_METHOD_HW && want > (1u << 20)) want = 1u << 20;     /* host-fed streams: 1 Mi samples per upload */
+    if (hvb200cu_run_begin(plan, stream, want, &batch)) return -1;
+
+    hvb200_hw_params hw;
+    mt_stream mt;
+    long double alpha[HVB200_MAXD];
+    double u[HVB200_MAXD];
+    if (method == HVB200_METHOD_HW) {
+        hw_params_init(&hw, d, nsamples);
+    } else if (method == HVB200_METHOD_MC) {
+        mt_seed(&mt, seed);
+        /* the stream is sequential: skip the normals of samples [0, i0) */
+        for (uint64_t j = 0; j < i0; j++) for (int k = 0; k < d; k++) (void)zig_normal(&mt);
+    } else if (method == HVB200_METHOD_RPHI) {
+        rphi_alpha(alpha, d - 1);
+        for (int k = 0; k < d - 1; k++) u[k] = 0.5;
+        for (uint64_t j = 0; j < i0; j++)
+            for (int k = 0; k < d - 1; k++) { const long double v = u[k] + alpha[k]; u[k] = (double)(v - truncl(v)); }
+    } else {
+        hvb200_set_error("unknown method %d", method);
+        return -2;
+    }
+
+    for (uint64_t b0 = i0; b0 < i1; b0 += batch) {
+        const uint64_t cnt = (i1 - b0 < batch) ? i1 - b0 : batch;
+        if (method == HVB200_METHOD_HW) {
+            if (hvb200cu_gen_hw(plan, &hw, b0, cnt)) return -1;
+        } else if (method == HVB200_METHOD_MC) {
+            double *z = hvb200cu_staging(plan, cnt * (size_t)d);
+            if (!z) return -1;
+            for (uint64_t j = 0; j < cnt * (uint64_t)d; j++) z[j] = zig_normal(&mt);
+            if (hvb200cu_gen_mc(plan, z, cnt)) return -1;
+        } else {
+            double *uu = hvb200cu_staging(plan, cnt * (size_t)(d - 1));
+            if (!uu) return -1;
+            for (uint64_t j = 0; j < cnt; j++)
+                for (int k = 0; k < d - 1; k++) {
+                    const long double v = u[k] + alpha[k];
+                    u[k] = (double)(v - truncl(v));
+                    uu[j * (size_t)(d - 1) + k] = u[k];
+                }
+            if (hvb200cu_gen_rphi(plan, uu, cnt)) return -1;
+        }
+        if (dirs_out && hvb200cu_read_dirs(plan, cnt, dirs_out + (b0 - i0) * (size_t)d)) return -1;
+        if (!dirs_out || values_out || out_hilo)
+            if (plan->n && hvb200cu_maxmin(plan, cnt, values_out ? values_out + (b0 - i0) : NULL)) return -1;
+    }
+    if (hvb200cu_run_end(plan, out_hilo)) return -1;
+    plan->stats.samples = i1 - i0;
+    return 0;
+}
+
+int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint32_t seed,
+                    uint64_t i0, uint64_t i1, void *cuda_stream, double out_hilo[2])
+{
+    return run_range(plan, method, (uint64_t)nsamples, seed, i0, i1, cuda_stream, out_hilo, NULL, NULL);
+}
+int hvb200_plan_sample_values(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint32_t seed,
+                              uint64_t i0, uint64_t count, double *values_out)
+{
+    double hilo[2];
+    return run_range(plan, method, (uint64_t)nsamples, seed, i0, i0 + count, NULL, hilo, values_out, NULL);
+}
+int hvb200_directions(int method, dimension_t nobjs, uint_fast32_t nsamples, uint32_t seed,
+                      uint64_t i0, uint64_t count, double *r_out, int device)
+{
+    /* a one-point plan just to own the device buffers */
+    const int d = (int)nobjs;
+    double one[HVB200_MAXD], ref[HVB200_MAXD];
+    boolvec mx[HVB200_MAXD];
+    if (d < 2 || d > HVB200_DIMENSION_MAX) { hvb200_set_error("nobjs = %d outside [2, %d]", d, HVB200_DIMENSION_MAX); return -2; }
+    for (int k = 0; k < d; k++) { one[k] = 0.0; ref[k] = 1.0; mx[k] = 0; }
+    hvb200_plan *plan = NULL;
+    int rc = hvb200_plan_create(&plan, one, 1, nobjs, ref, mx, device);
+    if (rc || !plan) return rc ? rc : -1;
+    rc = run_range(plan, method, (uint64_t)nsamples, seed, i0, i0 + count, NULL, NULL, NULL, r_out);
+    hvb200_plan_destroy(plan);
+    return rc;
+}
+int hvb200_plan_run_directions(hvb200_plan *plan, const double *r_host, uint64_t count,
+                               double *values_out, double out_hilo[2])
+{
+    tls_error[0] = 0;
+    uint64_t batch = 0;
+    uint64_t want = count ? count : 1;
+    if (want > (1u << 20)) want = 1u << 20;
+    if (hvb200cu_run_begin(plan, NULL, want, &batch)) return -1;
+    for (uint64_t b0 = 0; b0 < count; b0 += batch) {
+        const uint64_t cnt = (count - b0 < batch) ? count - b0 : batch;
+        if (hvb200cu_gen_uploaded(plan, r_host + b0 * (size_t)plan->d, cnt)) return -1;
+        if (hvb200cu_maxmin(plan, cnt, values_out ? values_out + b0 : NULL)) return -1;
+    }
+    if (hvb200cu_run_end(plan, out_hilo)) return -1;
+    plan->stats.samples = count;
+    return 0;
+}
+
+/* (double)(c_d * (sum / (long double)N)) — c/hvapprox.c:256-257, 691-692, 863-864 */
+double hvb200_finalize(dimension_t nobjs, uint_fast32_t nsamples, const double *hilo_pairs, int npairs)
+{
+    long double sum = 0.0L;
+    for (int i = 0; i < npairs; i++) sum += (long double)hilo_pairs[2 * i] + (long double)hilo_pairs[2 * i + 1];
+    const long double c_d = hvb200_cd[(int)nobjs];
+    return (double)(c_d * (sum / (long double)nsamples));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* single-process multi-GPU                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int method, device, rc;
+    const double *data; size_t npoints; dimension_t nobjs; const double *ref; const boolvec *maximise;
+    uint64_t nsamples, i0, i1; uint32_t seed;
+    double hilo[2];
+    int empty;
+    char err[512];
+} shard_job;
+
+static void *shard_main(void *arg)
+{
+    shard_job *j = arg;
+    hvb200_plan *plan = NULL;
+    j->hilo[0] = j->hilo[1] = 0.0;
+    j->rc = hvb200_plan_create(&plan, j->data, j->npoints, j->nobjs, j->ref, j->maximise, j->device);
+    if (j->rc == 0 && !plan) { j->empty = 1; return NULL; }
+    if (j->rc == 0) j->rc = hvb200_plan_run(plan, j->method, j->nsamples, j->seed, j->i0, j->i1, NULL, j->hilo);
+    if (j->rc) snprintf(j->err, sizeof j->err, "%s", tls_error);
+    hvb200_plan_destroy(plan);
+    return NULL;
+}
+
+double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, dimension_t nobjs,
+                              const double *ref, const boolvec *maximise,
+                              uint_fast32_t nsamples, uint32_t seed, int ndevices)
+{
+    tls_error[0] = 0;
+    const int avail = hvb200cu_device_count();
+    if (avail < 1) { hvb200_set_error("no CUDA device visible; this library has no CPU fallback"); return fail_nan("hv_approx"); }
+    if (ndevices < 1) ndevices = 1;
+    if (ndevices > avail) ndevices = avail;
+    if (ndevices > 16) ndevices = 16;
+    if ((uint64_t)ndevices > (uint64_t)nsamples) ndevices = 1;
+    shard_job jobs[16];
+    pthread_t th[16];
+    memset(jobs, 0, sizeof jobs);
+    for (int g = 0; g < ndevices; g++) {
+        shard_job *j = &jobs[g];
+        j->method = method; j->device = g;
+        j->data = data; j->npoints = npoints; j->nobjs = nobjs; j->ref = ref; j->maximise = maximise;
+        j->nsamples = (uint64_t)nsamples; j->seed = seed;
+        j->i0 = (uint64_t)nsamples * (uint64_t)g / (uint64_t)ndevices;
+        j->i1 = (uint64_t)nsamples * (uint64_t)(g + 1) / (uint64_t)ndevices;
+    }
+    if (ndevices == 1) {
+        shard_main(&jobs[0]);
+    } else {
+        for (int g = 0; g < ndevices; g++) pthread_create(&th[g], NULL, shard_main, &jobs[g]);
+        for (int g = 0; g < ndevices; g++) pthread_join(th[g], NULL);
+    }
+    double pairs[32];
+    for (int g = 0; g < ndevices; g++) {
+        if (jobs[g].rc) { hvb200_set_error("device %d: %s", g, jobs[g].err); return fail_nan("hv_approx"); }
+        if (jobs[g].empty) return 0.0;
+        pairs[2 * g] = jobs[g].hilo[0];
+        pairs[2 * g + 1] = jobs[g].hilo[1];
+    }
+    return hvb200_finalize(nobjs, nsamples, pairs, ndevices);
+}
+
+static int env_ndevices(void)
+{
+    const char *e = getenv("HVB200_NGPUS");
+    if (!e) return 1;
+    const int v = atoi(e);
+    return v < 1 ? 1 : v;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* the drop-in entry points (c/hvapprox.h:16-38)                                               */
+/* ------------------------------------------------------------------------------------------ */
+double hv_approx_normal(const double *restrict data, size_t npoints, dimension_t nobjs,
+                        const double *restrict ref, const boolvec *restrict maximise,
+                        uint_fast32_t nsamples, uint32_t random_seed)
+{
+    return hvb200_hv_approx_multi(HVB200_METHOD_MC, data, npoints, nobjs, ref, maximise, nsamples, random_seed, env_ndevices());
+}
+double hv_approx_hua_wang(const double *restrict data, size_t npoints, dimension_t nobjs,
+                          const double *restrict ref, const boolvec *restrict maximise,
+                          uint_fast32_t nsamples)
+{
+    return hvb200_hv_approx_multi(HVB200_METHOD_HW, data, npoints, nobjs, ref, maximise, nsamples, 0, env_ndevices());
+}
+double hv_approx_rphi_fang_wang_plus(const double *restrict data, size_t npoints, dimension_t nobjs,
+                                     const double *restrict ref, const boolvec *restrict maximise,
+                                     uint_fast32_t nsamples)
+{
+    return hvb200_hv_approx_multi(HVB200_METHOD_RPHI, data, npoints, nobjs, ref, maximise, nsamples, 0, env_ndevices());
+}
+
+double hvb200_measure_fp64_flops(int device, double *dmul_per_s, double *dsetp_per_s)
+{
+    return hvb200cu_measure_fp64(device, dmul_per_s, dsetp_per_s);
+}

@@ -1,0 +1,65 @@
+/* hvb200_internal.h — private interface between the host C layer (hvapprox_b200.c) and the
+ * CUDA translation unit (hvb200_kernels.cu).  Plain C; no CUDA types leak to the C side. */
+#ifndef HVB200_INTERNAL_H_
+#define HVB200_INTERNAL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/hvapprox_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef HVB200_MAXD
+#define HVB200_MAXD HVB200_DIMENSION_MAX
+#endif
+
+/* DZ2019-HW lattice parameters, built on the host (construct_polar_a, c/hvapprox.c:261-286). */
+typedef struct hvb200_hw_params {
+    uint64_t nsamples;                 /* N (<= 2^32 on the device path)          */
+    uint64_t a[HVB200_MAXD];           /* generator vector a[0..d-2]              */
+    int d;
+} hvb200_hw_params;
+
+struct hvb200_plan {
+    int device;
+    int d;                 /* number of objectives                                              */
+    size_t n;              /* n' surviving points                                               */
+    int kernel;            /* requested HVB200_KERNEL_*                                         */
+    /* device side (owned by the CUDA TU) */
+    void *dev;             /* struct dev_plan*                                                  */
+    hvb200_stats stats;
+};
+
+/* error reporting (thread-local buffer lives in the C TU) */
+void hvb200_set_error(const char *fmt, ...);
+
+/* ---- implemented in hvb200_kernels.cu ---- */
+int hvb200cu_device_count(void);
+/* upload n x d transformed points (host, row-major) */
+int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host);
+void hvb200cu_plan_free(struct hvb200_plan *plan);
+
+/* A run = begin, then per batch {generate directions, maxmin}, then end. */
+int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batch, uint64_t *batch_out);
+/* direction producers: fill the plan's direction buffer with `count` samples */
+int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
+int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count);     /* count*d normals */
+int hvb200cu_gen_rphi(struct hvb200_plan *plan, const double *u_host, uint64_t count);         /* count*(d-1) u   */
+int hvb200cu_gen_uploaded(struct hvb200_plan *plan, const double *r_host, uint64_t count);     /* count*d r       */
+/* consume the direction buffer; values_host (optional) receives per-sample s^d */
+int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double *values_host);
+/* copy the generated reciprocal directions of the current batch to the host (count x d) */
+int hvb200cu_read_dirs(struct hvb200_plan *plan, uint64_t count, double *r_host);
+int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2]);
+
+/* pinned staging buffer for host-produced streams (MC normals, Rphi u); grows on demand */
+double *hvb200cu_staging(struct hvb200_plan *plan, size_t ndoubles);
+
+double hvb200cu_measure_fp64(int device, double *dmul_per_s, double *dsetp_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1143 @@
+// hvb200_kernels.cu — sm_100a kernels of the hv_approx hot path and their launchers.
+//
+// Path (reference file:line, relative to /root/reference):
+//   direction generators   c/hvapprox.c:288-304,551-576,610-647 (DZ2019-HW), :239-250 (DZ2019-MC
+//                          post-processing), :791-826 (Rphi-FWE+ mapping)
+//   max-min + s^d          c/hvapprox.c:68-117 (get_expected_value), c/pow_int.h:16-74
+//   sum                    c/hvapprox.c:251,681,857
+//
+// Layout in HBM (per plan = per GPU):
+//   pts   [n_tiles][TP][d] FP64, transformed points p' = |ref - p| > 0, zero-padded to whole tiles
+//   dirs  [batch][2][d]    FP64, per sample the reciprocal direction r and winv = RN(1/r)
+//   chunk/CTA partial sums, one double per CTA; (hi, lo) result pair
+//
+// Kernels:
+//   k_gen_hw      one thread per sample: x87-exact lattice point (integer emulation of the
+//                 reference's long double arithmetic), d-1 Newton solves in FP64, polar->cartesian
+//   k_gen_mc      normals (host MT19937+ziggurat stream) -> |z|, clamp, norm, r = norm/|z|
+//   k_gen_rphi    u (host recurrence) -> Fang-Wang map -> r = 1/w
+//   k_prep_r      uploaded r -> winv
+//   k_maxmin      persistent CTAs; a producer warp streams point tiles into shared memory with
+//                 TMA bulk copies (cp.async.bulk + mbarrier, multi-stage); 256 consumer threads
+//                 own R directions each and sweep every tile.
+//                   EXACT : d DMUL + d min per sample*point, 1 max             (2d+1 FP64 ops)
+//                   SCREEN: per element one DSETP against a per-direction threshold
+//                           T_k < best/r_k (predicate chain); only candidates that may raise the
+//                           running max are evaluated with the EXACT arithmetic.  max/min are
+//                           exact and order-free, so both give bit-identical s.
+//   k_reduce      fixed-shape pairwise tree over CTA partial sums in double-double -> (hi, lo)
+//
+// No tensor cores: max-min is a semiring, not a contraction.  Compiled with -fmad=false so that
+// a*b+c is never contracted where the reference (x86-64, no FMA) rounds twice; fma() is written
+// explicitly where wanted.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+#include "hvb200_tables.h"
+#include "hvb200_internal.h"
+
+typedef unsigned long long ull;
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            hvb200_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),         \
+                             __FILE__, __LINE__);                                            \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------------
+static constexpr int kConsumerThreads = 256;
+static constexpr int kBlockThreads = kConsumerThreads + 32;   // + one producer warp
+static constexpr int kStages = 3;
+static constexpr int kStageBytes = 24 * 1024;
+static constexpr int kNewtonCap = 200;
+static constexpr int kMaxFmTerms = 32;
+
+__constant__ double c_fm_lead[HVB200_MAXD];
+__constant__ double c_fm_h[HVB200_MAXD][kMaxFmTerms];
+__constant__ int c_fm_nh[HVB200_MAXD];
+__constant__ double c_Im[HVB200_MAXD];
+__constant__ ull c_theta0_bits[32];
+
+// x^e multiplication trees: same shapes as c/pow_int.h:22-56 (see oracle/hvapprox_oracle.c for
+// the derivation of the table); step t computes v[t+1] = v[a]*v[b].
+struct PowProg { unsigned char n; unsigned char op[7][2]; };
+static constexpr PowProg kPowProg[32] = {
+    {0, {}}, {0, {}},
+    {1, {{0,0}}},
+    {2, {{0,0},{1,0}}},
+    {2, {{0,0},{1,1}}},
+    {3, {{0,0},{1,1},{2,0}}},
+    {3, {{0,0},{1,1},{2,1}}},
+    {4, {{0,0},{1,1},{2,1},{3,0}}},
+    {3, {{0,0},{1,1},{2,2}}},
+    {4, {{0,0},{1,0},{2,2},{3,2}}},
+    {4, {{0,0},{1,1},{2,2},{3,1}}},
+    {5, {{0,0},{1,1},{2,2},{3,1},{4,0}}},
+    {4, {{0,0},{1,1},{2,2},{3,2}}},
+    {5, {{0,0},{1,1},{2,2},{3,2},{4,0}}},
+    {5, {{0,0},{1,1},{2,2},{3,2},{4,1}}},
+    {5, {{0,0},{1,1},{2,0},{3,3},{4,3}}},
+    {4, {{0,0},{1,1},{2,2},{3,3}}},
+    {5, {{0,0},{1,1},{2,2},{3,3},{4,0}}},
+    {5, {{0,0},{1,0},{2,2},{3,2},{4,4}}},
+    {6, {{0,0},{1,0},{2,2},{3,2},{4,4},{5,0}}},
+    {5, {{0,0},{1,1},{2,2},{3,1},{4,4}}},
+    {6, {{0,0},{1,1},{2,2},{3,1},{4,4},{5,0}}},
+    {6, {{0,0},{1,1},{2,0},{3,3},{4,4},{5,1}}},
+    {6, {{0,0},{1,0},{1,2},{3,3},{4,4},{5,2}}},
+    {5, {{0,0},{1,1},{2,2},{3,2},{4,4}}},
+    {6, {{0,0},{1,1},{2,2},{3,2},{4,4},{5,0}}},
+    {6, {{0,0},{1,1},{2,2},{3,2},{4,0},{5,5}}},
+    {6, {{0,0},{1,0},{2,2},{3,3},{4,4},{5,2}}},
+    {6, {{0,0},{1,1},{2,2},{3,2},{4,1},{5,5}}},
+    {7, {{0,0},{1,1},{2,2},{3,2},{4,1},{5,5},{6,0}}},
+    {6, {{0,0},{1,1},{2,0},{3,3},{4,3},{5,5}}},
+    {7, {{0,0},{1,1},{2,0},{3,3},{4,3},{5,5},{6,0}}},
+};
+
+template <int E>
+__device__ __forceinline__ double pow_chain(double x)
+{
+    if constexpr (E == 0) {
+        return 1.0;
+    } else if constexpr (E <= 31) {
+        constexpr PowProg P = kPowProg[E];
+        double v[8];
+        v[0] = x;
+#pragma unroll
+        for (int t = 0; t < P.n; t++) v[t + 1] = v[P.op[t][0]] * v[P.op[t][1]];
+        return v[P.n];
+    } else {   // generic square-and-multiply, c/pow_int.h:65-73
+        double acc = (E & 1) ? x : 1.0;
+#pragma unroll
+        for (unsigned e = (unsigned)E >> 1; e; e >>= 1) {
+            x *= x;
+            if (e & 1u) acc *= x;
+        }
+        return acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(ull *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(ull *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(ull *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(ull *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, ull *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync()
+{   // named barrier 1 over the consumer threads only (the producer warp never joins)
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: max-min
+// ------------------------------------------------------------------------------------------------
+struct MaxminArgs {
+    const double *pts;       // [n_tiles][tile_points][D]
+    int n_tiles;
+    int tile_points;
+    const double *dirs;      // [count][2][D]
+    ull count;
+    double *cta_sums;        // [gridDim.x], accumulated across launches
+    double *values;          // optional [count]
+    ull *slow_counter;       // optional diagnostic
+};
+
+enum { MODE_EXACT = 1, MODE_SCREEN = 2 };
+
+// Threshold for the screen: a T with  p <= T  =>  RN(p * r) <= best.
+// winv = RN(1/r)  =>  best*winv*(1-2^-50) < (best/r)(1-2^-51); tiny values flush to 0 (= "always a
+// candidate"), which is always safe.
+__device__ __forceinline__ double screen_threshold(double best, double winv)
+{
+    const double t0 = best * winv;
+    const double t = fma(t0, -0x1p-50, t0);
+    return (t > 0x1p-900) ? t : 0.0;
+}
+
+template <int D>
+__device__ __forceinline__ void screen_slow_update(const double *__restrict__ p,       // smem, D doubles
+                                                   const double *__restrict__ dir,     // global r | winv
+                                                   double &best, double (&T)[D])
+{
+    double m = p[0] * __ldg(dir);
+#pragma unroll
+    for (int k = 1; k < D; k++) {
+        const double t = p[k] * __ldg(dir + k);
+        m = (t < m) ? t : m;
+    }
+    if (m > best) {
+        best = m;
+#pragma unroll
+        for (int k = 0; k < D; k++) T[k] = screen_threshold(m, __ldg(dir + D + k));
+    }
+}
+
+template <int D, int R, int G, int MODE>
+__global__ void __launch_bounds__(kBlockThreads) k_maxmin(const MaxminArgs a)
+{
+    static_assert((G * D) % 2 == 0, "a group of G points must be a whole number of 16-byte words");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tile_doubles = a.tile_points * D;
+    const unsigned tile_bytes = (unsigned)tile_doubles * 8u;
+    double *tiles = reinterpret_cast<double *>(smem_raw);
+    ull *full_bar = reinterpret_cast<ull *>(smem_raw + (size_t)kStages * kStageBytes);
+    ull *empty_bar = full_bar + kStages;
+    double *red = reinterpret_cast<double *>(empty_bar + kStages);   // 8 doubles
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    constexpr ull CH = (ull)kConsumerThreads * R;          // samples per chunk
+    const ull n_chunks = (a.count + CH - 1) / CH;
+    const ull my_chunks = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool resident = a.n_tiles <= kStages;           // whole point set fits: load once
+    const ull total_loads = resident ? (my_chunks ? (ull)a.n_tiles : 0) : my_chunks * (ull)a.n_tiles;
+
+    if (warp == kConsumerThreads / 32) {
+        // ---------------- producer warp: stream tiles with TMA bulk copies ----------------
+        if (lane == 0) {
+            for (ull q = 0; q < total_loads; q++) {
+                const int stage = (int)(q % kStages);
+                if (q >= (ull)kStages) mbar_wait(&empty_bar[stage], (unsigned)(((q / kStages) - 1) & 1));
+                mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
+                tma_load_1d(tiles + (size_t)stage * (kStageBytes / 8),
+                            a.pts + (size_t)(q % (ull)a.n_tiles) * tile_doubles, tile_bytes, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    double acc = 0.0;
+    ull slow = 0;
+    ull q = 0;
+    for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        ull sample[R];
+        bool valid[R];
+        double best[R];
+        double T[R][D];      // SCREEN: thresholds;  EXACT: reciprocal direction r
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            sample[r] = chunk * CH + (ull)r * kConsumerThreads + tid;
+            valid[r] = sample[r] < a.count;
+            best[r] = 0.0;
+            if (MODE == MODE_EXACT) {
+#pragma unroll
+                for (int k = 0; k < D; k++) T[r][k] = valid[r] ? __ldg(a.dirs + sample[r] * (2 * D) + k) : 0.0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < D; k++) T[r][k] = valid[r] ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+            }
+        }
+
+        for (int t = 0; t < a.n_tiles; t++, q++) {
+            const int stage = resident ? t : (int)(q % kStages);
+            const unsigned parity = resident ? 0u : (unsigned)((q / kStages) & 1);
+            mbar_wait(&full_bar[stage], parity);
+            const double *tile = tiles + (size_t)stage * (kStageBytes / 8);
+            const double2 *tile2 = reinterpret_cast<const double2 *>(tile);
+
+#pragma unroll 1
+            for (int g0 = 0; g0 < a.tile_points; g0 += G) {
+                const double2 *gp = tile2 + (g0 * D) / 2;
+                if (MODE == MODE_EXACT) {
+                    double m[R][G];
+#pragma unroll
+                    for (int j = 0; j < (G * D) / 2; j++) {
+                        const double2 v = gp[j];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int e = 2 * j + h, g = e / D, k = e % D;
+                            const double pv = h ? v.y : v.x;
+#pragma unroll
+                            for (int r = 0; r < R; r++) {
+                                const double prod = pv * T[r][k];
+                                if (k == 0) m[r][g] = prod;
+                                else m[r][g] = (prod < m[r][g]) ? prod : m[r][g];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+#pragma unroll
+                        for (int g = 0; g < G; g++) best[r] = (m[r][g] > best[r]) ? m[r][g] : best[r];
+                } else {
+                    bool c[R][G];
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+#pragma unroll
+                        for (int g = 0; g < G; g++) c[r][g] = true;
+#pragma unroll
+                    for (int j = 0; j < (G * D) / 2; j++) {
+                        const double2 v = gp[j];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int e = 2 * j + h, g = e / D, k = e % D;
+                            const double pv = h ? v.y : v.x;
+#pragma unroll
+                            for (int r = 0; r < R; r++) c[r][g] = c[r][g] & (pv > T[r][k]);
+                        }
+                    }
+                    bool any = false;
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+#pragma unroll
+                        for (int g = 0; g < G; g++) any = any | c[r][g];
+                    if (any) {
+#pragma unroll
+                        for (int g = 0; g < G; g++)
+#pragma unroll
+                            for (int r = 0; r < R; r++)
+                                if (c[r][g]) {
+                                    screen_slow_update<D>(tile + (size_t)(g0 + g) * D,
+                                                          a.dirs + sample[r] * (2 * D), best[r], T[r]);
+                                    slow++;
+                                }
+                    }
+                }
+            }
+            if (!resident) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            }
+        }
+
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const double v = pow_chain<D>(best[r]);
+            if (valid[r]) {
+                acc += v;
+                if (a.values) a.values[sample[r]] = v;
+            }
+        }
+    }
+
+    // fixed-shape block reduction over the 256 consumer threads
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (lane == 0) red[warp] = acc;
+    if (a.slow_counter) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) slow += __shfl_down_sync(0xffffffffu, slow, off);
+        if (lane == 0 && slow) atomicAdd(a.slow_counter, slow);
+    }
+    consumer_bar_sync();
+    if (tid == 0) {
+        double s01 = red[0] + red[1], s23 = red[2] + red[3], s45 = red[4] + red[5], s67 = red[6] + red[7];
+        a.cta_sums[blockIdx.x] += (s01 + s23) + (s45 + s67);
+    }
+}
+
+// Generic fall-back for d > 32 (extension beyond the reference's domain): runtime d, EXACT only,
+// directions read from L1/L2, one direction per thread.
+__global__ void __launch_bounds__(kBlockThreads) k_maxmin_generic(const MaxminArgs a, int d)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tile_doubles = a.tile_points * d;
+    const unsigned tile_bytes = (unsigned)tile_doubles * 8u;
+    double *tiles = reinterpret_cast<double *>(smem_raw);
+    ull *full_bar = reinterpret_cast<ull *>(smem_raw + (size_t)kStages * kStageBytes);
+    ull *empty_bar = full_bar + kStages;
+    double *red = reinterpret_cast<double *>(empty_bar + kStages);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerThreads / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const ull CH = kConsumerThreads;
+    const ull n_chunks = (a.count + CH - 1) / CH;
+    const ull my_chunks = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool resident = a.n_tiles <= kStages;
+    const ull total_loads = resident ? (my_chunks ? (ull)a.n_tiles : 0) : my_chunks * (ull)a.n_tiles;
+    if (warp == kConsumerThreads / 32) {
+        if (lane == 0) {
+            for (ull q = 0; q < total_loads; q++) {
+                const int stage = (int)(q % kStages);
+                if (q >= (ull)kStages) mbar_wait(&empty_bar[stage], (unsigned)(((q / kStages) - 1) & 1));
+                mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
+                tma_load_1d(tiles + (size_t)stage * (kStageBytes / 8),
+                            a.pts + (size_t)(q % (ull)a.n_tiles) * tile_doubles, tile_bytes, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+    double acc = 0.0;
+    ull q = 0;
+    for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const ull sample = chunk * CH + tid;
+        const bool valid = sample < a.count;
+        const double *rr = a.dirs + (valid ? sample : 0) * (ull)(2 * d);
+        double best = 0.0;
+        for (int t = 0; t < a.n_tiles; t++, q++) {
+            const int stage = resident ? t : (int)(q % kStages);
+            const unsigned parity = resident ? 0u : (unsigned)((q / kStages) & 1);
+            mbar_wait(&full_bar[stage], parity);
+            const double *tile = tiles + (size_t)stage * (kStageBytes / 8);
+            for (int g = 0; g < a.tile_points; g++) {
+                const double *p = tile + (size_t)g * d;
+                double m = p[0] * __ldg(rr);
+                for (int k = 1; k < d; k++) {
+                    const double pr = p[k] * __ldg(rr + k);
+                    m = (pr < m) ? pr : m;
+                }
+                best = (m > best) ? m : best;
+            }
+            if (!resident) { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[stage]); }
+        }
+        // generic square-and-multiply / chain by runtime exponent
+        double v;
+        {
+            unsigned e = (unsigned)d;
+            double x = best;
+            double accp = (e & 1u) ? x : 1.0;
+            for (e >>= 1; e; e >>= 1) { x *= x; if (e & 1u) accp *= x; }
+            v = accp;
+        }
+        if (valid) { acc += v; if (a.values) a.values[sample] = v; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (lane == 0) red[warp] = acc;
+    consumer_bar_sync();
+    if (tid == 0) {
+        double s01 = red[0] + red[1], s23 = red[2] + red[3], s45 = red[4] + red[5], s67 = red[6] + red[7];
+        a.cta_sums[blockIdx.x] += (s01 + s23) + (s45 + s67);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: final reduction, double-double pairwise tree of fixed shape (1 CTA, 1024 threads)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dd_add(double &hi, double &lo, double bh, double bl)
+{   // (hi,lo) += (bh,bl), Knuth two-sum + renormalisation
+    const double s = hi + bh;
+    const double bb = s - hi;
+    const double err = (hi - (s - bb)) + (bh - bb);
+    const double l = err + (lo + bl);
+    hi = s + l;
+    lo = l - (hi - s);
+}
+__global__ void __launch_bounds__(1024) k_reduce(const double *__restrict__ cta_sums, int n, double *out_hilo)
+{
+    __shared__ double sh[1024], sl[1024];
+    const int tid = threadIdx.x;
+    double hi = 0.0, lo = 0.0;
+    for (int i = tid; i < n; i += 1024) dd_add(hi, lo, cta_sums[i], 0.0);
+    sh[tid] = hi; sl[tid] = lo;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) {
+        if (tid < off) {
+            double h = sh[tid], l = sl[tid];
+            dd_add(h, l, sh[tid + off], sl[tid + off]);
+            sh[tid] = h; sl[tid] = l;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { out_hilo[0] = sh[0]; out_hilo[1] = sl[0]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: DZ2019-HW directions
+// ------------------------------------------------------------------------------------------------
+struct HwDev {
+    ull N;
+    ull a[HVB200_MAXD];
+    int d;
+};
+
+// RN64(x / N) as M * 2^e with M in [2^63, 2^64): bit-exact emulation of the x87 division
+// (i+1) / (long double)nsamples at c/hvapprox.c:295.  Requires 0 < x < N <= 2^32.
+struct X87Val { ull M; int e; };
+__device__ __forceinline__ X87Val x87_div(ull x, ull N)
+{
+    const int lx = 63 - __clzll((long long)x), lN = 63 - __clzll((long long)N);
+    int s = lN - lx;
+    ull X = x << s;
+    if (X < N) { X <<= 1; s++; }            // N <= X < 2N  ->  X/N in [1,2)
+    const ull r0 = X - N;
+    const ull t1 = r0 << 32;
+    const ull q1 = t1 / N, r1 = t1 - q1 * N;
+    const ull t2 = r1 << 31;
+    const ull q2 = t2 / N, r2 = t2 - q2 * N;
+    X87Val f;
+    f.M = (1ull << 63) + (q1 << 31) + q2;
+    f.e = -63 - s;
+    const ull twice = r2 << 1;
+    if (twice > N || (twice == N && (f.M & 1ull))) {
+        f.M += 1ull;
+        if (f.M == 0ull) { f.M = 1ull << 63; f.e += 1; }
+    }
+    return f;
+}
+// (double) fractl( RN64(f * a) ): c/hvapprox.c:297-298 followed by the cast of :615.
+__device__ __forceinline__ double x87_mul_frac(X87Val f, ull a)
+{
+    const ull lo = f.M * a;
+    const ull hi = __umul64hi(f.M, a);
+    ull Mv;
+    int ev;
+    if (hi == 0ull) {
+        Mv = lo; ev = f.e;                  // fits 64 bits: exact
+    } else {
+        int sh = 64 - __clzll((long long)hi);
+        Mv = (hi << (64 - sh)) | (lo >> sh);
+        const ull dropped = lo & ((1ull << sh) - 1ull), half = 1ull << (sh - 1);
+        if (dropped > half || (dropped == half && (Mv & 1ull))) {
+            Mv += 1ull;
+            if (Mv == 0ull) { Mv = 1ull << 63; sh += 1; }
+        }
+        ev = f.e + sh;
+    }
+    if (ev >= 0) return 0.0;
+    const int fbits = -ev;
+    const ull fr = (fbits >= 64) ? Mv : (Mv & ((1ull << fbits) - 1ull));
+    if (fr == 0ull) return 0.0;
+    return __ull2double_rn(fr) * __longlong_as_double((long long)(1023 - fbits) << 52);
+}
+
+// F_m(b) = int_0^b sin^m via the reduction formula (same restatement as the oracle):
+//   even m: lead*b - cos*sin*H(sin^2);  odd m: lead*(1-cos) - cos*sin^2*H(sin^2)
+__device__ __forceinline__ double fm_eval(int m, double b, double &sb, double &cb)
+{
+    sincos(b, &sb, &cb);
+    if (m == 0) return b;
+    if (m == 1) return 1.0 - cb;
+    const double s2 = sb * sb;
+    const int nh = c_fm_nh[m];
+    double H = c_fm_h[m][nh - 1];
+    for (int t = nh - 2; t >= 0; t--) H = H * s2 + c_fm_h[m][t];
+    if (m & 1) return c_fm_lead[m] * (1.0 - cb) - cb * s2 * H;
+    return c_fm_lead[m] * b - cb * sb * H;
+}
+__device__ __forceinline__ double ipow(double x, int e)
+{
+    double acc = (e & 1) ? x : 1.0;
+    for (e >>= 1; e; e >>= 1) { x *= x; if (e & 1) acc *= x; }
+    return acc;
+}
+// solve_inverse_int_of_power_sin (c/hvapprox.c:551-564) in FP64; returns sin/cos of the angle.
+__device__ void hw_solve(double target, int m, double &s_out, double &c_out, unsigned &capped)
+{
+    if (target == 0.0 && m < 32 && c_theta0_bits[m] != ~0ull) {
+        sincos(__longlong_as_double((long long)c_theta0_bits[m]), &s_out, &c_out);
+        return;
+    }
+    double x = 1.57079632679489661923;
+    double sb = 1.0, cb = 6.123233995736766e-17;     // sin, cos of (double)(pi/2)
+    double f = c_Im[m] - target;
+    int it = 0;
+    while (fabs(f) > 1e-15) {
+        if (++it > kNewtonCap || !(fabs(x) < 1e300)) { capped++; break; }
+        const double g = ipow(sb, m);
+        x -= f / g;
+        f = fm_eval(m, x, sb, cb) - target;
+    }
+    s_out = sb; c_out = cb;
+}
+
+__global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count, double *__restrict__ dirs,
+                                                ull *capped_counter)
+{
+    const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const int d = P.d;
+    const ull idx1 = i0 + j + 1;                    // i + 1
+    const bool last = !(idx1 < P.N);                // last sample: all zeros (c/hvapprox.c:300-303)
+    X87Val fac;
+    if (!last) fac = x87_div(idx1, P.N);
+    double *out = dirs + j * (ull)(2 * d);
+    unsigned capped = 0;
+    double prod = 1.0;
+    for (int q = 0; q < d - 1; q++) {
+        const int m = d - 2 - q;
+        const double u = last ? 0.0 : x87_mul_frac(fac, P.a[q]);
+        double s, c;
+        hw_solve(u * c_Im[m], m, s, c, capped);
+        // w_{d-1} = c_0; w_{d-1-q} = (s_0..s_{q-1}) c_q; w_0 = s_0..s_{d-2}  (c/hvapprox.c:632-638)
+        const double w = (q == 0) ? c : prod * c;
+        prod = (q == 0) ? s : s * prod;
+        const double r = (fabs(w) <= 1e-20) ? 1e20 : 1.0 / w;
+        double wi = 1.0 / r;
+        out[d - 1 - q] = r;
+        out[d + d - 1 - q] = (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;
+    }
+    {
+        const double w = prod;
+        const double r = (fabs(w) <= 1e-20) ? 1e20 : 1.0 / w;
+        double wi = 1.0 / r;
+        out[0] = r;
+        out[d] = (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;
+    }
+    if (capped) atomicAdd(capped_counter, (ull)capped);
+}
+
+__device__ __forceinline__ double safe_winv(double r)
+{
+    const double wi = 1.0 / r;
+    return (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;   // inf/NaN -> 0 (always candidate)
+}
+
+// K3: DZ2019-MC post-processing (c/hvapprox.c:241-250, euclidean_norm :203-212)
+__global__ void __launch_bounds__(128) k_gen_mc(const double *__restrict__ normals, ull count, int d,
+                                                double *__restrict__ dirs)
+{
+    const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const double *z = normals + j * (ull)d;
+    double *out = dirs + j * (ull)(2 * d);
+    double a0 = fabs(z[0]), a1 = fabs(z[1]);
+    a0 = (a0 < 1e-20) ? 1e-20 : a0;
+    a1 = (a1 < 1e-20) ? 1e-20 : a1;
+    double nrm = a0 * a0 + a1 * a1;
+    for (int k = 2; k < d; k++) {
+        double ak = fabs(z[k]);
+        ak = (ak < 1e-20) ? 1e-20 : ak;
+        nrm += ak * ak;
+    }
+    nrm = sqrt(nrm);
+    for (int k = 0; k < d; k++) {
+        double ak = fabs(z[k]);
+        ak = (ak < 1e-20) ? 1e-20 : ak;
+        const double r = nrm / ak;
+        out[k] = r;
+        out[d + k] = safe_winv(r);
+    }
+}
+
+// K4: Rphi-FWE+ mapping (fang_wang_efficient_mapping_plus, c/hvapprox.c:791-826) + r = 1/w (:855-856)
+__global__ void __launch_bounds__(128) k_gen_rphi(const double *__restrict__ uu, ull count, int d,
+                                                  double *__restrict__ dirs)
+{
+    const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const double HALF_PI = 1.57079632679489661923;
+    const double *u = uu + j * (ull)(d - 1);
+    double *out = dirs + j * (ull)(2 * d);
+    double prod = 1.0;
+    const int pairs = d / 2 - 1;
+    auto emit = [&](int k, double w) {
+        const double r = 1.0 / w;
+        out[k] = r;
+        out[d + k] = safe_winv(r);
+    };
+    for (int i = 0; i < pairs; i++) {
+        const int l = d - 2 * i - 2;
+        const double t = pow(u[l - 1], 1.0 / l);
+        const double dl = sqrt(1.0 - t * t) * prod;
+        prod *= t;
+        double sa, ca;
+        sincos(HALF_PI * u[l], &sa, &ca);
+        emit(2 * i, dl * sa);
+        emit(2 * i + 1, dl * ca);
+    }
+    double ang;
+    if (d % 2 == 0) {
+        ang = HALF_PI * u[0];
+    } else {
+        emit(d - 3, prod * u[0]);
+        prod *= sqrt(1 - u[0] * u[0]);
+        ang = HALF_PI * u[1];
+    }
+    double sa, ca;
+    sincos(ang, &sa, &ca);
+    emit(d - 2, prod * sa);
+    emit(d - 1, prod * ca);
+}
+
+// uploaded reciprocal directions -> (r, winv)
+__global__ void __launch_bounds__(128) k_prep_r(const double *__restrict__ rin, ull count, int d,
+                                                double *__restrict__ dirs)
+{
+    const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    for (int k = 0; k < d; k++) {
+        const double r = rin[j * (ull)d + k];
+        dirs[j * (ull)(2 * d) + k] = r;
+        dirs[j * (ull)(2 * d) + d + k] = safe_winv(r);
+    }
+}
+__global__ void __launch_bounds__(128) k_extract_r(const double *__restrict__ dirs, ull count, int d,
+                                                   double *__restrict__ rout)
+{
+    const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    for (int k = 0; k < d; k++) rout[j * (ull)d + k] = dirs[j * (ull)(2 * d) + k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 pipe micro-benchmarks (roofline denominator measured on the same GPU)
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256) k_fp64_bench(double *out, int iters, double seed)
+{
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = seed + 1e-3 * (threadIdx.x + i);
+    const double b = 1.0 + 1e-9 * threadIdx.x, c = 1e-12;
+    int cnt = 0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (OP == 0) x[i] = fma(x[i], b, c);
+                else if (OP == 1) x[i] = x[i] * b;
+                else cnt += (x[i] > b + (double)(it + u)) ? 1 : 0;   // DSETP (+ integer add)
+            }
+        }
+    }
+    double s = cnt;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct DevPlan {
+    int device = 0;
+    int d = 0;
+    size_t n = 0;
+    int n_tiles = 0, tile_points = 0;
+    int R = 1, G = 2;
+    double *pts = nullptr;
+    double *dirs = nullptr;      size_t dirs_cap = 0;      // samples
+    double *cta_sums = nullptr;  int cta_cap = 0;
+    double *values = nullptr;    size_t values_cap = 0;
+    double *out_hilo = nullptr;
+    ull *counters = nullptr;     // [0] newton capped, [1] slow path
+    double *staging_host = nullptr; size_t staging_cap = 0;   // pinned
+    double *staging_dev = nullptr;  size_t staging_dev_cap = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int sm_count = 0;
+    int grid = 0;                // CTAs of the max-min kernel
+    int kernel_used = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Span { int a, b, kind; };
+    std::vector<Span> spans;
+    size_t ev_next = 0;
+    cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr;
+};
+
+static bool g_const_ready[16] = {false};
+
+static int upload_constants(int device)
+{
+    if (device < 16 && g_const_ready[device]) return 0;
+    static double lead[HVB200_MAXD], h[HVB200_MAXD][kMaxFmTerms], Im[HVB200_MAXD];
+    static int nh[HVB200_MAXD];
+    const long double PI_L = 3.141592653589793238462643383279502884L;
+    for (int m = 0; m < HVB200_MAXD; m++) {
+        long double ld = 1.0L, hh[kMaxFmTerms];
+        int cnt = 0;
+        for (int j = m; j >= 2; j -= 2) {
+            hh[cnt++] = ld / (long double)j;
+            ld *= (long double)(j - 1) / (long double)j;
+        }
+        lead[m] = (double)ld;
+        nh[m] = cnt;
+        for (int t = 0; t < kMaxFmTerms; t++) h[m][t] = 0.0;
+        for (int t = 0; t < cnt; t++) h[m][t] = (double)hh[cnt - 1 - t];
+        // I_m = lead * (pi/2 for even m, 1 for odd m)  [c/hvapprox.c:480-548]
+        Im[m] = (double)((m & 1) ? ld : ld * (PI_L / 2));
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_fm_lead, lead, sizeof lead));
+    CUDA_TRY(cudaMemcpyToSymbol(c_fm_h, h, sizeof h));
+    CUDA_TRY(cudaMemcpyToSymbol(c_fm_nh, nh, sizeof nh));
+    CUDA_TRY(cudaMemcpyToSymbol(c_Im, Im, sizeof Im));
+    CUDA_TRY(cudaMemcpyToSymbol(c_theta0_bits, hvb200_theta0_bits, sizeof(ull) * 32));
+    if (device < 16) g_const_ready[device] = true;
+    return 0;
+}
+
+extern "C" int hvb200cu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static size_t maxmin_smem_bytes() { return (size_t)kStages * kStageBytes + 2 * kStages * sizeof(ull) + 8 * sizeof(double); }
+
+typedef void (*maxmin_fn)(const MaxminArgs);
+template <int D, int R, int G>
+static maxmin_fn pick_mode(int mode)
+{
+    return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<D, R, G, MODE_EXACT> : (maxmin_fn)k_maxmin<D, R, G, MODE_SCREEN>;
+}
+static constexpr int r_for(int D) { return D <= 16 ? 2 : 1; }
+static constexpr int g_for(int D) { return D <= 5 ? 4 : 2; }
+template <int D>
+static maxmin_fn pick_d(int d, int mode)
+{
+    if constexpr (D < 2) {
+        return nullptr;
+    } else {
+        if (d == D) return pick_mode<D, r_for(D), g_for(D)>(mode);
+        return pick_d<D - 1>(d, mode);
+    }
+}
+
+extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host)
+{
+    CUDA_TRY(cudaSetDevice(plan->device));
+    if (upload_constants(plan->device)) return -1;
+    DevPlan *dp = new DevPlan();
+    plan->dev = dp;
+    dp->device = plan->device;
+    dp->d = plan->d;
+    dp->n = plan->n;
+    const int d = plan->d;
+    dp->R = d <= 32 ? r_for(d) : 1;
+    dp->G = d <= 32 ? g_for(d) : 1;
+    int tp = kStageBytes / (8 * d);
+    tp &= ~3;                                      // multiple of 4 (covers G = 2 and 4)
+    if ((size_t)tp > ((plan->n + 3) & ~(size_t)3)) tp = (int)((plan->n + 3) & ~(size_t)3);
+    dp->tile_points = tp;
+    dp->n_tiles = (int)((plan->n + tp - 1) / tp);
+    const size_t padded = (size_t)dp->n_tiles * tp * d;
+    CUDA_TRY(cudaMalloc(&dp->pts, padded * sizeof(double)));
+    CUDA_TRY(cudaMemset(dp->pts, 0, padded * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(dp->pts, pts_host, plan->n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&dp->out_hilo, 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&dp->counters, 2 * sizeof(ull)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&dp->own_stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, plan->device));
+    dp->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaEventCreate(&dp->ev_h2d0));
+    CUDA_TRY(cudaEventCreate(&dp->ev_h2d1));
+    return 0;
+}
+
+extern "C" void hvb200cu_plan_free(struct hvb200_plan *plan)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (!dp) return;
+    cudaSetDevice(dp->device);
+    cudaFree(dp->pts); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
+    cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev);
+    if (dp->staging_host) cudaFreeHost(dp->staging_host);
+    for (auto e : dp->ev_pool) cudaEventDestroy(e);
+    if (dp->ev_h2d0) cudaEventDestroy(dp->ev_h2d0);
+    if (dp->ev_h2d1) cudaEventDestroy(dp->ev_h2d1);
+    if (dp->own_stream) cudaStreamDestroy(dp->own_stream);
+    delete dp;
+    plan->dev = nullptr;
+}
+
+static int span_begin(DevPlan *dp, int kind)
+{
+    while (dp->ev_pool.size() < dp->ev_next + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        dp->ev_pool.push_back(e);
+    }
+    const int a = (int)dp->ev_next, b = a + 1;
+    dp->ev_next += 2;
+    dp->spans.push_back({a, b, kind});
+    cudaEventRecord(dp->ev_pool[a], dp->stream);
+    return b;
+}
+static void span_end(DevPlan *dp, int b) { if (b >= 0) cudaEventRecord(dp->ev_pool[b], dp->stream); }
+
+extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batch, uint64_t *batch_out)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    CUDA_TRY(cudaSetDevice(dp->device));
+    dp->stream = stream ? (cudaStream_t)stream : dp->own_stream;
+    dp->spans.clear();
+    dp->ev_next = 0;
+    memset(&plan->stats, 0, sizeof plan->stats);
+    const int d = dp->d;
+    // batch size: bounded by 2 GiB of direction buffer and by what the caller needs
+    uint64_t batch = (2ull << 30) / (uint64_t)(16 * d);
+    batch &= ~(uint64_t)(kConsumerThreads * 2 - 1);
+    if (batch > max_batch) batch = max_batch;
+    if (batch < 1) batch = 1;
+    if (dp->dirs_cap < batch) {
+        cudaFree(dp->dirs);
+        dp->dirs = nullptr; dp->dirs_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->dirs, batch * (size_t)(2 * d) * sizeof(double)));
+        dp->dirs_cap = batch;
+    }
+    *batch_out = batch;
+
+    // kernel selection + launch geometry
+    int mode = plan->kernel == HVB200_KERNEL_EXACT ? MODE_EXACT : MODE_SCREEN;
+    if (d > 32) mode = MODE_EXACT;
+    dp->kernel_used = mode;
+    const size_t smem = maxmin_smem_bytes();
+    int occ = 1;
+    if (d <= 32) {
+        maxmin_fn fn = pick_d<32>(d, mode);
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBlockThreads, smem));
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute((const void *)k_maxmin_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k_maxmin_generic, kBlockThreads, smem));
+    }
+    if (occ < 1) { hvb200_set_error("max-min kernel does not fit on an SM (d=%d)", d); return -1; }
+    dp->grid = dp->sm_count * occ;
+    if (dp->cta_cap < dp->grid) {
+        cudaFree(dp->cta_sums);
+        CUDA_TRY(cudaMalloc(&dp->cta_sums, dp->grid * sizeof(double)));
+        dp->cta_cap = dp->grid;
+    }
+    CUDA_TRY(cudaMemsetAsync(dp->cta_sums, 0, dp->cta_cap * sizeof(double), dp->stream));
+    CUDA_TRY(cudaMemsetAsync(dp->counters, 0, 2 * sizeof(ull), dp->stream));
+    return 0;
+}
+
+extern "C" double *hvb200cu_staging(struct hvb200_plan *plan, size_t ndoubles)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (dp->staging_cap < ndoubles) {
+        if (dp->staging_host) cudaFreeHost(dp->staging_host);
+        dp->staging_host = nullptr; dp->staging_cap = 0;
+        if (cudaMallocHost(&dp->staging_host, ndoubles * sizeof(double)) != cudaSuccess) {
+            hvb200_set_error("cudaMallocHost(%zu bytes) failed", ndoubles * sizeof(double));
+            cudaGetLastError();
+            return nullptr;
+        }
+        dp->staging_cap = ndoubles;
+    }
+    return dp->staging_host;
+}
+
+static int stage_to_device(struct hvb200_plan *plan, DevPlan *dp, const double *host, size_t ndoubles)
+{
+    if (dp->staging_dev_cap < ndoubles) {
+        cudaFree(dp->staging_dev);
+        dp->staging_dev = nullptr; dp->staging_dev_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->staging_dev, ndoubles * sizeof(double)));
+        dp->staging_dev_cap = ndoubles;
+    }
+    const int b = span_begin(dp, 3);
+    CUDA_TRY(cudaMemcpyAsync(dp->staging_dev, host, ndoubles * sizeof(double), cudaMemcpyHostToDevice, dp->stream));
+    span_end(dp, b);
+    plan->stats.h2d_bytes += ndoubles * sizeof(double);
+    return 0;
+}
+
+extern "C" int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (hw->nsamples > (1ull << 32)) { hvb200_set_error("DZ2019-HW on the device supports nsamples <= 2^32"); return -1; }
+    HwDev P;
+    P.N = hw->nsamples;
+    P.d = hw->d;
+    for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
+    const int b = span_begin(dp, 1);
+    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(P, i0, count, dp->dirs, dp->counters);
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.dirgen_launches++;
+    return 0;
+}
+extern "C" int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (stage_to_device(plan, dp, normals_host, count * (size_t)dp->d)) return -1;
+    const int b = span_begin(dp, 1);
+    k_gen_mc<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->staging_dev, count, dp->d, dp->dirs);
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.dirgen_launches++;
+    return 0;
+}
+extern "C" int hvb200cu_gen_rphi(struct hvb200_plan *plan, const double *u_host, uint64_t count)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (stage_to_device(plan, dp, u_host, count * (size_t)(dp->d - 1))) return -1;
+    const int b = span_begin(dp, 1);
+    k_gen_rphi<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->staging_dev, count, dp->d, dp->dirs);
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.dirgen_launches++;
+    return 0;
+}
+extern "C" int hvb200cu_gen_uploaded(struct hvb200_plan *plan, const double *r_host, uint64_t count)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (stage_to_device(plan, dp, r_host, count * (size_t)dp->d)) return -1;
+    const int b = span_begin(dp, 1);
+    k_prep_r<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->staging_dev, count, dp->d, dp->dirs);
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.dirgen_launches++;
+    return 0;
+}
+extern "C" int hvb200cu_read_dirs(struct hvb200_plan *plan, uint64_t count, double *r_host)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    double *tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&tmp, count * (size_t)dp->d * sizeof(double)));
+    k_extract_r<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->dirs, count, dp->d, tmp);
+    cudaError_t e = cudaMemcpyAsync(r_host, tmp, count * (size_t)dp->d * sizeof(double), cudaMemcpyDeviceToHost, dp->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dp->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { hvb200_set_error("read_dirs: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+
+extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double *values_host)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    const int d = dp->d;
+    if (values_host && dp->values_cap < count) {
+        cudaFree(dp->values);
+        dp->values = nullptr; dp->values_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->values, count * sizeof(double)));
+        dp->values_cap = count;
+    }
+    MaxminArgs a;
+    a.pts = dp->pts;
+    a.n_tiles = dp->n_tiles;
+    a.tile_points = dp->tile_points;
+    a.dirs = dp->dirs;
+    a.count = count;
+    a.cta_sums = dp->cta_sums;
+    a.values = values_host ? dp->values : nullptr;
+    a.slow_counter = dp->counters + 1;
+    const size_t smem = maxmin_smem_bytes();
+    const ull chunk = (ull)kConsumerThreads * dp->R;
+    const ull n_chunks = (count + chunk - 1) / chunk;
+    const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks ? n_chunks : 1);
+    const int b = span_begin(dp, 0);
+    if (d <= 32) {
+        maxmin_fn fn = pick_d<32>(d, dp->kernel_used);
+        fn<<<grid, kBlockThreads, smem, dp->stream>>>(a);
+    } else {
+        k_maxmin_generic<<<grid, kBlockThreads, smem, dp->stream>>>(a, d);
+    }
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.maxmin_launches++;
+    if (values_host) {
+        CUDA_TRY(cudaMemcpyAsync(values_host, dp->values, count * sizeof(double), cudaMemcpyDeviceToHost, dp->stream));
+        CUDA_TRY(cudaStreamSynchronize(dp->stream));
+    }
+    return 0;
+}
+
+extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    {
+        const int b = span_begin(dp, 2);
+        k_reduce<<<1, 1024, 0, dp->stream>>>(dp->cta_sums, dp->grid, dp->out_hilo);
+        span_end(dp, b);
+        CUDA_TRY(cudaGetLastError());
+        plan->stats.reduce_launches++;
+    }
+    double host[2];
+    ull counters[2];
+    CUDA_TRY(cudaMemcpyAsync(host, dp->out_hilo, sizeof host, cudaMemcpyDeviceToHost, dp->stream));
+    CUDA_TRY(cudaMemcpyAsync(counters, dp->counters, sizeof counters, cudaMemcpyDeviceToHost, dp->stream));
+    CUDA_TRY(cudaStreamSynchronize(dp->stream));
+    if (out_hilo) { out_hilo[0] = host[0]; out_hilo[1] = host[1]; }
+    plan->stats.newton_capped = counters[0];
+    plan->stats.slow_path = counters[1];
+    plan->stats.npoints = dp->n;
+    plan->stats.kernel = dp->kernel_used == MODE_EXACT ? HVB200_KERNEL_EXACT : HVB200_KERNEL_SCREEN;
+    for (const auto &s : dp->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, dp->ev_pool[s.a], dp->ev_pool[s.b]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (s.kind == 0) plan->stats.maxmin_ms += ms;
+        else if (s.kind == 1) plan->stats.dirgen_ms += ms;
+        else if (s.kind == 2) plan->stats.reduce_ms += ms;
+        else plan->stats.h2d_ms += ms;
+    }
+    return 0;
+}
+
+extern "C" double hvb200cu_measure_fp64(int device, double *dmul_per_s, double *dsetp_per_s)
+{
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    double *out = nullptr;
+    if (cudaMalloc(&out, 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 4096, grid = prop.multiProcessorCount * 8, threads = 256;
+    const double ops = (double)grid * threads * iters * 64.0;
+    double res[3] = {0, 0, 0};
+    for (int op = 0; op < 3; op++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            if (op == 0) k_fp64_bench<0><<<grid, threads>>>(out, iters, 1.0);
+            else if (op == 1) k_fp64_bench<1><<<grid, threads>>>(out, iters, 1.0);
+            else k_fp64_bench<2><<<grid, threads>>>(out, iters, 1.0);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        res[op] = ops / (best * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    if (dmul_per_s) *dmul_per_s = res[1];
+    if (dsetp_per_s) *dsetp_per_s = res[2];
+    return 2.0 * res[0];
+}
