@@ -1,0 +1,39 @@
+"""Multi-GPU sharding of one hv_approx estimate.
+
+The N directions are independent, so rank g of G evaluates the contiguous index range
+[g*N/G, (g+1)*N/G) on its own GPU and produces one (hi, lo) FP64 pair; the only exchange step
+is an all-gather of those 16 bytes per rank (NCCL over NVLink when the process group is
+"nccl", gloo in the CPU tests), followed by a fixed-order long double sum and the c_d/N
+scaling of c/hvapprox.c:691-692.  An all-gather + ordered sum is used instead of an all-reduce
+so that the result does not depend on the collective's reduction order.
+"""
+from __future__ import annotations
+
+from typing import Sequence, Tuple
+
+
+def shard_range(nsamples: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, exhaustive, non-overlapping index range of `rank`."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    return (nsamples * rank) // world, (nsamples * (rank + 1)) // world
+
+
+def gather_partials(hilo: Sequence[float], group=None, device=None):
+    """All-gather one (hi, lo) pair per rank; returns a flat list [hi0, lo0, hi1, lo1, ...].
+
+    Works with any initialised torch.distributed backend; without an initialised process
+    group it returns the local pair (world size 1)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return [float(hilo[0]), float(hilo[1])]
+    world = dist.get_world_size(group)
+    t = torch.tensor([hilo[0], hilo[1]], dtype=torch.float64, device=device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    flat = []
+    for o in out:
+        flat.extend(o.cpu().tolist())
+    return flat
