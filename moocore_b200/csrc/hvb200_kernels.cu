@@ -34,6 +34,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -56,10 +57,11 @@ typedef unsigned long long ull;
 // ------------------------------------------------------------------------------------------------
 // constants
 // ------------------------------------------------------------------------------------------------
-static constexpr int kConsumerThreads = 256;
+static constexpr int kConsumerWarps = 7;                         // 7 + producer = 8 warps: 2 CTAs/SM at 128 regs
+static constexpr int kConsumerThreads = kConsumerWarps * 32;
 static constexpr int kBlockThreads = kConsumerThreads + 32;   // + one producer warp
 static constexpr int kStages = 3;
-static constexpr int kStageBytes = 24 * 1024;
+static constexpr int kMaxStageBytes = 24 * 1024;
 static constexpr int kNewtonCap = 200;
 static constexpr int kMaxFmTerms = 32;
 
@@ -161,6 +163,22 @@ __device__ __forceinline__ void mbar_wait(ull *bar, unsigned parity)
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Producer-side wait: the producer is 3 stages ahead, so it polls with a back-off instead of
+// spinning (a spinning lane costs its SM sub-partition ~25 % of its issue slots).
+__device__ __forceinline__ void mbar_wait_backoff(ull *bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, ull *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -178,6 +196,8 @@ struct MaxminArgs {
     const double *pts;       // [n_tiles][tile_points][D]
     int n_tiles;
     int tile_points;
+    int stage_bytes;         // bytes reserved per pipeline stage (>= tile bytes, multiple of 128)
+    int staged;              // 1: per-chunk directions are staged in shared memory
     const double *dirs;      // [count][2][D]
     ull count;
     double *cta_sums;        // [gridDim.x], accumulated across launches
@@ -197,35 +217,41 @@ __device__ __forceinline__ double screen_threshold(double best, double winv)
     return (t > 0x1p-900) ? t : 0.0;
 }
 
-template <int D>
+template <int D, bool STAGED>
 __device__ __forceinline__ void screen_slow_update(const double *__restrict__ p,       // smem, D doubles
-                                                   const double *__restrict__ dir,     // global r | winv
+                                                   const double *__restrict__ dir,     // r | winv (smem or global)
                                                    double &best, double (&T)[D])
 {
-    double m = p[0] * __ldg(dir);
+    auto ld = [&](int i) { return STAGED ? dir[i] : __ldg(dir + i); };
+    double m = p[0] * ld(0);
 #pragma unroll
     for (int k = 1; k < D; k++) {
-        const double t = p[k] * __ldg(dir + k);
+        const double t = p[k] * ld(k);
         m = (t < m) ? t : m;
     }
     if (m > best) {
         best = m;
 #pragma unroll
-        for (int k = 0; k < D; k++) T[k] = screen_threshold(m, __ldg(dir + D + k));
+        for (int k = 0; k < D; k++) T[k] = screen_threshold(m, ld(D + k));
     }
 }
 
-template <int D, int R, int G, int MODE>
-__global__ void __launch_bounds__(kBlockThreads) k_maxmin(const MaxminArgs a)
+template <int D, int R, int G, int MODE, int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB) k_maxmin(const MaxminArgs a)
 {
     static_assert((G * D) % 2 == 0, "a group of G points must be a whole number of 16-byte words");
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr ull CH = (ull)kConsumerThreads * R;          // samples per chunk
     const int tile_doubles = a.tile_points * D;
     const unsigned tile_bytes = (unsigned)tile_doubles * 8u;
+    const int stage_doubles = a.stage_bytes / 8;
     double *tiles = reinterpret_cast<double *>(smem_raw);
-    ull *full_bar = reinterpret_cast<ull *>(smem_raw + (size_t)kStages * kStageBytes);
+    double *dstage = tiles + (size_t)kStages * stage_doubles;                           // [CH][2D] if staged
+    ull *full_bar = reinterpret_cast<ull *>(dstage + (a.staged ? CH * 2 * D : 0));
     ull *empty_bar = full_bar + kStages;
-    double *red = reinterpret_cast<double *>(empty_bar + kStages);   // 8 doubles
+    ull *dfull_bar = empty_bar + kStages;
+    ull *dempty_bar = dfull_bar + 1;
+    double *red = reinterpret_cast<double *>(dempty_bar + 1);   // 8 doubles
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -236,25 +262,36 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin(const MaxminArgs a)
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kConsumerThreads / 32);
         }
+        mbar_init(dfull_bar, 1);
+        mbar_init(dempty_bar, kConsumerThreads / 32);
         mbar_fence_init();
     }
     __syncthreads();
 
-    constexpr ull CH = (ull)kConsumerThreads * R;          // samples per chunk
     const ull n_chunks = (a.count + CH - 1) / CH;
-    const ull my_chunks = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const bool resident = a.n_tiles <= kStages;           // whole point set fits: load once
-    const ull total_loads = resident ? (my_chunks ? (ull)a.n_tiles : 0) : my_chunks * (ull)a.n_tiles;
 
     if (warp == kConsumerThreads / 32) {
-        // ---------------- producer warp: stream tiles with TMA bulk copies ----------------
+        // ---------------- producer warp: TMA bulk copies of direction blocks and point tiles ----------------
         if (lane == 0) {
-            for (ull q = 0; q < total_loads; q++) {
-                const int stage = (int)(q % kStages);
-                if (q >= (ull)kStages) mbar_wait(&empty_bar[stage], (unsigned)(((q / kStages) - 1) & 1));
-                mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
-                tma_load_1d(tiles + (size_t)stage * (kStageBytes / 8),
-                            a.pts + (size_t)(q % (ull)a.n_tiles) * tile_doubles, tile_bytes, &full_bar[stage]);
+            ull q = 0, it = 0;
+            for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, it++) {
+                if (a.staged) {
+                    if (it > 0) mbar_wait_backoff(dempty_bar, (unsigned)((it - 1) & 1));
+                    const ull first = chunk * CH;
+                    const ull rows = (a.count - first < CH) ? a.count - first : CH;
+                    const unsigned bytes = (unsigned)(rows * 2 * D * 8);
+                    mbar_arrive_expect_tx(dfull_bar, bytes);
+                    tma_load_1d(dstage, a.dirs + first * (2 * D), bytes, dfull_bar);
+                }
+                if (resident && it > 0) continue;
+                for (int t = 0; t < a.n_tiles; t++, q++) {
+                    const int stage = (int)(q % kStages);
+                    if (q >= (ull)kStages) mbar_wait_backoff(&empty_bar[stage], (unsigned)(((q / kStages) - 1) & 1));
+                    mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
+                    tma_load_1d(tiles + (size_t)stage * stage_doubles, a.pts + (size_t)t * tile_doubles, tile_bytes,
+                                &full_bar[stage]);
+                }
             }
         }
         return;
@@ -263,20 +300,23 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin(const MaxminArgs a)
     // ---------------- consumers ----------------
     double acc = 0.0;
     ull slow = 0;
-    ull q = 0;
-    for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    ull q = 0, it = 0;
+    for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, it++) {
         ull sample[R];
         bool valid[R];
         double best[R];
         double T[R][D];      // SCREEN: thresholds;  EXACT: reciprocal direction r
+        const double *dir[R];
+        if (a.staged) mbar_wait(dfull_bar, (unsigned)(it & 1));
 #pragma unroll
         for (int r = 0; r < R; r++) {
             sample[r] = chunk * CH + (ull)r * kConsumerThreads + tid;
             valid[r] = sample[r] < a.count;
             best[r] = 0.0;
+            dir[r] = a.staged ? dstage + (size_t)(r * kConsumerThreads + tid) * (2 * D) : a.dirs + sample[r] * (2 * D);
             if (MODE == MODE_EXACT) {
 #pragma unroll
-                for (int k = 0; k < D; k++) T[r][k] = valid[r] ? __ldg(a.dirs + sample[r] * (2 * D) + k) : 0.0;
+                for (int k = 0; k < D; k++) T[r][k] = valid[r] ? (a.staged ? dir[r][k] : __ldg(dir[r] + k)) : 0.0;
             } else {
 #pragma unroll
                 for (int k = 0; k < D; k++) T[r][k] = valid[r] ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
@@ -287,7 +327,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin(const MaxminArgs a)
             const int stage = resident ? t : (int)(q % kStages);
             const unsigned parity = resident ? 0u : (unsigned)((q / kStages) & 1);
             mbar_wait(&full_bar[stage], parity);
-            const double *tile = tiles + (size_t)stage * (kStageBytes / 8);
+            const double *tile = tiles + (size_t)stage * stage_doubles;
             const double2 *tile2 = reinterpret_cast<const double2 *>(tile);
 
 #pragma unroll 1
@@ -342,8 +382,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin(const MaxminArgs a)
 #pragma unroll
                             for (int r = 0; r < R; r++)
                                 if (c[r][g]) {
-                                    screen_slow_update<D>(tile + (size_t)(g0 + g) * D,
-                                                          a.dirs + sample[r] * (2 * D), best[r], T[r]);
+                                    if (a.staged) screen_slow_update<D, true>(tile + (size_t)(g0 + g) * D, dir[r], best[r], T[r]);
+                                    else screen_slow_update<D, false>(tile + (size_t)(g0 + g) * D, dir[r], best[r], T[r]);
                                     slow++;
                                 }
                     }
@@ -353,6 +393,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin(const MaxminArgs a)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);
             }
+        }
+        if (a.staged) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dempty_bar);
         }
 
 #pragma unroll
@@ -376,8 +420,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin(const MaxminArgs a)
     }
     consumer_bar_sync();
     if (tid == 0) {
-        double s01 = red[0] + red[1], s23 = red[2] + red[3], s45 = red[4] + red[5], s67 = red[6] + red[7];
-        a.cta_sums[blockIdx.x] += (s01 + s23) + (s45 + s67);
+        double v[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) v[w] = (w < kConsumerWarps) ? red[w] : 0.0;
+        a.cta_sums[blockIdx.x] += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
 }
 
@@ -389,9 +435,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin_generic(const MaxminAr
     const int tile_doubles = a.tile_points * d;
     const unsigned tile_bytes = (unsigned)tile_doubles * 8u;
     double *tiles = reinterpret_cast<double *>(smem_raw);
-    ull *full_bar = reinterpret_cast<ull *>(smem_raw + (size_t)kStages * kStageBytes);
+    const int stage_doubles = a.stage_bytes / 8;
+    ull *full_bar = reinterpret_cast<ull *>(smem_raw + (size_t)kStages * a.stage_bytes);
     ull *empty_bar = full_bar + kStages;
-    double *red = reinterpret_cast<double *>(empty_bar + kStages);
+    double *red = reinterpret_cast<double *>(empty_bar + kStages + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerThreads / 32); }
@@ -409,7 +456,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin_generic(const MaxminAr
                 const int stage = (int)(q % kStages);
                 if (q >= (ull)kStages) mbar_wait(&empty_bar[stage], (unsigned)(((q / kStages) - 1) & 1));
                 mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
-                tma_load_1d(tiles + (size_t)stage * (kStageBytes / 8),
+                tma_load_1d(tiles + (size_t)stage * stage_doubles,
                             a.pts + (size_t)(q % (ull)a.n_tiles) * tile_doubles, tile_bytes, &full_bar[stage]);
             }
         }
@@ -426,7 +473,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin_generic(const MaxminAr
             const int stage = resident ? t : (int)(q % kStages);
             const unsigned parity = resident ? 0u : (unsigned)((q / kStages) & 1);
             mbar_wait(&full_bar[stage], parity);
-            const double *tile = tiles + (size_t)stage * (kStageBytes / 8);
+            const double *tile = tiles + (size_t)stage * stage_doubles;
             for (int g = 0; g < a.tile_points; g++) {
                 const double *p = tile + (size_t)g * d;
                 double m = p[0] * __ldg(rr);
@@ -454,8 +501,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_maxmin_generic(const MaxminAr
     if (lane == 0) red[warp] = acc;
     consumer_bar_sync();
     if (tid == 0) {
-        double s01 = red[0] + red[1], s23 = red[2] + red[3], s45 = red[4] + red[5], s67 = red[6] + red[7];
-        a.cta_sums[blockIdx.x] += (s01 + s23) + (s45 + s67);
+        double v[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) v[w] = (w < kConsumerWarps) ? red[w] : 0.0;
+        a.cta_sums[blockIdx.x] += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
 }
 
@@ -574,6 +623,12 @@ __device__ void hw_solve(double target, int m, double &s_out, double &c_out, uns
 {
     if (target == 0.0 && m < 32 && c_theta0_bits[m] != ~0ull) {
         sincos(__longlong_as_double((long long)c_theta0_bits[m]), &s_out, &c_out);
+        return;
+    }
+    if (m == 0) {
+        // F_0(b) = b: the reference's single Newton step x = pi/2 - (pi/2 - t) returns t up to a
+        // long double rounding (1e-19); in FP64 the same step would lose t below 1e-16 absolute.
+        sincos(target, &s_out, &c_out);
         return;
     }
     double x = 1.57079632679489661923;
@@ -755,6 +810,8 @@ struct DevPlan {
     size_t n = 0;
     int n_tiles = 0, tile_points = 0;
     int R = 1, G = 2;
+    int staged = 0, stage_bytes = 0;
+    size_t smem_bytes = 0;
     double *pts = nullptr;
     double *dirs = nullptr;      size_t dirs_cap = 0;      // samples
     double *cta_sums = nullptr;  int cta_cap = 0;
@@ -812,25 +869,77 @@ extern "C" int hvb200cu_device_count(void)
     return n;
 }
 
-static size_t maxmin_smem_bytes() { return (size_t)kStages * kStageBytes + 2 * kStages * sizeof(ull) + 8 * sizeof(double); }
+// ---- launch geometry ---------------------------------------------------------------------------
+// Per dimension: R directions per thread, G points per inner-loop group, whether the per-chunk
+// direction block (r | winv, 16*R*D bytes per thread) is staged in shared memory, and the number
+// of CTAs per SM the register budget is capped for.  Shared memory per CTA:
+//   kStages * stage_bytes  +  staged ? 256*R*2*D*8 : 0  +  barriers.
+struct KernelCfg { int R, G, minb; bool staged; };
+static constexpr KernelCfg cfg_for(int D)
+{
+    //             R  G  minb staged
+    if (D <= 5)  return {2, 4, 2, true};
+    if (D <= 12) return {3, 2, 2, false};
+    if (D <= 24) return {1, 2, 2, true};
+    return {1, 2, 2, false};
+}
+static constexpr size_t kSmemPerSm = 227 * 1024;
+static constexpr size_t kBarrierBytes = (2 * kStages + 2) * sizeof(ull) + 8 * sizeof(double);
 
 typedef void (*maxmin_fn)(const MaxminArgs);
-template <int D, int R, int G>
+template <int D>
 static maxmin_fn pick_mode(int mode)
 {
-    return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<D, R, G, MODE_EXACT> : (maxmin_fn)k_maxmin<D, R, G, MODE_SCREEN>;
+    constexpr KernelCfg c = cfg_for(D);
+    return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<D, c.R, c.G, MODE_EXACT, c.minb>
+                              : (maxmin_fn)k_maxmin<D, c.R, c.G, MODE_SCREEN, c.minb>;
 }
-static constexpr int r_for(int D) { return D <= 16 ? 2 : 1; }
-static constexpr int g_for(int D) { return D <= 5 ? 4 : 2; }
 template <int D>
 static maxmin_fn pick_d(int d, int mode)
 {
     if constexpr (D < 2) {
         return nullptr;
     } else {
-        if (d == D) return pick_mode<D, r_for(D), g_for(D)>(mode);
+        if (d == D) return pick_mode<D>(mode);
         return pick_d<D - 1>(d, mode);
     }
+}
+// Development aid: alternative register blockings for d = 10 selected with HVB200_VARIANT=1..5.
+static constexpr KernelCfg kVariants[] = {
+    {2, 2, 2, true}, {4, 1, 1, false}, {4, 1, 2, false}, {3, 2, 2, false}, {4, 1, 1, true}, {3, 2, 1, true},
+};
+static int variant_id()
+{
+    const char *e = getenv("HVB200_VARIANT");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 0 && v < (int)(sizeof kVariants / sizeof kVariants[0])) ? v : 0;
+}
+template <int V>
+static maxmin_fn pick_variant(int mode)
+{
+    constexpr KernelCfg c = kVariants[V];
+    return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<10, c.R, c.G, MODE_EXACT, c.minb>
+                              : (maxmin_fn)k_maxmin<10, c.R, c.G, MODE_SCREEN, c.minb>;
+}
+static maxmin_fn pick_kernel(int d, int mode)
+{
+    if (d == 10) {
+        switch (variant_id()) {
+            case 1: return pick_variant<1>(mode);
+            case 2: return pick_variant<2>(mode);
+            case 3: return pick_variant<3>(mode);
+            case 4: return pick_variant<4>(mode);
+            case 5: return pick_variant<5>(mode);
+            default: break;
+        }
+    }
+    return pick_d<32>(d, mode);
+}
+static KernelCfg cfg_runtime(int d)
+{
+    if (d > 32) return {1, 1, 1, false};
+    if (d == 10 && variant_id()) return kVariants[variant_id()];
+    return cfg_for(d);
 }
 
 extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host)
@@ -843,12 +952,23 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
     dp->d = plan->d;
     dp->n = plan->n;
     const int d = plan->d;
-    dp->R = d <= 32 ? r_for(d) : 1;
-    dp->G = d <= 32 ? g_for(d) : 1;
-    int tp = kStageBytes / (8 * d);
-    tp &= ~3;                                      // multiple of 4 (covers G = 2 and 4)
+    const KernelCfg kc = cfg_runtime(d);
+    dp->R = kc.R;
+    dp->G = kc.G;
+    dp->staged = kc.staged ? 1 : 0;
+    // shared memory budget per CTA for `minb` CTAs per SM -> bytes per pipeline stage
+    const size_t dir_bytes = kc.staged ? (size_t)kConsumerThreads * kc.R * 2 * d * 8 : 0;
+    size_t per_cta = kSmemPerSm / kc.minb - 1024;                     // 1 KB/CTA is reserved by the driver
+    size_t stage = (per_cta - dir_bytes - kBarrierBytes) / kStages;
+    if (stage > (size_t)kMaxStageBytes) stage = kMaxStageBytes;
+    stage &= ~(size_t)127;
+    int tp = (int)(stage / (8 * d));
+    tp &= ~3;                                      // multiple of 4 (covers G = 1, 2 and 4)
+    if (tp < 4) { hvb200_set_error("internal: no room for a point tile (d=%d)", d); return -1; }
     if ((size_t)tp > ((plan->n + 3) & ~(size_t)3)) tp = (int)((plan->n + 3) & ~(size_t)3);
     dp->tile_points = tp;
+    dp->stage_bytes = (int)((((size_t)tp * d * 8) + 127) & ~(size_t)127);
+    dp->smem_bytes = (size_t)kStages * dp->stage_bytes + dir_bytes + kBarrierBytes;
     dp->n_tiles = (int)((plan->n + tp - 1) / tp);
     const size_t padded = (size_t)dp->n_tiles * tp * d;
     CUDA_TRY(cudaMalloc(&dp->pts, padded * sizeof(double)));
@@ -907,7 +1027,7 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     const int d = dp->d;
     // batch size: bounded by 2 GiB of direction buffer and by what the caller needs
     uint64_t batch = (2ull << 30) / (uint64_t)(16 * d);
-    batch &= ~(uint64_t)(kConsumerThreads * 2 - 1);
+    batch -= batch % (uint64_t)(kConsumerThreads * 4);
     if (batch > max_batch) batch = max_batch;
     if (batch < 1) batch = 1;
     if (dp->dirs_cap < batch) {
@@ -919,17 +1039,23 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     *batch_out = batch;
 
     // kernel selection + launch geometry
-    int mode = plan->kernel == HVB200_KERNEL_EXACT ? MODE_EXACT : MODE_SCREEN;
+    // AUTO: the screen pays ~ln(n)+2 exact evaluations per direction plus warp divergence, which
+    // only amortises over a few hundred points (measured: n=100,d=3 exact 2x faster; n=1000,d=5 screen 7 % faster).
+    int mode = MODE_SCREEN;
+    if (plan->kernel == HVB200_KERNEL_EXACT) mode = MODE_EXACT;
+    else if (plan->kernel == HVB200_KERNEL_AUTO && dp->n < 512) mode = MODE_EXACT;
     if (d > 32) mode = MODE_EXACT;
     dp->kernel_used = mode;
-    const size_t smem = maxmin_smem_bytes();
+    const size_t smem = dp->smem_bytes;
     int occ = 1;
     if (d <= 32) {
-        maxmin_fn fn = pick_d<32>(d, mode);
+        maxmin_fn fn = pick_kernel(d, mode);
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBlockThreads, smem));
     } else {
         CUDA_TRY(cudaFuncSetAttribute((const void *)k_maxmin_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)k_maxmin_generic, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k_maxmin_generic, kBlockThreads, smem));
     }
     if (occ < 1) { hvb200_set_error("max-min kernel does not fit on an SM (d=%d)", d); return -1; }
@@ -1050,18 +1176,20 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     a.pts = dp->pts;
     a.n_tiles = dp->n_tiles;
     a.tile_points = dp->tile_points;
+    a.stage_bytes = dp->stage_bytes;
+    a.staged = dp->staged;
     a.dirs = dp->dirs;
     a.count = count;
     a.cta_sums = dp->cta_sums;
     a.values = values_host ? dp->values : nullptr;
     a.slow_counter = dp->counters + 1;
-    const size_t smem = maxmin_smem_bytes();
+    const size_t smem = dp->smem_bytes;
     const ull chunk = (ull)kConsumerThreads * dp->R;
     const ull n_chunks = (count + chunk - 1) / chunk;
     const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks ? n_chunks : 1);
     const int b = span_begin(dp, 0);
     if (d <= 32) {
-        maxmin_fn fn = pick_d<32>(d, dp->kernel_used);
+        maxmin_fn fn = pick_kernel(d, dp->kernel_used);
         fn<<<grid, kBlockThreads, smem, dp->stream>>>(a);
     } else {
         k_maxmin_generic<<<grid, kBlockThreads, smem, dp->stream>>>(a, d);

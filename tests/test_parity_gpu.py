@@ -182,8 +182,8 @@ def test_hw_lattice_is_x87_exact(mb, oracle):
         for i0 in (0, N - 2000 if N > 4000 else 0):
             got = _api.directions("DZ2019-HW", 2, N, 0, i0, min(2000, N - i0))
             want = oracle_dirs(oracle, "DZ2019-HW", 2, N, 0, i0, min(2000, N - i0))
-            assert np.max(np.abs(got - want) / np.abs(want)) < 5e-8   # last samples: cos(theta) ~ 1/N amplifies 1e-16
-            assert np.median(np.abs(got - want) / np.abs(want)) < 1e-15
+            assert np.max(np.abs(got - want) / np.abs(want)) < max(1e-12, 1e-15 * N)   # last samples: cos(theta) ~ 1/N amplifies 1e-16
+            assert np.median(np.abs(got - want) / np.abs(want)) < 2e-14
 
 
 def test_hw_zero_residue_samples(mb, oracle, golden):
