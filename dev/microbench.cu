@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256) k_reg(const double* __restrict__ in, unsi
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int k = 0; k < 8; k++) {   // make every operand loop-variant (ptxas hoists invariant setp's): 8 integer adds per 32 compares
-            if (KIND == 0 || KIND == 2) p[k] = __hiloint2double(__double2hiint(p[k]), __double2loint(p[k]) + it);
-            if (KIND == 1 || KIND == 2 || KIND == 3) ph[k] += it;
+            if (KIND == 0 || KIND == 2 || KIND == 6) p[k] = __hiloint2double(__double2hiint(p[k]), __double2loint(p[k]) + it);
+            if (KIND == 1 || KIND == 2 || KIND == 3 || KIND >= 6) ph[k] += it;
             if (KIND == 5) pf[k] = __uint_as_float(__float_as_uint(pf[k]) + it);
         }
         if (KIND == 0) cnt += blk_d(p, T);
@@ -102,6 +102,48 @@ __global__ void __launch_bounds__(256) k_reg(const double* __restrict__ in, unsi
             for (int k = 0; k < 4; k++) { a0 = __viaddmin_s16x2(ph[k], Th[k], a0); a1 = __viaddmin_s16x2(ph[k+1], Th[k], a1); a2 = __viaddmin_s16x2(ph[k+2], Th[k], a2); a3 = __viaddmin_s16x2(ph[k+3], Th[k], a3); }
             cnt += (a0 ^ a1 ^ a2 ^ a3) & 1; }
         else if (KIND == 5) cnt += blk_f(pf, Tf);
+        else if (KIND == 6) {   // 16 DSETP (2 chains of 8, one asm block) + 16 VIADDMNMX.S16x2 (4 accumulators) interleaved by the scheduler
+            unsigned a0 = cnt | 0x7fff0000u, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+            unsigned r;
+            asm volatile("{\n\t.reg .pred q0,q1;\n\t"
+                "setp.gt.f64 q0, %1, %9;\n\t setp.gt.f64 q1, %2, %9;\n\t"
+                "setp.gt.and.f64 q0, %2, %10, q0;\n\t setp.gt.and.f64 q1, %3, %10, q1;\n\t"
+                "setp.gt.and.f64 q0, %3, %11, q0;\n\t setp.gt.and.f64 q1, %4, %11, q1;\n\t"
+                "setp.gt.and.f64 q0, %4, %12, q0;\n\t setp.gt.and.f64 q1, %5, %12, q1;\n\t"
+                "setp.gt.and.f64 q0, %5, %13, q0;\n\t setp.gt.and.f64 q1, %6, %13, q1;\n\t"
+                "setp.gt.and.f64 q0, %6, %14, q0;\n\t setp.gt.and.f64 q1, %7, %14, q1;\n\t"
+                "setp.gt.and.f64 q0, %7, %15, q0;\n\t setp.gt.and.f64 q1, %8, %15, q1;\n\t"
+                "setp.gt.and.f64 q0, %8, %16, q0;\n\t setp.gt.and.f64 q1, %1, %16, q1;\n\t"
+                "or.pred q0, q0, q1;\n\tselp.u32 %0, 1, 0, q0;\n\t}"
+                : "=r"(r) : "d"(p[0]),"d"(p[1]),"d"(p[2]),"d"(p[3]),"d"(p[4]),"d"(p[5]),"d"(p[6]),"d"(p[7]),
+                            "d"(T[0]),"d"(T[1]),"d"(T[2]),"d"(T[3]),"d"(T[4]),"d"(T[5]),"d"(T[6]),"d"(T[7]));
+#pragma unroll
+            for (int k = 0; k < 4; k++) { a0 = __viaddmin_s16x2(ph[k], Th[k], a0); a1 = __viaddmin_s16x2(ph[k+1], Th[k], a1); a2 = __viaddmin_s16x2(ph[k+2], Th[k], a2); a3 = __viaddmin_s16x2(ph[k+3], Th[k], a3); }
+            cnt += r + ((a0 ^ a1 ^ a2 ^ a3) & 1); }
+        else if (KIND == 7) {   // 32 VIADDMNMX.S16x2 on 8 independent accumulators
+            unsigned a[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = (cnt + j) | 0x7fff0000u;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = __viaddmin_s16x2(ph[(k + j) & 7], Th[k], a[j]);
+            unsigned x = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) x ^= a[j];
+            cnt += x & 1; }
+        else if (KIND == 8) {   // 32 x (IADD + IMNMX as 32-bit viaddmin) on 8 accumulators
+            int a[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = (int)((cnt + j) | 0x7fff0000u);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = __viaddmin_s32((int)ph[(k + j) & 7], (int)Th[k], a[j]);
+            int x = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) x ^= a[j];
+            cnt += x & 1; }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = cnt;
 }
@@ -187,6 +229,9 @@ int main() {
         rep("REG ISETP.u32 chain", timeit([&] { k_reg<1><<<grid, 256>>>(d, o, ITERS); }));
         rep("REG mixed DSETP/ISETP 1:1", timeit([&] { k_reg<2><<<grid, 256>>>(d, o, ITERS); }));
         rep("REG VIADDMNMX.S16x2 (2 el/instr)", timeit([&] { k_reg<3><<<grid, 256>>>(d, o, ITERS); }));
+        rep("REG 16 DSETP + 16 DPX16x2 (48 el)", timeit([&] { k_reg<6><<<grid, 256>>>(d, o, ITERS); }) * (32.0f / 48.0f));
+        rep("REG DPX16x2 8 accs (64 el)", timeit([&] { k_reg<7><<<grid, 256>>>(d, o, ITERS); }) * 0.5f);
+        rep("REG VIADDMNMX.S32 8 accs (32 el)", timeit([&] { k_reg<8><<<grid, 256>>>(d, o, ITERS); }));
         rep("REG FSETP chain", timeit([&] { k_reg<5><<<grid, 256>>>(d, o, ITERS); }));
         {
             const double lds = (double)grid * 8 * ITERS * 16;   // warp-level LDS instructions per launch
