@@ -293,10 +293,23 @@ def run_ours(args, rank, local_rank, world):
                     "instead of DMUL+min and is bit-identical per sample to the (2d+1)-operation loop; "
                     "run with --kernel exact for the textbook loop",
         }
-        # CPU baseline: bounded sample of the same workload on 1 host core
+        # ncu-measured DRAM traffic of the profiled launch (profiles/), scaled to this run's launch size
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("config") == args.config:
+                per_dir = tj["dram_bytes_per_launch"] / tj["directions_per_launch"]
+                traffic = per_dir * float(i1 - i0) / max(1, mm_launches // max(1, args.steps))
+                roofline["traffic"] = traffic
+                roofline["traffic_source"] = tj["source"]
+        except Exception:
+            pass
+        # CPU baseline: bounded sample of the same workload on 1 host core (N=1 runs only)
         tp = hvcases.transformed(x, ref, maxi)
         spt = max(64, int(12.0 * 0.4e9 / tp.shape[0]))
         try:
+            if world > 1:
+                raise RuntimeError("cpu_baseline is timed at N=1 only")
             kind, thr, dt = cpu_throughput(tp, d, N, 1, spt)
             cpu = {"value": thr / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                    "sample": f"first {spt} of the N={N} DZ2019-HW directions, {dt:.1f} s on 1 host core "
