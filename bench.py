@@ -289,9 +289,10 @@ def run_ours(args, rank, local_rank, world):
             "hbm_gbs_needed": alg_bytes * mm_launches / (maxmin_ms_max / 1e3) / 1e9,
             "hbm_peak_gbs": peaks.get("hbm_gbs"),
             "traffic": None,
-            "note": "frac > 1 is expected for the SCREEN kernel: it decides max-min with one DSETP per element "
-                    "instead of DMUL+min and is bit-identical per sample to the (2d+1)-operation loop; "
-                    "run with --kernel exact for the textbook loop",
+            "note": "frac > 1 is expected for the screen kernels: they decide max-min with one compare per element "
+                    "(dpx: one VIADDMNMX.S16x2 per two elements on conservatively quantised keys, screen: one DSETP) "
+                    "instead of DMUL+min, evaluate only candidates in FP64, and are bit-identical per sample to the "
+                    "(2d+1)-operation loop; run with --kernel exact for the textbook loop",
         }
         # ncu-measured DRAM traffic of the profiled launch (profiles/), scaled to this run's launch size
         traffic = None
@@ -320,7 +321,7 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config), "kernel": plan.stats()["kernel"] == 2 and "screen" or "exact",
+            "config": {"workload": workload_name(args.config), "kernel": {1: "exact", 2: "screen", 3: "dpx"}.get(plan.stats()["kernel"], "?"),
                        "npoints_after_filter": npts, "parallelism": f"direction-range x{world}",
                        "l2": "point set (0.8 MB) is L2/shared-memory resident by design; the per-batch direction "
                              "buffer (2 GiB) exceeds L2, no flush needed",
@@ -348,7 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg3", choices=list(hvcases.CONFIGS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "screen"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "screen", "dpx"])
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":

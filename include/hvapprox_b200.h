@@ -32,8 +32,10 @@ enum {
 enum {
     HVB200_KERNEL_AUTO   = 0,
     HVB200_KERNEL_EXACT  = 1, /* d DMUL + d min + 1 max per sample*point (the textbook loop)   */
-    HVB200_KERNEL_SCREEN = 2  /* exact threshold screen: 1 DSETP per element, products only for
+    HVB200_KERNEL_SCREEN = 2, /* exact threshold screen: 1 DSETP per element, products only for
                                  candidates that can raise the running max                      */
+    HVB200_KERNEL_DPX    = 3  /* the same screen on conservatively quantised 16-bit keys with
+                                 DPX VIADDMNMX.S16x2 (2 elements per instruction, no predicates) */
 };
 
 /* Largest dimension the library accepts.  The reference stops at 31

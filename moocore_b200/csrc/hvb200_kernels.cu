@@ -205,7 +205,7 @@ struct MaxminArgs {
     ull *slow_counter;       // optional diagnostic
 };
 
-enum { MODE_EXACT = 1, MODE_SCREEN = 2 };
+enum { MODE_EXACT = 1, MODE_SCREEN = 2, MODE_DPX = 3 };
 
 // Threshold for the screen: a T with  p <= T  =>  RN(p * r) <= best.
 // winv = RN(1/r)  =>  best*winv*(1-2^-50) < (best/r)(1-2^-51); tiny values flush to 0 (= "always a
@@ -410,6 +410,279 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_maxmin(const MaxminArgs
     }
 
     // fixed-shape block reduction over the 256 consumer threads
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (lane == 0) red[warp] = acc;
+    if (a.slow_counter) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) slow += __shfl_down_sync(0xffffffffu, slow, off);
+        if (lane == 0 && slow) atomicAdd(a.slow_counter, slow);
+    }
+    consumer_bar_sync();
+    if (tid == 0) {
+        double v[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) v[w] = (w < kConsumerWarps) ? red[w] : 0.0;
+        a.cta_sums[blockIdx.x] += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1-DPX: the same exact screen on packed 16-bit keys (DPX VIADDMNMX.S16x2)
+//
+// The DSETP screen is limited by the SM's predicate-compare rate (~57 compares/clk/SM measured,
+// whatever the operand type).  VIADDMNMX.S16x2 does min(acc, a+b) on two 16-bit lanes without
+// touching predicates (45 instr = 90 element-compares/clk/SM measured).  Per objective k the
+// points' coordinates and the thresholds are mapped through the SAME monotone map
+//     f_k(x) = (x - lo_k) * scale_k ,  lo_k/hi_k = range of p'_k over the point set, scale_k = 32000/(hi_k-lo_k)
+// to keys  KP = clamp(ceil f_k(p), 0, S)  (rounded up)  and  KT = floor f_k(T)  (rounded down;
+// 0 if T < lo_k, S+1 if T >= hi_k), so that  p > T  =>  KP - KT >= 0.  A point is a candidate iff
+// min_k (KP_k - KT_k) >= 0; candidates take the same exact FP64 slow path as the DSETP screen, so the
+// per-sample result keeps the reference's bits.  One 32-bit word holds the keys of two points
+// (point 2j in the low half, 2j+1 in the high half) for one objective; the threshold key is
+// duplicated in both halves.  Padding points carry KP = -1 (never candidates).
+// ------------------------------------------------------------------------------------------------
+static constexpr int kKeyScale = 32000;
+static constexpr int kDpxPivots = 64;
+
+struct DpxArgs {
+    const unsigned *keys;    // [n_tiles][tile_pairs][D] packed words
+    int n_tiles;
+    int tile_pairs;
+    int stage_bytes;
+    ull npoints;
+    int n_pivots;            // first points of the set, evaluated exactly for every direction as a warm-up
+    const double *pts;       // FP64 points, row-major [npoints_padded][D] (slow path)
+    const double *dirs;      // [count][2][D]
+    ull count;
+    double *cta_sums;
+    double *values;
+    ull *slow_counter;
+    double qlo[32], qhi[32], qscale[32];
+};
+
+__device__ __forceinline__ unsigned dpx_neg_key(double T, double lo, double hi, double scale)
+{
+    int kt;
+    if (!(T >= lo)) kt = 0;
+    else if (T >= hi) kt = kKeyScale + 1;
+    else {
+        kt = (int)floor((T - lo) * scale);
+        kt = kt > kKeyScale ? kKeyScale : kt;
+    }
+    const unsigned v = (unsigned)(-kt) & 0xffffu;
+    return v | (v << 16);
+}
+
+__global__ void __launch_bounds__(256) k_quantize(const double *__restrict__ pts, ull n, int d, int tile_pairs,
+                                                  ull total_pairs, const double *__restrict__ qlo,
+                                                  const double *__restrict__ qhi, const double *__restrict__ qscale,
+                                                  unsigned *__restrict__ keys)
+{
+    const ull w = (ull)blockIdx.x * blockDim.x + threadIdx.x;      // word index = pair * d + k
+    if (w >= total_pairs * (ull)d) return;
+    const ull pair = w / d;
+    const int k = (int)(w - pair * d);
+    unsigned word = 0;
+    for (int h = 0; h < 2; h++) {
+        const ull idx = 2 * pair + h;
+        unsigned key = 0xffffu;                                      // -1: padding, never a candidate
+        if (idx < n) {
+            const double p = pts[idx * d + k];
+            double f = ceil((p - qlo[k]) * qscale[k]);
+            f = f < 0.0 ? 0.0 : (f > (double)kKeyScale ? (double)kKeyScale : f);
+            key = (unsigned)(int)f;
+        }
+        word |= key << (16 * h);
+    }
+    keys[w] = word;
+    (void)tile_pairs; (void)qhi;
+}
+
+template <int D>
+__device__ __forceinline__ void dpx_refresh_keys(double best, const double *__restrict__ winv, unsigned (&negT)[D],
+                                                 const DpxArgs &a)
+{
+#pragma unroll
+    for (int k = 0; k < D; k++)
+        negT[k] = dpx_neg_key(screen_threshold(best, __ldg(winv + k)), a.qlo[k], a.qhi[k], a.qscale[k]);
+}
+template <int D>
+__device__ __forceinline__ void dpx_slow_update(const double *__restrict__ p,      // global, D doubles
+                                                const double *__restrict__ dir,    // global r | winv
+                                                double &best, unsigned (&negT)[D], const DpxArgs &a)
+{
+    double m = __ldg(p) * __ldg(dir);
+#pragma unroll
+    for (int k = 1; k < D; k++) {
+        const double t = __ldg(p + k) * __ldg(dir + k);
+        m = (t < m) ? t : m;
+    }
+    if (m > best) {
+        best = m;
+        dpx_refresh_keys<D>(m, dir + D, negT, a);
+    }
+}
+
+template <int D, int R, int G, int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB) k_maxmin_dpx(const __grid_constant__ DpxArgs a)
+{
+    static_assert((G * D) % 4 == 0, "a group of G point pairs must be a whole number of 16-byte words");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr ull CH = (ull)kConsumerThreads * R;
+    const int tile_words = a.tile_pairs * D;
+    const unsigned tile_bytes = (unsigned)tile_words * 4u;
+    const int stage_words = a.stage_bytes / 4;
+    unsigned *tiles = reinterpret_cast<unsigned *>(smem_raw);
+    ull *full_bar = reinterpret_cast<ull *>(smem_raw + (size_t)kStages * a.stage_bytes);
+    ull *empty_bar = full_bar + kStages;
+    double *red = reinterpret_cast<double *>(empty_bar + kStages + 2);
+    double *pivots = red + 8;                                   // [n_pivots][D] FP64: the first points of the set
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    const int n_piv = a.n_pivots;
+    for (int i = tid; i < n_piv * D; i += kBlockThreads) pivots[i] = a.pts[i];
+    __syncthreads();
+
+    const ull n_chunks = (a.count + CH - 1) / CH;
+    const ull my_chunks = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool resident = a.n_tiles <= kStages;
+    const ull total_loads = resident ? (my_chunks ? (ull)a.n_tiles : 0) : my_chunks * (ull)a.n_tiles;
+
+    if (warp == kConsumerThreads / 32) {
+        if (lane == 0) {
+            for (ull q = 0; q < total_loads; q++) {
+                const int stage = (int)(q % kStages);
+                if (q >= (ull)kStages) mbar_wait_backoff(&empty_bar[stage], (unsigned)(((q / kStages) - 1) & 1));
+                mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
+                tma_load_1d(tiles + (size_t)stage * stage_words, a.keys + (size_t)(q % (ull)a.n_tiles) * tile_words,
+                            tile_bytes, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+
+    double acc = 0.0;
+    ull slow = 0;
+    ull q = 0;
+    for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        ull sample[R];
+        bool valid[R];
+        double best[R];
+        unsigned negT[R][D];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            sample[r] = chunk * CH + (ull)r * kConsumerThreads + tid;
+            valid[r] = sample[r] < a.count;
+            best[r] = 0.0;
+            if (valid[r]) {
+                // warm-up: exact max-min over the pivot points (branch-free, all lanes busy) so that the
+                // screen starts from a useful running max instead of paying a divergent slow-path entry
+                // for each of the first ~ln(n_piv) records of every direction
+                const double *dir = a.dirs + sample[r] * (2 * D);
+                double rr[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) rr[k] = __ldg(dir + k);
+                double b = 0.0;
+#pragma unroll 2
+                for (int i = 0; i < n_piv; i++) {
+                    const double *pp = pivots + i * D;
+                    double m = pp[0] * rr[0];
+#pragma unroll
+                    for (int k = 1; k < D; k++) {
+                        const double t = pp[k] * rr[k];
+                        m = (t < m) ? t : m;
+                    }
+                    b = (m > b) ? m : b;
+                }
+                best[r] = b;
+                dpx_refresh_keys<D>(b, dir + D, negT[r], a);
+            } else {
+                // tail samples beyond count get the "nothing passes" key
+                const unsigned v = ((unsigned)(-(kKeyScale + 1)) & 0xffffu) * 0x10001u;
+#pragma unroll
+                for (int k = 0; k < D; k++) negT[r][k] = v;
+            }
+        }
+
+        for (int t = 0; t < a.n_tiles; t++, q++) {
+            const int stage = resident ? t : (int)(q % kStages);
+            const unsigned parity = resident ? 0u : (unsigned)((q / kStages) & 1);
+            mbar_wait(&full_bar[stage], parity);
+            const uint4 *tile4 = reinterpret_cast<const uint4 *>(tiles + (size_t)stage * stage_words);
+            const ull tile_first_point = (ull)t * a.tile_pairs * 2;
+
+#pragma unroll 1
+            for (int g0 = 0; g0 < a.tile_pairs; g0 += G) {
+                const uint4 *gp = tile4 + (g0 * D) / 4;
+                unsigned am[R][G];
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int g = 0; g < G; g++) am[r][g] = 0x7fff7fffu;
+#pragma unroll
+                for (int j = 0; j < (G * D) / 4; j++) {
+                    const uint4 w = gp[j];
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const int e = 4 * j + h, g = e / D, k = e % D;
+                        const unsigned wh = h == 0 ? w.x : (h == 1 ? w.y : (h == 2 ? w.z : w.w));
+#pragma unroll
+                        for (int r = 0; r < R; r++) am[r][g] = __viaddmin_s16x2(wh, negT[r][k], am[r][g]);
+                    }
+                }
+                // any halfword >= 0 ?  (sign bit clear)
+                unsigned all_neg = 0x80008000u;
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int g = 0; g < G; g++) all_neg &= am[r][g];
+                if (all_neg != 0x80008000u) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        // candidate bits of direction r: bit (2g+h) <=> point 2(g0+g)+h
+                        unsigned cand = 0;
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            const unsigned nm = ~am[r][g];
+                            cand |= ((nm >> 15) & 1u) << (2 * g);
+                            cand |= ((nm >> 31) & 1u) << (2 * g + 1);
+                        }
+                        while (cand) {
+                            const int bit = __ffs((int)cand) - 1;
+                            cand &= cand - 1;
+                            const ull idx = tile_first_point + 2 * (ull)g0 + (ull)bit;
+                            dpx_slow_update<D>(a.pts + idx * D, a.dirs + sample[r] * (2 * D), best[r], negT[r], a);
+                            slow++;
+                        }
+                    }
+                }
+            }
+            if (!resident) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            }
+        }
+
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const double v = pow_chain<D>(best[r]);
+            if (valid[r]) {
+                acc += v;
+                if (a.values) a.values[sample[r]] = v;
+            }
+        }
+    }
+
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
     if (lane == 0) red[warp] = acc;
@@ -813,6 +1086,11 @@ struct DevPlan {
     int staged = 0, stage_bytes = 0;
     size_t smem_bytes = 0;
     double *pts = nullptr;
+    unsigned *keys = nullptr;            // DPX screen: packed 16-bit keys
+    int k_tile_pairs = 0, k_n_tiles = 0, k_stage_bytes = 0;
+    size_t k_smem_bytes = 0;
+    int kR = 1, kG = 2;
+    double qlo[32] = {0}, qhi[32] = {0}, qscale[32] = {0};
     double *dirs = nullptr;      size_t dirs_cap = 0;      // samples
     double *cta_sums = nullptr;  int cta_cap = 0;
     double *values = nullptr;    size_t values_cap = 0;
@@ -935,6 +1213,26 @@ static maxmin_fn pick_kernel(int d, int mode)
     }
     return pick_d<32>(d, mode);
 }
+// DPX screen geometry: R directions per thread, G point pairs per group ((G*D) % 4 == 0).
+struct DpxCfg { int R, G, minb; };
+static constexpr DpxCfg dpx_cfg_for(int D)
+{
+    return {D <= 20 ? 4 : 2, (D % 2 == 0) ? 2 : 4, D <= 8 ? 3 : 2};
+}
+typedef void (*dpx_fn)(const DpxArgs);
+template <int D>
+static dpx_fn pick_dpx(int d)
+{
+    if constexpr (D < 2) {
+        return nullptr;
+    } else {
+        if (d == D) {
+            constexpr DpxCfg c = dpx_cfg_for(D);
+            return (dpx_fn)k_maxmin_dpx<D, c.R, c.G, c.minb>;
+        }
+        return pick_dpx<D - 1>(d);
+    }
+}
 static KernelCfg cfg_runtime(int d)
 {
     if (d > 32) return {1, 1, 1, false};
@@ -974,6 +1272,43 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
     CUDA_TRY(cudaMalloc(&dp->pts, padded * sizeof(double)));
     CUDA_TRY(cudaMemset(dp->pts, 0, padded * sizeof(double)));
     CUDA_TRY(cudaMemcpy(dp->pts, pts_host, plan->n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice));
+    if (d <= 32) {
+        // ---- DPX keys: per-objective range of the point set, monotone 16-bit quantisation on the device
+        for (int k = 0; k < d; k++) { dp->qlo[k] = INFINITY; dp->qhi[k] = -INFINITY; }
+        for (size_t i = 0; i < plan->n; i++)
+            for (int k = 0; k < d; k++) {
+                const double v = pts_host[i * (size_t)d + k];
+                if (v < dp->qlo[k]) dp->qlo[k] = v;
+                if (v > dp->qhi[k]) dp->qhi[k] = v;
+            }
+        for (int k = 0; k < d; k++) {
+            const double range = dp->qhi[k] - dp->qlo[k];
+            dp->qscale[k] = (range > 0 && std::isfinite(range)) ? (double)kKeyScale / range : 0.0;
+            if (!std::isfinite(dp->qscale[k])) dp->qscale[k] = 0.0;
+        }
+        const DpxCfg dc = dpx_cfg_for(d);
+        dp->kR = dc.R;
+        dp->kG = dc.G;
+        const size_t total_pairs_raw = (plan->n + 1) / 2;
+        int tpairs = (16 * 1024 / (4 * d)) & ~3;
+        if ((size_t)tpairs > ((total_pairs_raw + 3) & ~(size_t)3)) tpairs = (int)((total_pairs_raw + 3) & ~(size_t)3);
+        dp->k_tile_pairs = tpairs;
+        dp->k_n_tiles = (int)((total_pairs_raw + tpairs - 1) / tpairs);
+        dp->k_stage_bytes = (int)((((size_t)tpairs * d * 4) + 127) & ~(size_t)127);
+        dp->k_smem_bytes = (size_t)kStages * dp->k_stage_bytes + kBarrierBytes + (size_t)kDpxPivots * d * sizeof(double);
+        const size_t total_pairs = (size_t)dp->k_n_tiles * tpairs;
+        CUDA_TRY(cudaMalloc(&dp->keys, total_pairs * d * sizeof(unsigned)));
+        double *qdev = nullptr;
+        CUDA_TRY(cudaMalloc(&qdev, 3 * 32 * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(qdev, dp->qlo, 32 * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(qdev + 32, dp->qhi, 32 * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(qdev + 64, dp->qscale, 32 * sizeof(double), cudaMemcpyHostToDevice));
+        const ull words = (ull)total_pairs * d;
+        k_quantize<<<(unsigned)((words + 255) / 256), 256>>>(dp->pts, (ull)plan->n, d, tpairs, (ull)total_pairs, qdev, qdev + 32, qdev + 64, dp->keys);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(qdev);
+    }
     CUDA_TRY(cudaMalloc(&dp->out_hilo, 2 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&dp->counters, 2 * sizeof(ull)));
     CUDA_TRY(cudaStreamCreateWithFlags(&dp->own_stream, cudaStreamNonBlocking));
@@ -990,7 +1325,7 @@ extern "C" void hvb200cu_plan_free(struct hvb200_plan *plan)
     DevPlan *dp = (DevPlan *)plan->dev;
     if (!dp) return;
     cudaSetDevice(dp->device);
-    cudaFree(dp->pts); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
+    cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev);
     if (dp->staging_host) cudaFreeHost(dp->staging_host);
     for (auto e : dp->ev_pool) cudaEventDestroy(e);
@@ -1039,16 +1374,23 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     *batch_out = batch;
 
     // kernel selection + launch geometry
-    // AUTO: the screen pays ~ln(n)+2 exact evaluations per direction plus warp divergence, which
-    // only amortises over a few hundred points (measured: n=100,d=3 exact 2x faster; n=1000,d=5 screen 7 % faster).
-    int mode = MODE_SCREEN;
+    // AUTO: the screens pay a divergent exact evaluation per candidate, which only amortises over a
+    // few hundred points (measured on B200: n=100,d=3 EXACT 602 / DPX 243 / SCREEN 371 Gsp/s;
+    // n=1000,d=5 EXACT 734 / SCREEN 930 / DPX 1277; n=1e4,d=10 EXACT 484 / SCREEN 1240 / DPX 1946).
+    int mode = MODE_DPX;
     if (plan->kernel == HVB200_KERNEL_EXACT) mode = MODE_EXACT;
-    else if (plan->kernel == HVB200_KERNEL_AUTO && dp->n < 512) mode = MODE_EXACT;
+    else if (plan->kernel == HVB200_KERNEL_SCREEN) mode = MODE_SCREEN;
+    else if (plan->kernel == HVB200_KERNEL_AUTO && dp->n < 256) mode = MODE_EXACT;
     if (d > 32) mode = MODE_EXACT;
     dp->kernel_used = mode;
-    const size_t smem = dp->smem_bytes;
+    const size_t smem = mode == MODE_DPX ? dp->k_smem_bytes : dp->smem_bytes;
     int occ = 1;
-    if (d <= 32) {
+    if (mode == MODE_DPX) {
+        dpx_fn fn = pick_dpx<32>(d);
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBlockThreads, smem));
+    } else if (d <= 32) {
         maxmin_fn fn = pick_kernel(d, mode);
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -1183,12 +1525,30 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     a.cta_sums = dp->cta_sums;
     a.values = values_host ? dp->values : nullptr;
     a.slow_counter = dp->counters + 1;
-    const size_t smem = dp->smem_bytes;
-    const ull chunk = (ull)kConsumerThreads * dp->R;
+    const bool dpx = dp->kernel_used == MODE_DPX;
+    const size_t smem = dpx ? dp->k_smem_bytes : dp->smem_bytes;
+    const ull chunk = (ull)kConsumerThreads * (dpx ? dp->kR : dp->R);
     const ull n_chunks = (count + chunk - 1) / chunk;
     const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks ? n_chunks : 1);
     const int b = span_begin(dp, 0);
-    if (d <= 32) {
+    if (dpx) {
+        DpxArgs ka;
+        ka.keys = dp->keys;
+        ka.n_tiles = dp->k_n_tiles;
+        ka.tile_pairs = dp->k_tile_pairs;
+        ka.stage_bytes = dp->k_stage_bytes;
+        ka.npoints = dp->n;
+        ka.n_pivots = (int)std::min<size_t>(dp->n, (size_t)kDpxPivots);
+        ka.pts = dp->pts;
+        ka.dirs = dp->dirs;
+        ka.count = count;
+        ka.cta_sums = dp->cta_sums;
+        ka.values = a.values;
+        ka.slow_counter = dp->counters + 1;
+        for (int k = 0; k < 32; k++) { ka.qlo[k] = dp->qlo[k]; ka.qhi[k] = dp->qhi[k]; ka.qscale[k] = dp->qscale[k]; }
+        dpx_fn fn = pick_dpx<32>(d);
+        fn<<<grid, kBlockThreads, smem, dp->stream>>>(ka);
+    } else if (d <= 32) {
         maxmin_fn fn = pick_kernel(d, dp->kernel_used);
         fn<<<grid, kBlockThreads, smem, dp->stream>>>(a);
     } else {
@@ -1223,7 +1583,7 @@ extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
     plan->stats.newton_capped = counters[0];
     plan->stats.slow_path = counters[1];
     plan->stats.npoints = dp->n;
-    plan->stats.kernel = dp->kernel_used == MODE_EXACT ? HVB200_KERNEL_EXACT : HVB200_KERNEL_SCREEN;
+    plan->stats.kernel = dp->kernel_used == MODE_EXACT ? HVB200_KERNEL_EXACT : (dp->kernel_used == MODE_DPX ? HVB200_KERNEL_DPX : HVB200_KERNEL_SCREEN);
     for (const auto &s : dp->spans) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, dp->ev_pool[s.a], dp->ev_pool[s.b]) != cudaSuccess) { cudaGetLastError(); continue; }
