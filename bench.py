@@ -278,7 +278,7 @@ def run_ours(args, rank, local_rank, world):
             pass
         alg_bytes = 8.0 * npts * d
         roofline = {
-            "bound": "fp64", "kernel": "k_maxmin", "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
+            "bound": "fp64", "kernel": {1: "k_maxmin<EXACT>", 2: "k_maxmin<SCREEN>", 3: "k_maxmin_dpx"}.get(plan.stats()["kernel"], "k_maxmin"), "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
             "unit": "TFP64-instr/s", "frac": achieved / peak_instr,
             "peak_source": "DFMA micro-benchmark measured in this run on this GPU (P64/2; MEASURED_PEAKS.json has no FP64 entry)",
             "p64_tflops_measured": fp["dfma_flops"] / 1e12,

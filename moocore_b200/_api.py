@@ -43,7 +43,8 @@ class Stats(ctypes.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, _LIBNAME)
+    # HVB200_LIBRARY: development override (A/B-testing differently tuned builds)
+    return os.environ.get("HVB200_LIBRARY") or os.path.join(_HERE, _LIBNAME)
 
 
 _lib = None

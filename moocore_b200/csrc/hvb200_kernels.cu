@@ -169,14 +169,16 @@ __device__ __forceinline__ void mbar_wait_backoff(ull *bar, unsigned parity)
 {
     unsigned done = 0;
     for (;;) {
+        // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes
+        // or ~20 us pass, instead of returning after its short default time limit
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
         if (done) break;
-        __nanosleep(256);
+        __nanosleep(2000);
     }
 }
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, ull *bar)
@@ -444,6 +446,12 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_maxmin(const MaxminArgs
 // ------------------------------------------------------------------------------------------------
 static constexpr int kKeyScale = 32000;
 static constexpr int kDpxPivots = 64;
+static int dpx_pivots()
+{
+    const char *e = getenv("HVB200_PIVOTS");
+    const int v = e ? atoi(e) : kDpxPivots;
+    return v < 0 ? 0 : (v > 1024 ? 1024 : v);
+}
 
 struct DpxArgs {
     const unsigned *keys;    // [n_tiles][tile_pairs][D] packed words
@@ -1217,7 +1225,11 @@ static maxmin_fn pick_kernel(int d, int mode)
 struct DpxCfg { int R, G, minb; };
 static constexpr DpxCfg dpx_cfg_for(int D)
 {
-    return {D <= 20 ? 4 : 2, (D % 2 == 0) ? 2 : 4, D <= 8 ? 3 : 2};
+    //                          R  G  CTAs/SM      (measured on B200: d=10 {4,4,2} 2.10 Tsp/s; d=20 {3,4,2} 0.96, {4,2,2} 0.88)
+    if (D <= 8)  return {4, 4, 3};
+    if (D <= 12) return {4, 4, 2};
+    if (D <= 20) return {3, 4, 2};
+    return {2, (D % 2) ? 4 : 2, 2};
 }
 typedef void (*dpx_fn)(const DpxArgs);
 template <int D>
@@ -1295,7 +1307,7 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
         dp->k_tile_pairs = tpairs;
         dp->k_n_tiles = (int)((total_pairs_raw + tpairs - 1) / tpairs);
         dp->k_stage_bytes = (int)((((size_t)tpairs * d * 4) + 127) & ~(size_t)127);
-        dp->k_smem_bytes = (size_t)kStages * dp->k_stage_bytes + kBarrierBytes + (size_t)kDpxPivots * d * sizeof(double);
+        dp->k_smem_bytes = (size_t)kStages * dp->k_stage_bytes + kBarrierBytes + (size_t)dpx_pivots() * d * sizeof(double);
         const size_t total_pairs = (size_t)dp->k_n_tiles * tpairs;
         CUDA_TRY(cudaMalloc(&dp->keys, total_pairs * d * sizeof(unsigned)));
         double *qdev = nullptr;
@@ -1362,6 +1374,10 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     const int d = dp->d;
     // batch size: bounded by 2 GiB of direction buffer and by what the caller needs
     uint64_t batch = (2ull << 30) / (uint64_t)(16 * d);
+    {
+        const char *e = getenv("HVB200_BATCH");          // samples per launch (development knob)
+        if (e && atoll(e) > 0) batch = (uint64_t)atoll(e);
+    }
     batch -= batch % (uint64_t)(kConsumerThreads * 4);
     if (batch > max_batch) batch = max_batch;
     if (batch < 1) batch = 1;
@@ -1538,7 +1554,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
         ka.tile_pairs = dp->k_tile_pairs;
         ka.stage_bytes = dp->k_stage_bytes;
         ka.npoints = dp->n;
-        ka.n_pivots = (int)std::min<size_t>(dp->n, (size_t)kDpxPivots);
+        ka.n_pivots = (int)std::min<size_t>(dp->n, (size_t)dpx_pivots());
         ka.pts = dp->pts;
         ka.dirs = dp->dirs;
         ka.count = count;
