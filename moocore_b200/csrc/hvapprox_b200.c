@@ -249,18 +249,24 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
     uint64_t batch = 0;
     uint64_t want = i1 - i0 ? i1 - i0 : 1;
     if ((values_out || dirs_out) && want > (1u << 22)) want = 1u << 22;
-    if (method != HVB200_METHOD_HW && want > (1u << 20)) want = 1u << 20;     /* host-fed streams: 1 Mi samples per upload */
+    if (method != HVB200_METHOD_HW && want > (1u << 20)) want = 1u << 20;     /* MC / Rphi streams: 1 Mi samples per batch */
     if (hvb200cu_run_begin(plan, stream, want, &batch)) return -1;
 
+    /* DZ2019-MC stream: generated on the device unless HVB200_MC=host asks for the host generator
+       (kept as an independent cross-check of the device generator) */
+    const char *mc_env = getenv("HVB200_MC");
+    const int mc_on_device = !(mc_env && !strcmp(mc_env, "host"));
     hvb200_hw_params hw;
     mt_stream mt;
     long double alpha[HVB200_MAXD];
     double u[HVB200_MAXD];
     if (method == HVB200_METHOD_HW) {
         hw_params_init(&hw, d, nsamples);
+    } else if (method == HVB200_METHOD_MC && mc_on_device) {
+        /* the stream is sequential: skip the normals of samples [0, i0) */
+        if (hvb200cu_mc_begin(plan, seed) || hvb200cu_mc_skip(plan, i0 * (uint64_t)d)) return -1;
     } else if (method == HVB200_METHOD_MC) {
         mt_seed(&mt, seed);
-        /* the stream is sequential: skip the normals of samples [0, i0) */
         for (uint64_t j = 0; j < i0; j++) for (int k = 0; k < d; k++) (void)zig_normal(&mt);
     } else if (method == HVB200_METHOD_RPHI) {
         rphi_alpha(alpha, d - 1);
@@ -276,6 +282,8 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
         const uint64_t cnt = (i1 - b0 < batch) ? i1 - b0 : batch;
         if (method == HVB200_METHOD_HW) {
             if (hvb200cu_gen_hw(plan, &hw, b0, cnt)) return -1;
+        } else if (method == HVB200_METHOD_MC && mc_on_device) {
+            if (hvb200cu_gen_mc_device(plan, cnt)) return -1;
         } else if (method == HVB200_METHOD_MC) {
             double *z = hvb200cu_staging(plan, cnt * (size_t)d);
             if (!z) return -1;

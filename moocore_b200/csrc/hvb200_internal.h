@@ -46,6 +46,10 @@ int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batc
 /* direction producers: fill the plan's direction buffer with `count` samples */
 int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
 int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count);     /* count*d normals */
+/* DZ2019-MC stream generated on the device: begin(seed), skip n normals, then per batch */
+int hvb200cu_mc_begin(struct hvb200_plan *plan, uint32_t seed);
+int hvb200cu_mc_skip(struct hvb200_plan *plan, uint64_t nnormals);
+int hvb200cu_gen_mc_device(struct hvb200_plan *plan, uint64_t count);
 int hvb200cu_gen_rphi(struct hvb200_plan *plan, const double *u_host, uint64_t count);         /* count*(d-1) u   */
 int hvb200cu_gen_uploaded(struct hvb200_plan *plan, const double *r_host, uint64_t count);     /* count*d r       */
 /* consume the direction buffer; values_host (optional) receives per-sample s^d */

@@ -37,6 +37,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <mutex>
 #include <algorithm>
 
 #include "hvb200_tables.h"
@@ -1104,7 +1105,9 @@ struct DevPlan {
     double *values = nullptr;    size_t values_cap = 0;
     double *out_hilo = nullptr;
     ull *counters = nullptr;     // [0] newton capped, [1] slow path
-    double *staging_host = nullptr; size_t staging_cap = 0;   // pinned
+    double *staging_host[2] = {nullptr, nullptr}; size_t staging_cap[2] = {0, 0};   // pinned, double-buffered
+    cudaEvent_t staging_free[2] = {nullptr, nullptr};   // recorded after the H2D copy out of buffer i
+    int staging_next = 0, staging_cur = 0;
     double *staging_dev = nullptr;  size_t staging_dev_cap = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int sm_count = 0;
@@ -1115,12 +1118,20 @@ struct DevPlan {
     std::vector<Span> spans;
     size_t ev_next = 0;
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr;
+    struct McGen *mc = nullptr;      // device generator of the DZ2019-MC stream (hvb200_mcgen.cuh)
 };
 
+static int span_begin(DevPlan *dp, int kind);
+static void span_end(DevPlan *dp, int b);
+#include "hvb200_mcgen.cuh"
+
+
 static bool g_const_ready[16] = {false};
+static std::mutex g_const_mutex;
 
 static int upload_constants(int device)
 {
+    std::lock_guard<std::mutex> lock(g_const_mutex);     // plans may be created from several host threads
     if (device < 16 && g_const_ready[device]) return 0;
     static double lead[HVB200_MAXD], h[HVB200_MAXD][kMaxFmTerms], Im[HVB200_MAXD];
     static int nh[HVB200_MAXD];
@@ -1339,10 +1350,14 @@ extern "C" void hvb200cu_plan_free(struct hvb200_plan *plan)
     cudaSetDevice(dp->device);
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev);
-    if (dp->staging_host) cudaFreeHost(dp->staging_host);
+    for (int i = 0; i < 2; i++) {
+        if (dp->staging_host[i]) cudaFreeHost(dp->staging_host[i]);
+        if (dp->staging_free[i]) cudaEventDestroy(dp->staging_free[i]);
+    }
     for (auto e : dp->ev_pool) cudaEventDestroy(e);
     if (dp->ev_h2d0) cudaEventDestroy(dp->ev_h2d0);
     if (dp->ev_h2d1) cudaEventDestroy(dp->ev_h2d1);
+    if (dp->mc) { mcgen_free(dp->mc); delete dp->mc; }
     if (dp->own_stream) cudaStreamDestroy(dp->own_stream);
     delete dp;
     plan->dev = nullptr;
@@ -1362,6 +1377,7 @@ static int span_begin(DevPlan *dp, int kind)
     return b;
 }
 static void span_end(DevPlan *dp, int b) { if (b >= 0) cudaEventRecord(dp->ev_pool[b], dp->stream); }
+
 
 extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batch, uint64_t *batch_out)
 {
@@ -1428,20 +1444,36 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     return 0;
 }
 
+// Pinned host staging for host-produced streams (MC normals, Rphi u, uploaded directions).
+// Two buffers alternate: the host fills buffer b+1 while the copy of buffer b is in flight; a buffer
+// is handed out again only after the event recorded behind its last H2D copy has completed.
 extern "C" double *hvb200cu_staging(struct hvb200_plan *plan, size_t ndoubles)
 {
     DevPlan *dp = (DevPlan *)plan->dev;
-    if (dp->staging_cap < ndoubles) {
-        if (dp->staging_host) cudaFreeHost(dp->staging_host);
-        dp->staging_host = nullptr; dp->staging_cap = 0;
-        if (cudaMallocHost(&dp->staging_host, ndoubles * sizeof(double)) != cudaSuccess) {
+    const int i = dp->staging_next;
+    dp->staging_next ^= 1;
+    dp->staging_cur = i;
+    if (dp->staging_free[i] == nullptr) {
+        if (cudaEventCreateWithFlags(&dp->staging_free[i], cudaEventDisableTiming) != cudaSuccess) {
+            hvb200_set_error("cudaEventCreate failed");
+            cudaGetLastError();
+            return nullptr;
+        }
+    } else if (cudaEventSynchronize(dp->staging_free[i]) != cudaSuccess) {
+        hvb200_set_error("cudaEventSynchronize(staging) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    if (dp->staging_cap[i] < ndoubles) {
+        if (dp->staging_host[i]) cudaFreeHost(dp->staging_host[i]);
+        dp->staging_host[i] = nullptr; dp->staging_cap[i] = 0;
+        if (cudaMallocHost(&dp->staging_host[i], ndoubles * sizeof(double)) != cudaSuccess) {
             hvb200_set_error("cudaMallocHost(%zu bytes) failed", ndoubles * sizeof(double));
             cudaGetLastError();
             return nullptr;
         }
-        dp->staging_cap = ndoubles;
+        dp->staging_cap[i] = ndoubles;
     }
-    return dp->staging_host;
+    return dp->staging_host[i];
 }
 
 static int stage_to_device(struct hvb200_plan *plan, DevPlan *dp, const double *host, size_t ndoubles)
@@ -1455,6 +1487,10 @@ static int stage_to_device(struct hvb200_plan *plan, DevPlan *dp, const double *
     const int b = span_begin(dp, 3);
     CUDA_TRY(cudaMemcpyAsync(dp->staging_dev, host, ndoubles * sizeof(double), cudaMemcpyHostToDevice, dp->stream));
     span_end(dp, b);
+    // the pinned buffer may be refilled once this copy has drained; a caller-owned (pageable) source is
+    // copied synchronously by the runtime, so the event is harmless there
+    if (host == dp->staging_host[dp->staging_cur] && dp->staging_free[dp->staging_cur])
+        CUDA_TRY(cudaEventRecord(dp->staging_free[dp->staging_cur], dp->stream));
     plan->stats.h2d_bytes += ndoubles * sizeof(double);
     return 0;
 }
@@ -1478,6 +1514,41 @@ extern "C" int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_h
 {
     DevPlan *dp = (DevPlan *)plan->dev;
     if (stage_to_device(plan, dp, normals_host, count * (size_t)dp->d)) return -1;
+    const int b = span_begin(dp, 1);
+    k_gen_mc<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->staging_dev, count, dp->d, dp->dirs);
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.dirgen_launches++;
+    return 0;
+}
+// DZ2019-MC with the stream generated on the device
+extern "C" int hvb200cu_mc_begin(struct hvb200_plan *plan, uint32_t seed)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (!dp->mc) dp->mc = new McGen();
+    return mcgen_begin(dp, dp->mc, seed);
+}
+extern "C" int hvb200cu_mc_skip(struct hvb200_plan *plan, uint64_t nnormals)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    while (nnormals) {
+        const uint64_t step = nnormals < (1ull << 24) ? nnormals : (1ull << 24);
+        if (mcgen_normals(plan, dp, dp->mc, step, nullptr)) return -1;
+        nnormals -= step;
+    }
+    return 0;
+}
+extern "C" int hvb200cu_gen_mc_device(struct hvb200_plan *plan, uint64_t count)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    const size_t ndoubles = count * (size_t)dp->d;
+    if (dp->staging_dev_cap < ndoubles) {
+        cudaFree(dp->staging_dev);
+        dp->staging_dev = nullptr; dp->staging_dev_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->staging_dev, ndoubles * sizeof(double)));
+        dp->staging_dev_cap = ndoubles;
+    }
+    if (mcgen_normals(plan, dp, dp->mc, ndoubles, dp->staging_dev)) return -1;
     const int b = span_begin(dp, 1);
     k_gen_mc<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->staging_dev, count, dp->d, dp->dirs);
     span_end(dp, b);

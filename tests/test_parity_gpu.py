@@ -287,3 +287,35 @@ def test_multi_gpu_single_process_matches_single(mb):
     finally:
         del os.environ["HVB200_NGPUS"]
     assert rel(a, b) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------
+# DZ2019-MC stream generated on the device (MT19937 + ziggurat, hvb200_mcgen.cuh)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [0, 1, 42, 2**32 - 1])
+def test_mc_device_stream_bit_exact_across_batches(mb, oracle, seed):
+    """Directions deep inside the stream (several internal batches, windows straddling the 2^20
+    sample batch boundary) must equal the oracle's bit for bit: same MT19937 words, same ziggurat
+    decisions, IEEE sqrt/div afterwards."""
+    from moocore_b200 import _api
+    d, N = 3, 2_500_000
+    for i0 in (0, (1 << 20) - 500, 2_400_000):
+        want = oracle_dirs(oracle, "DZ2019-MC", d, N, seed, i0, 1000)
+        got = _api.directions("DZ2019-MC", d, N, seed, i0, 1000)
+        assert np.array_equal(got, want), (seed, i0)
+
+
+def test_mc_device_equals_host_generator(mb, monkeypatch):
+    x, ref, maxi = hvcases.config_inputs("cfg2")
+    a = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=7, method="DZ2019-MC")
+    monkeypatch.setenv("HVB200_MC", "host")
+    b = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=7, method="DZ2019-MC")
+    assert a == b
+
+
+def test_mc_many_dimensions_stream(mb, oracle):
+    """d = 31 consumes 31 normals per sample: checks the normal -> (sample, objective) mapping."""
+    from moocore_b200 import _api
+    want = oracle_dirs(oracle, "DZ2019-MC", 31, 200_000, 123, 150_000, 2000)
+    got = _api.directions("DZ2019-MC", 31, 200_000, 123, 150_000, 2000)
+    assert np.array_equal(got, want)
