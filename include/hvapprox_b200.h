@@ -100,6 +100,10 @@ MOOCORE_API int hvb200_directions(int method, dimension_t nobjs, uint_fast32_t n
 MOOCORE_API int hvb200_plan_run_directions(hvb200_plan *plan, const double *r_host, uint64_t count,
                                            double *values_out, double out_hilo[2]);
 
+/* Host-only parity/debug: the Rphi-FWE+ u-sequence (c/hvapprox.c:741-747) of samples [i0, i0+count),
+ * count x (nobjs-1) doubles row-major, as produced by the library (one host thread per objective). */
+MOOCORE_API int hvb200_rphi_sequence(dimension_t nobjs, uint64_t i0, uint64_t count, double *u_out);
+
 /* Single-process multi-GPU: evaluate one estimate sharded over `ndevices` GPUs
  * (devices 0..ndevices-1, contiguous index ranges, partial sums combined with one NCCL
  * all-gather when libnccl can be loaded, else by per-device copies). */

@@ -232,6 +232,107 @@ static void rphi_alpha(long double *alpha, int ldim)
     for (int k = 1; k < ldim; k++) alpha[k] = alpha[k - 1] * hvb200_rho[ldim];
 }
 
+/* Rphi_next (c/hvapprox.c:741-747): u <- (double) fractl(u + alpha), a sequential recurrence in x87
+ * long double that is rounded to double at every step.  It is carried in 64-bit fixed point here:
+ *   - alpha = rho^(k+1) >= rho^m = phi/(phi+1) > 0.5, so alpha = M * 2^-64 with M its 64-bit mantissa;
+ *   - every state is a multiple of 2^-64 (0.5 is; an x87 sum of two such numbers rounds to a multiple of
+ *     2^-64 or 2^-63; rounding to 53 bits only coarsens the grid), so U = u * 2^64 is an integer;
+ *   - S = U + M exactly (65 bits).  S < 2^64: the x87 sum is exact and frac = S.  S >= 2^64: the sum
+ *     has 65 significant bits and is rounded to nearest-even at bit 0, frac = sum - 1;
+ *   - u' = RN53(frac): round the integer to 53 significant bits, ties to even.  A round-up to 2^64
+ *     (u' == 1.0) is kept as the 65-bit value so that the next sum is still exact.
+ * Checked bit-for-bit against the native x87 recurrence (tests/test_abi_cpu.py); ~3x faster than x87
+ * per step and free of libm calls. */
+static inline unsigned __int128 rphi_step_fixed(unsigned __int128 U, uint64_t M)
+{
+    const unsigned __int128 S = U + M;                       /* U <= 2^64, M < 2^64 */
+    uint64_t F;
+    if ((uint64_t)(S >> 64)) {
+        unsigned __int128 q = S >> 1;                        /* sum = S * 2^-64 in [1, 2.x): 64-bit mantissa = S >> 1 */
+        if ((uint64_t)S & 1u) q += (uint64_t)q & 1u;         /* ties to even */
+        /* q * 2^-63 in [1, 2]: frac.  q == 2^64 (sum rounded to 2.0) gives frac 0; U = 2^64 with M >= 2^63
+           gives sums in [1.5, 2) as well, so one subtraction of 2^63 is always enough below 2^64 */
+        if ((uint64_t)(q >> 64)) return 0;
+        F = ((uint64_t)q - ((uint64_t)1 << 63)) << 1;
+    } else {
+        F = (uint64_t)S;
+    }
+    if (F >> 53) {                                           /* more than 53 significant bits: RNE */
+        const int r = 11 - __builtin_clzll(F);               /* bits to drop, 1..11 */
+        const uint64_t unit = (uint64_t)1 << r, half = unit >> 1, low = F & (unit - 1);
+        uint64_t hi = F - low;
+        if (low > half || (low == half && (hi & unit))) {
+            const uint64_t up = hi + unit;
+            if (up < hi) return (unsigned __int128)1 << 64;  /* rounded up to 1.0 */
+            hi = up;
+        }
+        F = hi;
+    }
+    return F;
+}
+static void rphi_mantissas(uint64_t *M, int ldim)
+{
+    long double alpha[HVB200_MAXD];
+    rphi_alpha(alpha, ldim);
+    for (int k = 0; k < ldim; k++) memcpy(&M[k], &alpha[k], 8);       /* x87: low 8 bytes = explicit 64-bit mantissa */
+}
+static inline double rphi_to_double(unsigned __int128 U)
+{
+    return (uint64_t)(U >> 64) ? 1.0 : (double)(uint64_t)U * 0x1p-64;   /* exact: U has <= 53 significant bits */
+}
+typedef struct { unsigned __int128 U; uint64_t M; uint64_t steps; double *out; size_t stride; } rphi_job;
+static void *rphi_worker(void *arg)
+{
+    rphi_job *j = arg;
+    unsigned __int128 U = j->U;
+    const uint64_t M = j->M;
+    if (j->out) {
+        double *o = j->out;
+        for (uint64_t i = 0; i < j->steps; i++, o += j->stride) { U = rphi_step_fixed(U, M); *o = rphi_to_double(U); }
+    } else {
+        for (uint64_t i = 0; i < j->steps; i++) U = rphi_step_fixed(U, M);
+    }
+    j->U = U;
+    return NULL;
+}
+/* Advance all ldim sequences by `steps`; out (optional) receives u_k at step i in out[k*steps + i]
+ * (one contiguous run per objective: no cache line is shared between the writer threads).  The
+ * sequences of different objectives are independent: one host thread each when there is enough work. */
+static void rphi_advance(unsigned __int128 *u, const uint64_t *M, int ldim, uint64_t steps, double *out)
+{
+    rphi_job jobs[HVB200_MAXD];
+    pthread_t th[HVB200_MAXD];
+    for (int k = 0; k < ldim; k++) {
+        jobs[k].U = u[k]; jobs[k].M = M[k]; jobs[k].steps = steps;
+        jobs[k].out = out ? out + (size_t)k * steps : NULL; jobs[k].stride = 1;
+    }
+    const int threaded = steps * (uint64_t)ldim >= 65536 && ldim > 1;
+    int started[HVB200_MAXD] = {0};
+    for (int k = 0; k < ldim; k++) {
+        if (threaded && pthread_create(&th[k], NULL, rphi_worker, &jobs[k]) == 0) started[k] = 1;
+        else rphi_worker(&jobs[k]);
+    }
+    for (int k = 0; k < ldim; k++) { if (started[k]) pthread_join(th[k], NULL); u[k] = jobs[k].U; }
+}
+/* Host-only debug/parity entry: the u-sequence of Rphi-FWE+ for samples [i0, i0+count). */
+int hvb200_rphi_sequence(dimension_t nobjs, uint64_t i0, uint64_t count, double *u_out)
+{
+    const int ldim = (int)nobjs - 1;
+    if (ldim < 1 || ldim > HVB200_MAXM) { hvb200_set_error("nobjs outside [2, %d]", HVB200_MAXM + 1); return -2; }
+    uint64_t M[HVB200_MAXD];
+    unsigned __int128 u[HVB200_MAXD];
+    rphi_mantissas(M, ldim);
+    for (int k = 0; k < ldim; k++) u[k] = (unsigned __int128)1 << 63;       /* seed 0.5, c/hvapprox.c:847-849 */
+    rphi_advance(u, M, ldim, i0, NULL);
+    double *soa = malloc((count ? count : 1) * (size_t)ldim * sizeof *soa);
+    if (!soa) { hvb200_set_error("out of host memory"); return -4; }
+    rphi_advance(u, M, ldim, count, soa);
+    for (uint64_t i = 0; i < count; i++)
+        for (int k = 0; k < ldim; k++) u_out[i * (size_t)ldim + k] = soa[(size_t)k * count + i];
+    free(soa);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* run                                                                                         */
 /* ------------------------------------------------------------------------------------------ */
@@ -246,20 +347,22 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
         hvb200_set_error("DZ2019-HW supports at most %d objectives", MOOCORE_HVAPPROX_DIMENSION_MAX + 1);
         return -2;
     }
-    uint64_t batch = 0;
-    uint64_t want = i1 - i0 ? i1 - i0 : 1;
-    if ((values_out || dirs_out) && want > (1u << 22)) want = 1u << 22;
-    if (method != HVB200_METHOD_HW && want > (1u << 20)) want = 1u << 20;     /* MC / Rphi streams: 1 Mi samples per batch */
-    if (hvb200cu_run_begin(plan, stream, want, &batch)) return -1;
-
     /* DZ2019-MC stream: generated on the device unless HVB200_MC=host asks for the host generator
        (kept as an independent cross-check of the device generator) */
     const char *mc_env = getenv("HVB200_MC");
     const int mc_on_device = !(mc_env && !strcmp(mc_env, "host"));
+    uint64_t batch = 0;
+    uint64_t want = i1 - i0 ? i1 - i0 : 1;
+    if ((values_out || dirs_out) && want > (1u << 22)) want = 1u << 22;
+    if (method != HVB200_METHOD_HW && want > (1u << 20)) want = 1u << 20;     /* MC stream: 1 Mi samples per batch */
+    /* host-fed streams: smaller batches so that producing batch b+1 overlaps the GPU work on batch b */
+    if ((method == HVB200_METHOD_RPHI || (method == HVB200_METHOD_MC && !mc_on_device)) && want > (1u << 18)) want = 1u << 18;
+    if (hvb200cu_run_begin(plan, stream, want, &batch)) return -1;
+
     hvb200_hw_params hw;
     mt_stream mt;
-    long double alpha[HVB200_MAXD];
-    double u[HVB200_MAXD];
+    uint64_t rphi_M[HVB200_MAXD];
+    unsigned __int128 u[HVB200_MAXD];
     if (method == HVB200_METHOD_HW) {
         hw_params_init(&hw, d, nsamples);
     } else if (method == HVB200_METHOD_MC && mc_on_device) {
@@ -269,10 +372,9 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
         mt_seed(&mt, seed);
         for (uint64_t j = 0; j < i0; j++) for (int k = 0; k < d; k++) (void)zig_normal(&mt);
     } else if (method == HVB200_METHOD_RPHI) {
-        rphi_alpha(alpha, d - 1);
-        for (int k = 0; k < d - 1; k++) u[k] = 0.5;
-        for (uint64_t j = 0; j < i0; j++)
-            for (int k = 0; k < d - 1; k++) { const long double v = u[k] + alpha[k]; u[k] = (double)(v - truncl(v)); }
+        rphi_mantissas(rphi_M, d - 1);
+        for (int k = 0; k < d - 1; k++) u[k] = (unsigned __int128)1 << 63;       /* seed 0.5 */
+        rphi_advance(u, rphi_M, d - 1, i0, NULL);
     } else {
         hvb200_set_error("unknown method %d", method);
         return -2;
@@ -292,12 +394,7 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
         } else {
             double *uu = hvb200cu_staging(plan, cnt * (size_t)(d - 1));
             if (!uu) return -1;
-            for (uint64_t j = 0; j < cnt; j++)
-                for (int k = 0; k < d - 1; k++) {
-                    const long double v = u[k] + alpha[k];
-                    u[k] = (double)(v - truncl(v));
-                    uu[j * (size_t)(d - 1) + k] = u[k];
-                }
+            rphi_advance(u, rphi_M, d - 1, cnt, uu);
             if (hvb200cu_gen_rphi(plan, uu, cnt)) return -1;
         }
         if (dirs_out && hvb200cu_read_dirs(plan, cnt, dirs_out + (b0 - i0) * (size_t)d)) return -1;

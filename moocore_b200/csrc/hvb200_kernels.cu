@@ -1002,7 +1002,9 @@ __global__ void __launch_bounds__(128) k_gen_rphi(const double *__restrict__ uu,
     const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
     const double HALF_PI = 1.57079632679489661923;
-    const double *u = uu + j * (ull)(d - 1);
+    // uu is objective-major: u_k of sample j at uu[k * count + j] (coalesced; the host writes one
+    // contiguous run per objective)
+    auto u = [&](int k) { return uu[(ull)k * count + j]; };
     double *out = dirs + j * (ull)(2 * d);
     double prod = 1.0;
     const int pairs = d / 2 - 1;
@@ -1013,21 +1015,21 @@ __global__ void __launch_bounds__(128) k_gen_rphi(const double *__restrict__ uu,
     };
     for (int i = 0; i < pairs; i++) {
         const int l = d - 2 * i - 2;
-        const double t = pow(u[l - 1], 1.0 / l);
+        const double t = pow(u(l - 1), 1.0 / l);
         const double dl = sqrt(1.0 - t * t) * prod;
         prod *= t;
         double sa, ca;
-        sincos(HALF_PI * u[l], &sa, &ca);
+        sincos(HALF_PI * u(l), &sa, &ca);
         emit(2 * i, dl * sa);
         emit(2 * i + 1, dl * ca);
     }
     double ang;
     if (d % 2 == 0) {
-        ang = HALF_PI * u[0];
+        ang = HALF_PI * u(0);
     } else {
-        emit(d - 3, prod * u[0]);
-        prod *= sqrt(1 - u[0] * u[0]);
-        ang = HALF_PI * u[1];
+        emit(d - 3, prod * u(0));
+        prod *= sqrt(1 - u(0) * u(0));
+        ang = HALF_PI * u(1);
     }
     double sa, ca;
     sincos(ang, &sa, &ca);
@@ -1094,13 +1096,15 @@ struct DevPlan {
     int R = 1, G = 2;
     int staged = 0, stage_bytes = 0;
     size_t smem_bytes = 0;
-    double *pts = nullptr;
-    unsigned *keys = nullptr;            // DPX screen: packed 16-bit keys
+    double *pts = nullptr;   size_t pts_cap = 0;       // doubles
+    unsigned *keys = nullptr; size_t keys_cap = 0;     // DPX screen: packed 16-bit keys (words)
+    double *qdev = nullptr;              // 3 x 32 doubles: quantisation parameters for k_quantize
+    bool resources_ready = false;        // stream / events / small buffers exist (workspace reuse)
     int k_tile_pairs = 0, k_n_tiles = 0, k_stage_bytes = 0;
     size_t k_smem_bytes = 0;
     int kR = 1, kG = 2;
     double qlo[32] = {0}, qhi[32] = {0}, qscale[32] = {0};
-    double *dirs = nullptr;      size_t dirs_cap = 0;      // samples
+    double *dirs = nullptr;      size_t dirs_cap = 0;      // doubles (the workspace may serve plans of different d)
     double *cta_sums = nullptr;  int cta_cap = 0;
     double *values = nullptr;    size_t values_cap = 0;
     double *out_hilo = nullptr;
@@ -1263,11 +1267,43 @@ static KernelCfg cfg_runtime(int d)
     return cfg_for(d);
 }
 
+// Workspace cache: a DevPlan keeps its device buffers, stream and events when its plan is destroyed
+// and is handed to the next plan created on the same device, so that repeated hv_approx calls (the
+// common use: one call per generation of an optimiser) pay cudaMalloc/cudaFree only once.
+// HVB200_NO_CACHE=1 disables it; at most kPoolMax workspaces are kept per device.
+static std::mutex g_pool_mutex;
+static std::vector<DevPlan *> g_pool[16];
+static constexpr size_t kPoolMax = 4;
+static bool pool_enabled()
+{
+    const char *e = getenv("HVB200_NO_CACHE");
+    return !(e && e[0] == '1');
+}
+static DevPlan *pool_take(int device)
+{
+    if (device < 0 || device >= 16 || !pool_enabled()) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool[device].empty()) return nullptr;
+    DevPlan *dp = g_pool[device].back();
+    g_pool[device].pop_back();
+    return dp;
+}
+static void devplan_release(DevPlan *dp);
+static bool pool_give(DevPlan *dp)
+{
+    if (dp->device < 0 || dp->device >= 16 || !pool_enabled()) return false;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool[dp->device].size() >= kPoolMax) return false;
+    g_pool[dp->device].push_back(dp);
+    return true;
+}
+
 extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host)
 {
     CUDA_TRY(cudaSetDevice(plan->device));
     if (upload_constants(plan->device)) return -1;
-    DevPlan *dp = new DevPlan();
+    DevPlan *dp = pool_take(plan->device);
+    if (!dp) dp = new DevPlan();
     plan->dev = dp;
     dp->device = plan->device;
     dp->d = plan->d;
@@ -1292,9 +1328,29 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
     dp->smem_bytes = (size_t)kStages * dp->stage_bytes + dir_bytes + kBarrierBytes;
     dp->n_tiles = (int)((plan->n + tp - 1) / tp);
     const size_t padded = (size_t)dp->n_tiles * tp * d;
-    CUDA_TRY(cudaMalloc(&dp->pts, padded * sizeof(double)));
-    CUDA_TRY(cudaMemset(dp->pts, 0, padded * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(dp->pts, pts_host, plan->n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice));
+    if (!dp->resources_ready) {
+        CUDA_TRY(cudaMalloc(&dp->out_hilo, 2 * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&dp->counters, 2 * sizeof(ull)));
+        CUDA_TRY(cudaMalloc(&dp->qdev, 3 * 32 * sizeof(double)));
+        CUDA_TRY(cudaStreamCreateWithFlags(&dp->own_stream, cudaStreamNonBlocking));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, plan->device));
+        dp->sm_count = prop.multiProcessorCount;
+        CUDA_TRY(cudaEventCreate(&dp->ev_h2d0));
+        CUDA_TRY(cudaEventCreate(&dp->ev_h2d1));
+        dp->resources_ready = true;
+    }
+    cudaStream_t us = dp->own_stream;
+    if (dp->pts_cap < padded) {
+        cudaFree(dp->pts);
+        dp->pts = nullptr; dp->pts_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->pts, padded * sizeof(double)));
+        dp->pts_cap = padded;
+    }
+    // zero only the padding rows behind the real points
+    CUDA_TRY(cudaMemcpyAsync(dp->pts, pts_host, plan->n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice, us));
+    if (padded > plan->n * (size_t)d)
+        CUDA_TRY(cudaMemsetAsync(dp->pts + plan->n * (size_t)d, 0, (padded - plan->n * (size_t)d) * sizeof(double), us));
     if (d <= 32) {
         // ---- DPX keys: per-objective range of the point set, monotone 16-bit quantisation on the device
         for (int k = 0; k < d; k++) { dp->qlo[k] = INFINITY; dp->qhi[k] = -INFINITY; }
@@ -1320,26 +1376,25 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
         dp->k_stage_bytes = (int)((((size_t)tpairs * d * 4) + 127) & ~(size_t)127);
         dp->k_smem_bytes = (size_t)kStages * dp->k_stage_bytes + kBarrierBytes + (size_t)dpx_pivots() * d * sizeof(double);
         const size_t total_pairs = (size_t)dp->k_n_tiles * tpairs;
-        CUDA_TRY(cudaMalloc(&dp->keys, total_pairs * d * sizeof(unsigned)));
-        double *qdev = nullptr;
-        CUDA_TRY(cudaMalloc(&qdev, 3 * 32 * sizeof(double)));
-        CUDA_TRY(cudaMemcpy(qdev, dp->qlo, 32 * sizeof(double), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(qdev + 32, dp->qhi, 32 * sizeof(double), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(qdev + 64, dp->qscale, 32 * sizeof(double), cudaMemcpyHostToDevice));
         const ull words = (ull)total_pairs * d;
-        k_quantize<<<(unsigned)((words + 255) / 256), 256>>>(dp->pts, (ull)plan->n, d, tpairs, (ull)total_pairs, qdev, qdev + 32, qdev + 64, dp->keys);
+        if (dp->keys_cap < words) {
+            cudaFree(dp->keys);
+            dp->keys = nullptr; dp->keys_cap = 0;
+            CUDA_TRY(cudaMalloc(&dp->keys, words * sizeof(unsigned)));
+            dp->keys_cap = words;
+        }
+        double *qdev = dp->qdev;
+        double qhost[96];
+        memcpy(qhost, dp->qlo, 32 * sizeof(double));
+        memcpy(qhost + 32, dp->qhi, 32 * sizeof(double));
+        memcpy(qhost + 64, dp->qscale, 32 * sizeof(double));
+        CUDA_TRY(cudaMemcpyAsync(qdev, qhost, sizeof qhost, cudaMemcpyHostToDevice, us));
+        k_quantize<<<(unsigned)((words + 255) / 256), 256, 0, us>>>(dp->pts, (ull)plan->n, d, tpairs, (ull)total_pairs, qdev, qdev + 32, qdev + 64, dp->keys);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaDeviceSynchronize());
-        cudaFree(qdev);
     }
-    CUDA_TRY(cudaMalloc(&dp->out_hilo, 2 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&dp->counters, 2 * sizeof(ull)));
-    CUDA_TRY(cudaStreamCreateWithFlags(&dp->own_stream, cudaStreamNonBlocking));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, plan->device));
-    dp->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(cudaEventCreate(&dp->ev_h2d0));
-    CUDA_TRY(cudaEventCreate(&dp->ev_h2d1));
+    // pts_host and qhost are caller/stack memory: the copies must have left them before returning; later
+    // runs may use another stream, so everything issued here is complete when the plan is handed out
+    CUDA_TRY(cudaStreamSynchronize(us));
     return 0;
 }
 
@@ -1347,9 +1402,16 @@ extern "C" void hvb200cu_plan_free(struct hvb200_plan *plan)
 {
     DevPlan *dp = (DevPlan *)plan->dev;
     if (!dp) return;
+    plan->dev = nullptr;
     cudaSetDevice(dp->device);
+    // all work of the plan is complete here (every run ends with a stream synchronisation)
+    if (dp->resources_ready && pool_give(dp)) return;
+    devplan_release(dp);
+}
+static void devplan_release(DevPlan *dp)
+{
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
-    cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev);
+    cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
     for (int i = 0; i < 2; i++) {
         if (dp->staging_host[i]) cudaFreeHost(dp->staging_host[i]);
         if (dp->staging_free[i]) cudaEventDestroy(dp->staging_free[i]);
@@ -1360,7 +1422,6 @@ extern "C" void hvb200cu_plan_free(struct hvb200_plan *plan)
     if (dp->mc) { mcgen_free(dp->mc); delete dp->mc; }
     if (dp->own_stream) cudaStreamDestroy(dp->own_stream);
     delete dp;
-    plan->dev = nullptr;
 }
 
 static int span_begin(DevPlan *dp, int kind)
@@ -1397,11 +1458,11 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     batch -= batch % (uint64_t)(kConsumerThreads * 4);
     if (batch > max_batch) batch = max_batch;
     if (batch < 1) batch = 1;
-    if (dp->dirs_cap < batch) {
+    if (dp->dirs_cap < batch * (size_t)(2 * d)) {
         cudaFree(dp->dirs);
         dp->dirs = nullptr; dp->dirs_cap = 0;
         CUDA_TRY(cudaMalloc(&dp->dirs, batch * (size_t)(2 * d) * sizeof(double)));
-        dp->dirs_cap = batch;
+        dp->dirs_cap = batch * (size_t)(2 * d);
     }
     *batch_out = batch;
 

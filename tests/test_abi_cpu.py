@@ -109,3 +109,20 @@ def test_product_does_not_reference_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", os.path.join(pkg, "libmoocore_b200.so")], capture_output=True, text=True).stdout
     assert "hvoracle" not in out and "hvref" not in out
+
+
+@pytest.mark.parametrize("d", [2, 3, 4, 5, 8, 10, 16, 20, 31, 32])
+def test_rphi_integer_recurrence_matches_x87(mb, oracle, d):
+    """hvb200_rphi_sequence (the library's threaded-per-objective host recurrence, objective-major
+    output) against the oracle's sequential recurrence: bit-exact, deep into the sequence."""
+    import ctypes
+    from util import P
+    L = mb.lib
+    L.hvb200_rphi_sequence.restype = ctypes.c_int
+    L.hvb200_rphi_sequence.argtypes = [ctypes.c_uint8, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double)]
+    for i0, cnt in ((0, 5000), (300_000, 40_000)):
+        got = np.zeros((cnt, d - 1))
+        assert L.hvb200_rphi_sequence(d, i0, cnt, P(got)) == 0
+        want = np.zeros((cnt, d - 1))
+        oracle.orc_rphi_window(None, ctypes.c_size_t(0), d, ctypes.c_uint64(i0), ctypes.c_uint64(cnt), None, None, P(want))
+        assert np.array_equal(got, want), (d, i0)
