@@ -14,17 +14,21 @@
 // Kernels:
 //   k_gen_hw      one thread per sample: x87-exact lattice point (integer emulation of the
 //                 reference's long double arithmetic), d-1 Newton solves in FP64, polar->cartesian
-//   k_gen_mc      normals (host MT19937+ziggurat stream) -> |z|, clamp, norm, r = norm/|z|
-//   k_gen_rphi    u (host recurrence) -> Fang-Wang map -> r = 1/w
+//   k_mt_generate, k_zig_*   (hvb200_mcgen.cuh) the reference's MT19937+ziggurat normal stream, bit-exact
+//   k_gen_mc      normals -> |z|, clamp, norm, r = norm/|z|
+//   k_gen_rphi    u (host fixed-point recurrence) -> Fang-Wang map -> r = 1/w
 //   k_prep_r      uploaded r -> winv
 //   k_maxmin      persistent CTAs; a producer warp streams point tiles into shared memory with
-//                 TMA bulk copies (cp.async.bulk + mbarrier, multi-stage); 256 consumer threads
+//                 TMA bulk copies (cp.async.bulk + mbarrier, multi-stage); 224 consumer threads
 //                 own R directions each and sweep every tile.
 //                   EXACT : d DMUL + d min per sample*point, 1 max             (2d+1 FP64 ops)
 //                   SCREEN: per element one DSETP against a per-direction threshold
 //                           T_k < best/r_k (predicate chain); only candidates that may raise the
 //                           running max are evaluated with the EXACT arithmetic.  max/min are
 //                           exact and order-free, so both give bit-identical s.
+//   k_maxmin_dpx  the same screen on conservatively quantised 16-bit keys with DPX VIADDMNMX.S16x2
+//                 (two elements per instruction, no predicates); default for n' >= 256
+//   k_quantize    point keys for k_maxmin_dpx
 //   k_reduce      fixed-shape pairwise tree over CTA partial sums in double-double -> (hi, lo)
 //
 // No tensor cores: max-min is a semiring, not a contraction.  Compiled with -fmad=false so that
