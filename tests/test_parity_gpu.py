@@ -319,3 +319,41 @@ def test_mc_many_dimensions_stream(mb, oracle):
     want = oracle_dirs(oracle, "DZ2019-MC", 31, 200_000, 123, 150_000, 2000)
     got = _api.directions("DZ2019-MC", 31, 200_000, 123, 150_000, 2000)
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------
+# small-N and large-n edges
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 33, 1000])
+@pytest.mark.parametrize("d", [2, 3, 10])
+def test_tiny_sample_counts(mb, oracle, N, d):
+    """nsamples = 1 makes the only DZ2019-HW sample the all-zero 'last point' (c/hvapprox.c:300-303),
+    whose angles are the reference's zero-target artefacts; small N also exercises partial chunks."""
+    x = hvcases.front("sphere", 300, d, 50 + d)
+    for method in METHODS:
+        got = mb.hv_approx(x, ref=1.1, nsamples=N, seed=5, method=method)
+        want = estimate(oracle, "orc_", method, x, 1.1, False, N, 5)
+        assert rel(got, want) <= TOL, (method, N, d, got, want)
+
+
+def test_large_point_set(mb, oracle):
+    """2e5 points x 4 objectives: many tiles per chunk, keys and FP64 points beyond L1."""
+    d, n = 4, 200_000
+    x = hvcases.front("sphere", n, d, 77)
+    tp = np.ascontiguousarray(1.1 - x)
+    r = oracle_dirs(oracle, "DZ2019-HW", d, 100_000, 0, 40_000, 48)
+    want = oracle_values(oracle, tp, r)
+    for kern in ("exact", "screen", "dpx"):
+        with mb.Plan(x, 1.1, kernel=kern) as plan:
+            vals, _ = plan.run_directions(r)
+            assert np.array_equal(vals, want), kern
+
+
+def test_plan_reuse_across_shapes(mb, oracle):
+    """The workspace cache hands device buffers from one plan to the next: interleave shapes."""
+    shapes = [(500, 3), (40, 12), (3000, 7), (10, 31), (500, 3)]
+    for n, d in shapes:
+        x = hvcases.front("random", n, d, n + d)
+        got = mb.hv_approx(x, ref=1.2, nsamples=5000, method="DZ2019-HW")
+        want = estimate(oracle, "orc_", "DZ2019-HW", x, 1.2, False, 5000)
+        assert rel(got, want) <= TOL, (n, d)
