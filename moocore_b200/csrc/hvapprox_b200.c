@@ -469,6 +469,7 @@ typedef struct {
     uint64_t nsamples, i0, i1; uint32_t seed;
     double hilo[2];
     int empty;
+    hvb200_plan *plan;      /* kept alive until the exchange step */
     char err[512];
 } shard_job;
 
@@ -481,7 +482,7 @@ static void *shard_main(void *arg)
     if (j->rc == 0 && !plan) { j->empty = 1; return NULL; }
     if (j->rc == 0) j->rc = hvb200_plan_run(plan, j->method, j->nsamples, j->seed, j->i0, j->i1, NULL, j->hilo);
     if (j->rc) snprintf(j->err, sizeof j->err, "%s", tls_error);
-    hvb200_plan_destroy(plan);
+    j->plan = plan;
     return NULL;
 }
 
@@ -514,13 +515,35 @@ double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, di
         for (int g = 0; g < ndevices; g++) pthread_join(th[g], NULL);
     }
     double pairs[32];
+    int failed = -1, empty = 0;
+    hvb200_plan *plans[16];
     for (int g = 0; g < ndevices; g++) {
-        if (jobs[g].rc) { hvb200_set_error("device %d: %s", g, jobs[g].err); return fail_nan("hv_approx"); }
-        if (jobs[g].empty) return 0.0;
+        if (jobs[g].rc && failed < 0) failed = g;
+        empty |= jobs[g].empty;
+        plans[g] = jobs[g].plan;
         pairs[2 * g] = jobs[g].hilo[0];
         pairs[2 * g + 1] = jobs[g].hilo[1];
     }
-    return hvb200_finalize(nobjs, nsamples, pairs, ndevices);
+    double result;
+    if (failed >= 0) {
+        hvb200_set_error("device %d: %s", failed, jobs[failed].err);
+        result = fail_nan("hv_approx");
+    } else if (empty) {
+        result = 0.0;
+    } else {
+        /* exchange step: one NCCL all-gather of the 16-byte partials over NVLink; every GPU ends up
+           with all pairs, device 0's copy is finalised (fixed order, long double).  Without NCCL the
+           host copies of the same pairs are used. */
+        if (ndevices > 1 && !getenv("HVB200_NO_NCCL")) {
+            double gathered[32];
+            const int rc = hvb200cu_nccl_allgather(plans, ndevices, gathered);
+            if (rc == 0) memcpy(pairs, gathered, 2 * (size_t)ndevices * sizeof(double));
+            else if (rc < 0) fprintf(stderr, "moocore_b200: NCCL exchange failed (%s); using host copies\n", tls_error);
+        }
+        result = hvb200_finalize(nobjs, nsamples, pairs, ndevices);
+    }
+    for (int g = 0; g < ndevices; g++) hvb200_plan_destroy(jobs[g].plan);
+    return result;
 }
 
 static int env_ndevices(void)

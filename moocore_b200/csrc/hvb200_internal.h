@@ -61,6 +61,9 @@ int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2]);
 /* pinned staging buffer for host-produced streams (MC normals, Rphi u); grows on demand */
 double *hvb200cu_staging(struct hvb200_plan *plan, size_t ndoubles);
 
+/* one NCCL all-gather of the plans' (hi, lo) device results; 1 = NCCL unavailable, 0 = ok, -1 = error */
+int hvb200cu_nccl_allgather(struct hvb200_plan **plans, int n, double *pairs_out);
+
 double hvb200cu_measure_fp64(int device, double *dmul_per_s, double *dsetp_per_s);
 
 #ifdef __cplusplus

@@ -1747,6 +1747,90 @@ extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-process multi-GPU exchange step: one NCCL all-gather of the per-GPU (hi, lo) pairs over
+// NVLink.  libnccl is opened lazily with dlopen (no link-time dependency: a process that already
+// loaded PyTorch's bundled NCCL gets that copy; without NCCL the caller combines the host copies).
+// ------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace {
+typedef void *nccl_comm_t;
+struct NcclApi {
+    int (*CommInitAll)(nccl_comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false, tried = false;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+int g_nccl_ndev = 0;
+nccl_comm_t g_nccl_comms[16];
+double *g_nccl_gather[16] = {nullptr};
+
+bool nccl_load()
+{
+    if (g_nccl.tried) return g_nccl.ok;
+    g_nccl.tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    g_nccl.CommInitAll = (int (*)(nccl_comm_t *, int, const int *))dlsym(h, "ncclCommInitAll");
+    g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.CommInitAll && g_nccl.AllGather && g_nccl.GroupStart && g_nccl.GroupEnd;
+    return g_nccl.ok;
+}
+}  // namespace
+
+// All-gather the (hi, lo) results of `n` plans (plan g on device g, results still in device memory
+// after hvb200cu_run_end) and return the 2n doubles of device 0's copy.  Returns 1 if NCCL is not
+// available (caller falls back to the host copies), -1 on error, 0 on success.
+extern "C" int hvb200cu_nccl_allgather(struct hvb200_plan **plans, int n, double *pairs_out)
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (n < 2 || n > 16 || !nccl_load()) return 1;
+    if (g_nccl_ndev != n) {
+        if (g_nccl_ndev) {
+            for (int g = 0; g < g_nccl_ndev; g++) {
+                if (g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl_comms[g]);
+                cudaSetDevice(g); cudaFree(g_nccl_gather[g]); g_nccl_gather[g] = nullptr;
+            }
+            g_nccl_ndev = 0;
+        }
+        int devs[16];
+        for (int g = 0; g < n; g++) devs[g] = g;
+        const int rc = g_nccl.CommInitAll(g_nccl_comms, n, devs);
+        if (rc != 0) { hvb200_set_error("ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return -1; }
+        for (int g = 0; g < n; g++) {
+            CUDA_TRY(cudaSetDevice(g));
+            CUDA_TRY(cudaMalloc(&g_nccl_gather[g], 2 * 16 * sizeof(double)));
+        }
+        g_nccl_ndev = n;
+    }
+    g_nccl.GroupStart();
+    for (int g = 0; g < n; g++) {
+        DevPlan *dp = (DevPlan *)plans[g]->dev;
+        const int rc = g_nccl.AllGather(dp->out_hilo, g_nccl_gather[g], 2, 8 /* ncclFloat64 */, g_nccl_comms[g], dp->own_stream);
+        if (rc != 0) { g_nccl.GroupEnd(); hvb200_set_error("ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return -1; }
+    }
+    const int rc = g_nccl.GroupEnd();
+    if (rc != 0) { hvb200_set_error("ncclGroupEnd: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return -1; }
+    for (int g = 0; g < n; g++) {
+        DevPlan *dp = (DevPlan *)plans[g]->dev;
+        CUDA_TRY(cudaSetDevice(g));
+        CUDA_TRY(cudaStreamSynchronize(dp->own_stream));
+    }
+    CUDA_TRY(cudaSetDevice(0));
+    CUDA_TRY(cudaMemcpy(pairs_out, g_nccl_gather[0], 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" double hvb200cu_measure_fp64(int device, double *dmul_per_s, double *dsetp_per_s)
 {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -1.0; }
