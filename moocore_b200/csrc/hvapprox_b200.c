@@ -380,9 +380,19 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
         return -2;
     }
 
+    /* DZ2019-HW sums: the generator of the next batch overlaps the max-min kernel of this one */
+    /* (opt-in, HVB200_PIPELINE=1: measured neutral on B200 — the generator and the max-min kernel compete
+       for the same issue slots, 669 vs 671 ms per cfg3 step) */
+    const int hw_pipelined = method == HVB200_METHOD_HW && !dirs_out && !values_out && plan->n && getenv("HVB200_PIPELINE") != NULL;
+    if (hw_pipelined && i0 < i1 && hvb200cu_hw_prefetch(plan, &hw, i0, (i1 - i0 < batch) ? i1 - i0 : batch)) return -1;
+
     for (uint64_t b0 = i0; b0 < i1; b0 += batch) {
         const uint64_t cnt = (i1 - b0 < batch) ? i1 - b0 : batch;
-        if (method == HVB200_METHOD_HW) {
+        if (hw_pipelined) {
+            if (hvb200cu_hw_swap(plan)) return -1;
+            const uint64_t nb = b0 + batch;
+            if (nb < i1 && hvb200cu_hw_prefetch(plan, &hw, nb, (i1 - nb < batch) ? i1 - nb : batch)) return -1;
+        } else if (method == HVB200_METHOD_HW) {
             if (hvb200cu_gen_hw(plan, &hw, b0, cnt)) return -1;
         } else if (method == HVB200_METHOD_MC && mc_on_device) {
             if (hvb200cu_gen_mc_device(plan, cnt)) return -1;

@@ -45,6 +45,9 @@ void hvb200cu_plan_free(struct hvb200_plan *plan);
 int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batch, uint64_t *batch_out);
 /* direction producers: fill the plan's direction buffer with `count` samples */
 int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
+/* pipelined DZ2019-HW: generate a batch on a second stream into the spare direction buffer, then swap */
+int hvb200cu_hw_prefetch(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
+int hvb200cu_hw_swap(struct hvb200_plan *plan);
 int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count);     /* count*d normals */
 /* DZ2019-MC stream generated on the device: begin(seed), skip n normals, then per batch */
 int hvb200cu_mc_begin(struct hvb200_plan *plan, uint32_t seed);

@@ -471,20 +471,22 @@ struct DpxArgs {
     double *cta_sums;
     double *values;
     ull *slow_counter;
-    double qlo[32], qhi[32], qscale[32];
+    double qscale[32], qlos[32];     // key map: scale_k and lo_k*scale_k*(1+2^-20)+2^-10 (see dpx_neg_key)
 };
 
-__device__ __forceinline__ unsigned dpx_neg_key(double T, double lo, double hi, double scale)
+// Threshold key of objective k for a running max `best_m` = best*(1-2^-20):
+//   x  = best_m * winv_k * scale_k - (lo_k*scale_k*(1+2^-20) + 2^-10)      <=  f_k(T_k) - margin,
+//   KT = clamp(floor(x), 0, S+1)
+// where T_k = best*winv_k*(1-2^-50) is the FP64 screen threshold.  The margin (>= 2^-21 relative,
+// 2^-10 absolute in key units) dominates every rounding error of the two evaluations of f_k (each
+// <= 2^-50 relative), so KT <= floor f_k(T_k) and  p > T_k  =>  KP = ceil f_k(p) >= KT  still holds; it
+// only admits a few more false candidates.  Branch-free: 2 FP64 ops, one conversion, one clamp.
+__device__ __forceinline__ unsigned dpx_neg_key(double best_m, double winv, double scale, double lo_s)
 {
-    int kt;
-    if (!(T >= lo)) kt = 0;
-    else if (T >= hi) kt = kKeyScale + 1;
-    else {
-        kt = (int)floor((T - lo) * scale);
-        kt = kt > kKeyScale ? kKeyScale : kt;
-    }
-    const unsigned v = (unsigned)(-kt) & 0xffffu;
-    return v | (v << 16);
+    const double x = fma(best_m * winv, scale, -lo_s);
+    int kt = __double2int_rd(x);                  // NaN -> 0, +-inf saturate
+    kt = max(0, min(kt, kKeyScale + 1));
+    return ((unsigned)(-kt) & 0xffffu) * 0x10001u;
 }
 
 __global__ void __launch_bounds__(256) k_quantize(const double *__restrict__ pts, ull n, int d, int tile_pairs,
@@ -516,20 +518,46 @@ template <int D>
 __device__ __forceinline__ void dpx_refresh_keys(double best, const double *__restrict__ winv, unsigned (&negT)[D],
                                                  const DpxArgs &a)
 {
+    const double best_m = best * (1.0 - 0x1p-20);
+    if constexpr (D % 2 == 0) {
+        const double2 *w2 = reinterpret_cast<const double2 *>(winv);       // rows of 2D doubles: 16-byte aligned
 #pragma unroll
-    for (int k = 0; k < D; k++)
-        negT[k] = dpx_neg_key(screen_threshold(best, __ldg(winv + k)), a.qlo[k], a.qhi[k], a.qscale[k]);
+        for (int k = 0; k < D; k += 2) {
+            const double2 w = __ldg(w2 + k / 2);
+            negT[k] = dpx_neg_key(best_m, w.x, a.qscale[k], a.qlos[k]);
+            negT[k + 1] = dpx_neg_key(best_m, w.y, a.qscale[k + 1], a.qlos[k + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; k++) negT[k] = dpx_neg_key(best_m, __ldg(winv + k), a.qscale[k], a.qlos[k]);
+    }
 }
 template <int D>
 __device__ __forceinline__ void dpx_slow_update(const double *__restrict__ p,      // global, D doubles
                                                 const double *__restrict__ dir,    // global r | winv
                                                 double &best, unsigned (&negT)[D], const DpxArgs &a)
 {
-    double m = __ldg(p) * __ldg(dir);
+    double m;
+    if constexpr (D % 2 == 0) {
+        const double2 *p2 = reinterpret_cast<const double2 *>(p), *r2 = reinterpret_cast<const double2 *>(dir);
+        const double2 p0 = __ldg(p2), r0 = __ldg(r2);
+        m = p0.x * r0.x;
+        const double t1 = p0.y * r0.y;
+        m = (t1 < m) ? t1 : m;
 #pragma unroll
-    for (int k = 1; k < D; k++) {
-        const double t = __ldg(p + k) * __ldg(dir + k);
-        m = (t < m) ? t : m;
+        for (int k = 2; k < D; k += 2) {
+            const double2 pv = __ldg(p2 + k / 2), rv = __ldg(r2 + k / 2);
+            const double ta = pv.x * rv.x, tb = pv.y * rv.y;
+            m = (ta < m) ? ta : m;
+            m = (tb < m) ? tb : m;
+        }
+    } else {
+        m = __ldg(p) * __ldg(dir);
+#pragma unroll
+        for (int k = 1; k < D; k++) {
+            const double t = __ldg(p + k) * __ldg(dir + k);
+            m = (t < m) ? t : m;
+        }
     }
     if (m > best) {
         best = m;
@@ -1097,7 +1125,7 @@ struct DevPlan {
     int d = 0;
     size_t n = 0;
     int n_tiles = 0, tile_points = 0;
-    int R = 1, G = 2;
+    int R = 1, G = 2, R_exact = 1;
     int staged = 0, stage_bytes = 0;
     size_t smem_bytes = 0;
     double *pts = nullptr;   size_t pts_cap = 0;       // doubles
@@ -1109,6 +1137,14 @@ struct DevPlan {
     int kR = 1, kG = 2;
     double qlo[32] = {0}, qhi[32] = {0}, qscale[32] = {0};
     double *dirs = nullptr;      size_t dirs_cap = 0;      // doubles (the workspace may serve plans of different d)
+    // DZ2019-HW pipelining: the generator of batch b+1 runs on gen_stream into the other buffer while
+    // the max-min kernel of batch b runs on the main stream (different pipes: FP64 vs ALU for the DPX screen)
+    double *dirs_buf[2] = {nullptr, nullptr}; size_t dirs_buf_cap[2] = {0, 0};
+    cudaStream_t gen_stream = nullptr;
+    cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr}, ev_begin = nullptr;
+    bool used_recorded[2] = {false, false};
+    int cur_buf = 0, pending_buf = -1;
+    bool pipelined = false;
     double *cta_sums = nullptr;  int cta_cap = 0;
     double *values = nullptr;    size_t values_cap = 0;
     double *out_hilo = nullptr;
@@ -1192,11 +1228,22 @@ static constexpr size_t kSmemPerSm = 227 * 1024;
 static constexpr size_t kBarrierBytes = (2 * kStages + 2) * sizeof(ull) + 8 * sizeof(double);
 
 typedef void (*maxmin_fn)(const MaxminArgs);
+// The textbook loop keeps r (not thresholds) in registers and is bound by FP64 + ALU issue; two
+// directions per thread measured best (d=10: {2,2} 541 Gsp/s vs {3,2} 484).  Same tile geometry as the
+// screen configuration of the same D (only R and G differ).
+static constexpr KernelCfg cfg_exact_for(int D)
+{
+    if (D <= 5)  return {2, 4, 2, true};
+    if (D <= 12) return {2, 2, 2, false};
+    return cfg_for(D);
+}
 template <int D>
 static maxmin_fn pick_mode(int mode)
 {
     constexpr KernelCfg c = cfg_for(D);
-    return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<D, c.R, c.G, MODE_EXACT, c.minb>
+    constexpr KernelCfg e = cfg_exact_for(D);
+    static_assert(c.staged == e.staged && c.minb == e.minb, "EXACT and SCREEN share the shared-memory geometry");
+    return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<D, e.R, e.G, MODE_EXACT, e.minb>
                               : (maxmin_fn)k_maxmin<D, c.R, c.G, MODE_SCREEN, c.minb>;
 }
 template <int D>
@@ -1209,37 +1256,7 @@ static maxmin_fn pick_d(int d, int mode)
         return pick_d<D - 1>(d, mode);
     }
 }
-// Development aid: alternative register blockings for d = 10 selected with HVB200_VARIANT=1..5.
-static constexpr KernelCfg kVariants[] = {
-    {2, 2, 2, true}, {4, 1, 1, false}, {4, 1, 2, false}, {3, 2, 2, false}, {4, 1, 1, true}, {3, 2, 1, true},
-};
-static int variant_id()
-{
-    const char *e = getenv("HVB200_VARIANT");
-    const int v = e ? atoi(e) : 0;
-    return (v >= 0 && v < (int)(sizeof kVariants / sizeof kVariants[0])) ? v : 0;
-}
-template <int V>
-static maxmin_fn pick_variant(int mode)
-{
-    constexpr KernelCfg c = kVariants[V];
-    return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<10, c.R, c.G, MODE_EXACT, c.minb>
-                              : (maxmin_fn)k_maxmin<10, c.R, c.G, MODE_SCREEN, c.minb>;
-}
-static maxmin_fn pick_kernel(int d, int mode)
-{
-    if (d == 10) {
-        switch (variant_id()) {
-            case 1: return pick_variant<1>(mode);
-            case 2: return pick_variant<2>(mode);
-            case 3: return pick_variant<3>(mode);
-            case 4: return pick_variant<4>(mode);
-            case 5: return pick_variant<5>(mode);
-            default: break;
-        }
-    }
-    return pick_d<32>(d, mode);
-}
+static maxmin_fn pick_kernel(int d, int mode) { return pick_d<32>(d, mode); }
 // DPX screen geometry: R directions per thread, G point pairs per group ((G*D) % 4 == 0).
 struct DpxCfg { int R, G, minb; };
 static constexpr DpxCfg dpx_cfg_for(int D)
@@ -1267,7 +1284,6 @@ static dpx_fn pick_dpx(int d)
 static KernelCfg cfg_runtime(int d)
 {
     if (d > 32) return {1, 1, 1, false};
-    if (d == 10 && variant_id()) return kVariants[variant_id()];
     return cfg_for(d);
 }
 
@@ -1316,6 +1332,7 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
     const KernelCfg kc = cfg_runtime(d);
     dp->R = kc.R;
     dp->G = kc.G;
+    dp->R_exact = d > 32 ? 1 : cfg_exact_for(d).R;
     dp->staged = kc.staged ? 1 : 0;
     // shared memory budget per CTA for `minb` CTAs per SM -> bytes per pipeline stage
     const size_t dir_bytes = kc.staged ? (size_t)kConsumerThreads * kc.R * 2 * d * 8 : 0;
@@ -1416,6 +1433,10 @@ static void devplan_release(DevPlan *dp)
 {
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
+    cudaFree(dp->dirs_buf[1]);
+    for (int i = 0; i < 2; i++) { if (dp->ev_gen[i]) cudaEventDestroy(dp->ev_gen[i]); if (dp->ev_used[i]) cudaEventDestroy(dp->ev_used[i]); }
+    if (dp->ev_begin) cudaEventDestroy(dp->ev_begin);
+    if (dp->gen_stream) cudaStreamDestroy(dp->gen_stream);
     for (int i = 0; i < 2; i++) {
         if (dp->staging_host[i]) cudaFreeHost(dp->staging_host[i]);
         if (dp->staging_free[i]) cudaEventDestroy(dp->staging_free[i]);
@@ -1428,6 +1449,19 @@ static void devplan_release(DevPlan *dp)
     delete dp;
 }
 
+static int span_begin_on(DevPlan *dp, int kind, cudaStream_t st)
+{
+    while (dp->ev_pool.size() < dp->ev_next + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        dp->ev_pool.push_back(e);
+    }
+    const int a = (int)dp->ev_next, b = a + 1;
+    dp->ev_next += 2;
+    dp->spans.push_back({a, b, kind});
+    cudaEventRecord(dp->ev_pool[a], st);
+    return b;
+}
 static int span_begin(DevPlan *dp, int kind)
 {
     while (dp->ev_pool.size() < dp->ev_next + 2) {
@@ -1506,6 +1540,9 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     }
     CUDA_TRY(cudaMemsetAsync(dp->cta_sums, 0, dp->cta_cap * sizeof(double), dp->stream));
     CUDA_TRY(cudaMemsetAsync(dp->counters, 0, 2 * sizeof(ull), dp->stream));
+    dp->pipelined = false;
+    dp->pending_buf = -1;
+    dp->used_recorded[0] = dp->used_recorded[1] = false;
     return 0;
 }
 
@@ -1573,6 +1610,65 @@ extern "C" int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params 
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
     plan->stats.dirgen_launches++;
+    return 0;
+}
+// Pipelined DZ2019-HW: prefetch(batch b+1) on gen_stream into the buffer that is not in use, then
+// swap() makes the main stream wait for it and points the max-min kernel at it.
+extern "C" int hvb200cu_hw_prefetch(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (hw->nsamples > (1ull << 32)) { hvb200_set_error("DZ2019-HW on the device supports nsamples <= 2^32"); return -1; }
+    if (!dp->gen_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&dp->gen_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_gen[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_used[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_begin, cudaEventDisableTiming));
+    }
+    if (!dp->pipelined) {
+        // first prefetch of a run: adopt the run's direction buffer as buffer 0, order the generator
+        // stream behind the run's initial memsets
+        dp->dirs_buf[0] = dp->dirs; dp->dirs_buf_cap[0] = dp->dirs_cap;
+        dp->cur_buf = 1;                      // so that the first prefetch targets buffer 0
+        CUDA_TRY(cudaEventRecord(dp->ev_begin, dp->stream));
+        CUDA_TRY(cudaStreamWaitEvent(dp->gen_stream, dp->ev_begin, 0));
+        dp->pipelined = true;
+    }
+    const int buf = dp->cur_buf ^ 1;
+    const size_t need = count * (size_t)(2 * dp->d);
+    if (dp->dirs_buf_cap[buf] < need) {
+        if (dp->used_recorded[buf]) CUDA_TRY(cudaEventSynchronize(dp->ev_used[buf]));
+        cudaFree(dp->dirs_buf[buf]);
+        dp->dirs_buf[buf] = nullptr; dp->dirs_buf_cap[buf] = 0;
+        const size_t cap = std::max(need, dp->dirs_cap);
+        CUDA_TRY(cudaMalloc(&dp->dirs_buf[buf], cap * sizeof(double)));
+        dp->dirs_buf_cap[buf] = cap;
+    }
+    if (dp->used_recorded[buf]) CUDA_TRY(cudaStreamWaitEvent(dp->gen_stream, dp->ev_used[buf], 0));
+    HwDev P;
+    P.N = hw->nsamples;
+    P.d = hw->d;
+    for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
+    const int b = span_begin_on(dp, 1, dp->gen_stream);
+    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->gen_stream>>>(P, i0, count, dp->dirs_buf[buf], dp->counters);
+    if (b >= 0) cudaEventRecord(dp->ev_pool[b], dp->gen_stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(dp->ev_gen[buf], dp->gen_stream));
+    dp->pending_buf = buf;
+    plan->stats.dirgen_launches++;
+    return 0;
+}
+extern "C" int hvb200cu_hw_swap(struct hvb200_plan *plan)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (dp->pending_buf < 0) { hvb200_set_error("internal: swap without prefetch"); return -1; }
+    const int buf = dp->pending_buf;
+    CUDA_TRY(cudaStreamWaitEvent(dp->stream, dp->ev_gen[buf], 0));
+    dp->cur_buf = buf;
+    dp->dirs = dp->dirs_buf[buf];
+    dp->dirs_cap = dp->dirs_buf_cap[buf];
+    dp->pending_buf = -1;
     return 0;
 }
 extern "C" int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count)
@@ -1679,7 +1775,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     a.slow_counter = dp->counters + 1;
     const bool dpx = dp->kernel_used == MODE_DPX;
     const size_t smem = dpx ? dp->k_smem_bytes : dp->smem_bytes;
-    const ull chunk = (ull)kConsumerThreads * (dpx ? dp->kR : dp->R);
+    const ull chunk = (ull)kConsumerThreads * (dpx ? dp->kR : (dp->kernel_used == MODE_EXACT ? dp->R_exact : dp->R));
     const ull n_chunks = (count + chunk - 1) / chunk;
     const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks ? n_chunks : 1);
     const int b = span_begin(dp, 0);
@@ -1697,7 +1793,10 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
         ka.cta_sums = dp->cta_sums;
         ka.values = a.values;
         ka.slow_counter = dp->counters + 1;
-        for (int k = 0; k < 32; k++) { ka.qlo[k] = dp->qlo[k]; ka.qhi[k] = dp->qhi[k]; ka.qscale[k] = dp->qscale[k]; }
+        for (int k = 0; k < 32; k++) {
+            ka.qscale[k] = dp->qscale[k];
+            ka.qlos[k] = k < d ? dp->qlo[k] * dp->qscale[k] * (1.0 + 0x1p-20) + 0x1p-10 : 0.0;
+        }
         dpx_fn fn = pick_dpx<32>(d);
         fn<<<grid, kBlockThreads, smem, dp->stream>>>(ka);
     } else if (d <= 32) {
@@ -1708,6 +1807,10 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     }
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
+    if (dp->pipelined) {
+        CUDA_TRY(cudaEventRecord(dp->ev_used[dp->cur_buf], dp->stream));
+        dp->used_recorded[dp->cur_buf] = true;
+    }
     plan->stats.maxmin_launches++;
     if (values_host) {
         CUDA_TRY(cudaMemcpyAsync(values_host, dp->values, count * sizeof(double), cudaMemcpyDeviceToHost, dp->stream));
@@ -1719,6 +1822,11 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
 extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
 {
     DevPlan *dp = (DevPlan *)plan->dev;
+    if (dp->pipelined) {
+        // the run's own buffer is buffer 0 again; buffer 1 stays cached for the next pipelined run
+        dp->dirs = dp->dirs_buf[0];
+        dp->dirs_cap = dp->dirs_buf_cap[0];
+    }
     {
         const int b = span_begin(dp, 2);
         k_reduce<<<1, 1024, 0, dp->stream>>>(dp->cta_sums, dp->grid, dp->out_hilo);
