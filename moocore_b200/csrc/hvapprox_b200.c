@@ -357,6 +357,7 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
     if (method != HVB200_METHOD_HW && want > (1u << 20)) want = 1u << 20;     /* MC stream: 1 Mi samples per batch */
     /* host-fed streams: smaller batches so that producing batch b+1 overlaps the GPU work on batch b */
     if ((method == HVB200_METHOD_RPHI || (method == HVB200_METHOD_MC && !mc_on_device)) && want > (1u << 18)) want = 1u << 18;
+    plan->run_samples = (values_out || dirs_out) ? 0 : i1 - i0;
     if (hvb200cu_run_begin(plan, stream, want, &batch)) return -1;
 
     hvb200_hw_params hw;
@@ -450,6 +451,7 @@ int hvb200_plan_run_directions(hvb200_plan *plan, const double *r_host, uint64_t
     uint64_t batch = 0;
     uint64_t want = count ? count : 1;
     if (want > (1u << 20)) want = 1u << 20;
+    plan->run_samples = 0;
     if (hvb200cu_run_begin(plan, NULL, want, &batch)) return -1;
     for (uint64_t b0 = 0; b0 < count; b0 += batch) {
         const uint64_t cnt = (count - b0 < batch) ? count - b0 : batch;

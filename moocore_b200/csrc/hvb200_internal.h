@@ -27,6 +27,7 @@ struct hvb200_plan {
     int d;                 /* number of objectives                                              */
     size_t n;              /* n' surviving points                                               */
     int kernel;            /* requested HVB200_KERNEL_*                                         */
+    uint64_t run_samples;  /* size of the run being started (lets the device side amortise one-off work) */
     /* device side (owned by the CUDA TU) */
     void *dev;             /* struct dev_plan*                                                  */
     hvb200_stats stats;
