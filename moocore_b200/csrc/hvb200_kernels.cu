@@ -758,7 +758,9 @@ __device__ __forceinline__ unsigned hash_u32(unsigned x)
 __global__ void __launch_bounds__(128) k_probe_argmax(const double *__restrict__ pts, unsigned n, int d, unsigned nprobe,
                                                       unsigned *__restrict__ wins)
 {
-    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per probe direction; the lanes stride over the points
+    const unsigned j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
     if (j >= nprobe) return;
     double r[HVB200_MAXD];
     for (int k = 0; k < d; k++) {
@@ -769,8 +771,8 @@ __global__ void __launch_bounds__(128) k_probe_argmax(const double *__restrict__
         r[k] = 1.0 / ((double)fabsf(z) + 1e-6);
     }
     double best = -1.0;
-    unsigned arg = 0;
-    for (unsigned i = 0; i < n; i++) {
+    unsigned arg = 0xffffffffu;
+    for (unsigned i = lane; i < n; i += 32) {
         const double *p = pts + (size_t)i * d;
         double m = __ldg(p) * r[0];
         for (int k = 1; k < d; k++) {
@@ -779,7 +781,13 @@ __global__ void __launch_bounds__(128) k_probe_argmax(const double *__restrict__
         }
         if (m > best) { best = m; arg = i; }
     }
-    atomicAdd(&wins[arg], 1u);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_down_sync(0xffffffffu, best, off);
+        const unsigned oa = __shfl_down_sync(0xffffffffu, arg, off);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0 && arg != 0xffffffffu) atomicAdd(&wins[arg], 1u);
 }
 __global__ void __launch_bounds__(256) k_gather_rows(const double *__restrict__ src, const unsigned *__restrict__ order,
                                                      ull n, int d, double *__restrict__ dst)
@@ -1554,7 +1562,7 @@ static int order_points(DevPlan *dp)
         dp->pts_tmp_cap = n * (size_t)d;
     }
     CUDA_TRY(cudaMemsetAsync(dp->wins, 0, n * sizeof(unsigned), us));
-    k_probe_argmax<<<(nprobe + 127) / 128, 128, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, dp->wins);
+    k_probe_argmax<<<(nprobe * 32 + 127) / 128, 128, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, dp->wins);
     CUDA_TRY(cudaGetLastError());
     std::vector<unsigned> wins(n), order(n);
     CUDA_TRY(cudaMemcpyAsync(wins.data(), dp->wins, n * sizeof(unsigned), cudaMemcpyDeviceToHost, us));
