@@ -278,7 +278,7 @@ def run_ours(args, rank, local_rank, world):
             pass
         alg_bytes = 8.0 * npts * d
         roofline = {
-            "bound": "fp64", "kernel": {1: "k_maxmin<EXACT>", 2: "k_maxmin<SCREEN>", 3: "k_maxmin_dpx"}.get(plan.stats()["kernel"], "k_maxmin"), "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
+            "bound": "fp64", "kernel": {1: "k_maxmin<EXACT>", 2: "k_maxmin<SCREEN>", 3: "k_maxmin_dpx", 4: "k_maxmin_bp"}.get(plan.stats()["kernel"], "k_maxmin"), "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
             "unit": "TFP64-instr/s", "frac": achieved / peak_instr,
             "peak_source": "DFMA micro-benchmark measured in this run on this GPU (P64/2; MEASURED_PEAKS.json has no FP64 entry)",
             "p64_tflops_measured": fp["dfma_flops"] / 1e12,
@@ -321,7 +321,7 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config), "kernel": {1: "exact", 2: "screen", 3: "dpx"}.get(plan.stats()["kernel"], "?"),
+            "config": {"workload": workload_name(args.config), "kernel": {1: "exact", 2: "screen", 3: "dpx", 4: "pruned"}.get(plan.stats()["kernel"], "?"),
                        "npoints_after_filter": npts, "parallelism": f"direction-range x{world}",
                        "l2": "point set (0.8 MB) is L2/shared-memory resident by design; the per-batch direction "
                              "buffer (2 GiB) exceeds L2, no flush needed",
@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg3", choices=list(hvcases.CONFIGS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "screen", "dpx"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "screen", "dpx", "pruned"])
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":

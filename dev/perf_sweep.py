@@ -10,7 +10,7 @@ for cfg in which:
     c = hvcases.CONFIGS[cfg]
     x, ref, maxi = hvcases.config_inputs(cfg)
     res = {}
-    for kern in ("exact", "screen", "dpx"):
+    for kern in ("exact", "screen", "dpx", "pruned"):
         with mb.Plan(x, ref, maxi, kernel=kern, allow_extension=True) as plan:
             cnt = min(budget[cfg], c["nsamples"])
             meth = c["method"] if c["d"] <= 31 or c["method"] != "DZ2019-HW" else "DZ2019-MC"
@@ -21,4 +21,4 @@ for cfg in which:
             print("%s %-6s d=%d n=%d cnt=%d  maxmin %.3f ms (%.1f Gsp/s)  dirgen %.3f ms  h2d %.3f ms  wall %.1f ms  slow/sample %.2f  capped %d" % (
                 cfg, kern, c["d"], plan.npoints, cnt, st["maxmin_ms"], cnt * plan.npoints / max(st["maxmin_ms"], 1e-9) / 1e6,
                 st["dirgen_ms"], st["h2d_ms"], wall * 1e3, st["slow_path"] / cnt, st["newton_capped"]), flush=True)
-    print(cfg, "exact==screen==dpx sums:", res["exact"] == res["screen"] == res["dpx"], res["exact"], res["screen"], res["dpx"])
+    print(cfg, "all sums equal:", res["exact"] == res["screen"] == res["dpx"] == res["pruned"], res["exact"], res["pruned"])

@@ -34,8 +34,10 @@ enum {
     HVB200_KERNEL_EXACT  = 1, /* d DMUL + d min + 1 max per sample*point (the textbook loop)   */
     HVB200_KERNEL_SCREEN = 2, /* exact threshold screen: 1 DSETP per element, products only for
                                  candidates that can raise the running max                      */
-    HVB200_KERNEL_DPX    = 3  /* the same screen on conservatively quantised 16-bit keys with
+    HVB200_KERNEL_DPX    = 3, /* the same screen on conservatively quantised 16-bit keys with
                                  DPX VIADDMNMX.S16x2 (2 elements per instruction, no predicates) */
+    HVB200_KERNEL_BP     = 4  /* block-pruned: blocks of 32 points are discarded by their
+                                 per-objective maxima before any of their points is looked at     */
 };
 
 /* Largest dimension the library accepts.  The reference stops at 31

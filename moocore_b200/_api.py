@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBNAME = "libmoocore_b200.so"
 
 METHOD_IDS = {"DZ2019-MC": 1, "DZ2019-HW": 2, "Rphi-FWE+": 3}
-KERNEL_IDS = {"auto": 0, "exact": 1, "screen": 2, "dpx": 3}
+KERNEL_IDS = {"auto": 0, "exact": 1, "screen": 2, "dpx": 3, "pruned": 4}
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_u8_p = ctypes.POINTER(ctypes.c_uint8)

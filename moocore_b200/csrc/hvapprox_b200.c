@@ -100,6 +100,7 @@ int hvb200_plan_create(hvb200_plan **plan_out, const double *data, size_t npoint
     if (env && !strcmp(env, "exact")) plan->kernel = HVB200_KERNEL_EXACT;
     if (env && !strcmp(env, "screen")) plan->kernel = HVB200_KERNEL_SCREEN;
     if (env && !strcmp(env, "dpx")) plan->kernel = HVB200_KERNEL_DPX;
+    if (env && !strcmp(env, "pruned")) plan->kernel = HVB200_KERNEL_BP;
     const int rc = hvb200cu_plan_upload(plan, pts);
     free(pts);
     if (rc) { hvb200cu_plan_free(plan); free(plan); return -1; }
@@ -115,7 +116,7 @@ void hvb200_plan_destroy(hvb200_plan *plan)
 size_t hvb200_plan_npoints(const hvb200_plan *plan) { return plan ? plan->n : 0; }
 int hvb200_plan_set_kernel(hvb200_plan *plan, int kernel)
 {
-    if (kernel < HVB200_KERNEL_AUTO || kernel > HVB200_KERNEL_DPX) { hvb200_set_error("bad kernel id %d", kernel); return -2; }
+    if (kernel < HVB200_KERNEL_AUTO || kernel > HVB200_KERNEL_BP) { hvb200_set_error("bad kernel id %d", kernel); return -2; }
     plan->kernel = kernel;
     return 0;
 }

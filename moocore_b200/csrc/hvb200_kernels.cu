@@ -212,7 +212,7 @@ struct MaxminArgs {
     ull *slow_counter;       // optional diagnostic
 };
 
-enum { MODE_EXACT = 1, MODE_SCREEN = 2, MODE_DPX = 3 };
+enum { MODE_EXACT = 1, MODE_SCREEN = 2, MODE_DPX = 3, MODE_BP = 4 };
 
 // Threshold for the screen: a T with  p <= T  =>  RN(p * r) <= best.
 // winv = RN(1/r)  =>  best*winv*(1-2^-50) < (best/r)(1-2^-51); tiny values flush to 0 (= "always a
@@ -741,6 +741,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_maxmin_dpx(const __grid
     }
 }
 
+#include "hvb200_bp.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // Point ordering for the screens.  max over points is order-free (exact), so the processing order
 // is a pure performance knob: a screen pays a divergent exact evaluation every time a point raises a
@@ -1233,6 +1235,12 @@ struct DevPlan {
     double *qdev = nullptr;              // 3 x 32 doubles: quantisation parameters for k_quantize
     bool resources_ready = false;        // stream / events / small buffers exist (workspace reuse)
     bool ordered = false;                // points already sorted by probe arg-max frequency
+    // block-pruned kernel (hvb200_bp.cuh)
+    bool bp_ready = false;
+    double *bp_pts = nullptr, *bp_piv = nullptr; size_t bp_pts_cap = 0;
+    unsigned *bp_pkeys = nullptr, *bp_bkeys = nullptr, *bp_bpair = nullptr; size_t bp_keys_cap = 0;
+    int bp_nb = 0, bp_nb_pad = 0, bp_seg_blocks = 0, bp_npiv = 0, bp_resident = 0;
+    size_t bp_smem = 0;
     double *pts_tmp = nullptr; size_t pts_tmp_cap = 0;
     unsigned *wins = nullptr; size_t wins_cap = 0;      // 2n words: win counts, then the order
     int k_tile_pairs = 0, k_n_tiles = 0, k_stage_bytes = 0;
@@ -1443,6 +1451,7 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
     dp->d = plan->d;
     dp->n = plan->n;
     dp->ordered = false;
+    dp->bp_ready = false;
     const int d = plan->d;
     const KernelCfg kc = cfg_runtime(d);
     dp->R = kc.R;
@@ -1466,7 +1475,7 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
     const size_t padded = (size_t)dp->n_tiles * tp * d;
     if (!dp->resources_ready) {
         CUDA_TRY(cudaMalloc(&dp->out_hilo, 2 * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&dp->counters, 2 * sizeof(ull)));
+        CUDA_TRY(cudaMalloc(&dp->counters, 8 * sizeof(ull)));
         CUDA_TRY(cudaMalloc(&dp->qdev, 3 * 32 * sizeof(double)));
         CUDA_TRY(cudaStreamCreateWithFlags(&dp->own_stream, cudaStreamNonBlocking));
         cudaDeviceProp prop;
@@ -1549,6 +1558,7 @@ static void devplan_release(DevPlan *dp)
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
     cudaFree(dp->dirs_buf[1]); cudaFree(dp->pts_tmp); cudaFree(dp->wins);
+    cudaFree(dp->bp_pts); cudaFree(dp->bp_piv); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bkeys); cudaFree(dp->bp_bpair);
     for (int i = 0; i < 2; i++) { if (dp->ev_gen[i]) cudaEventDestroy(dp->ev_gen[i]); if (dp->ev_used[i]) cudaEventDestroy(dp->ev_used[i]); }
     if (dp->ev_begin) cudaEventDestroy(dp->ev_begin);
     if (dp->gen_stream) cudaStreamDestroy(dp->gen_stream);
@@ -1592,6 +1602,107 @@ static int span_begin(DevPlan *dp, int kind)
 }
 static void span_end(DevPlan *dp, int b) { if (b >= 0) cudaEventRecord(dp->ev_pool[b], dp->stream); }
 
+
+// Build the block-pruned kernel's inputs (hvb200_bp.cuh): warm-up set = the most frequent probe winners,
+// blocks = points sorted by weakest normalised objective, three key layouts.
+typedef void (*bp_fn)(const BpArgs);
+template <int D>
+static bp_fn pick_bp(int d)
+{
+    if constexpr (D < 2) {
+        return nullptr;
+    } else {
+        if (d == D) return (bp_fn)k_maxmin_bp<D>;
+        return pick_bp<D - 1>(d);
+    }
+}
+static int bp_prepare(DevPlan *dp)
+{
+    const size_t n = dp->n;
+    const int d = dp->d, W = (d + 1) / 2;
+    cudaStream_t us = dp->own_stream;
+    unsigned nprobe = 4096;
+    while (nprobe > 256 && (double)nprobe * (double)n > 6e8) nprobe /= 2;
+    if (dp->wins_cap < 2 * n) {
+        cudaFree(dp->wins);
+        dp->wins = nullptr; dp->wins_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->wins, 2 * n * sizeof(unsigned)));
+        dp->wins_cap = 2 * n;
+    }
+    CUDA_TRY(cudaMemsetAsync(dp->wins, 0, n * sizeof(unsigned), us));
+    k_probe_argmax<<<(nprobe * 32 + 127) / 128, 128, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, dp->wins);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<unsigned> wins(n);
+    std::vector<double> pts(n * (size_t)d);
+    CUDA_TRY(cudaMemcpyAsync(wins.data(), dp->wins, n * sizeof(unsigned), cudaMemcpyDeviceToHost, us));
+    CUDA_TRY(cudaMemcpyAsync(pts.data(), dp->pts, n * (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, us));
+    CUDA_TRY(cudaStreamSynchronize(us));
+    // warm-up set: the points that won most probes
+    std::vector<unsigned> idx(n);
+    for (size_t i = 0; i < n; i++) idx[i] = (unsigned)i;
+    const size_t npiv = std::min<size_t>(n, (size_t)kBpPivots);
+    std::partial_sort(idx.begin(), idx.begin() + npiv, idx.end(),
+                      [&](unsigned x, unsigned y) { return wins[x] != wins[y] ? wins[x] > wins[y] : x < y; });
+    std::vector<double> piv((size_t)kBpPivots * d, 0.0);
+    for (size_t i = 0; i < npiv; i++) memcpy(&piv[i * d], &pts[(size_t)idx[i] * d], d * sizeof(double));
+    // block order: weakest normalised objective, then its value
+    std::vector<double> colmax(d, 0.0);
+    for (size_t i = 0; i < n; i++) for (int k = 0; k < d; k++) colmax[k] = std::max(colmax[k], pts[i * d + k]);
+    std::vector<int> wk(n);
+    std::vector<double> wv(n);
+    for (size_t i = 0; i < n; i++) {
+        int bk = 0; double bv = INFINITY;
+        for (int k = 0; k < d; k++) { const double v = pts[i * d + k] / colmax[k]; if (v < bv) { bv = v; bk = k; } }
+        wk[i] = bk; wv[i] = bv;
+    }
+    for (size_t i = 0; i < n; i++) idx[i] = (unsigned)i;
+    std::sort(idx.begin(), idx.end(), [&](unsigned x, unsigned y) {
+        if (wk[x] != wk[y]) return wk[x] < wk[y];
+        if (wv[x] != wv[y]) return wv[x] < wv[y];
+        return x < y;
+    });
+    const int nb = (int)((n + kBpBlock - 1) / kBpBlock);
+    const int nb_pad = (nb + 2 * kBpG - 1) / (2 * kBpG) * (2 * kBpG);
+    const size_t n_pad = (size_t)nb_pad * kBpBlock;
+    std::vector<double> sorted(n_pad * (size_t)d, 0.0);
+    for (size_t i = 0; i < n; i++) memcpy(&sorted[i * d], &pts[(size_t)idx[i] * d], d * sizeof(double));
+    if (dp->bp_pts_cap < n_pad * (size_t)d) {
+        cudaFree(dp->bp_pts);
+        dp->bp_pts = nullptr; dp->bp_pts_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->bp_pts, n_pad * (size_t)d * sizeof(double)));
+        dp->bp_pts_cap = n_pad * (size_t)d;
+    }
+    if (!dp->bp_piv) CUDA_TRY(cudaMalloc(&dp->bp_piv, (size_t)kBpPivots * 64 * sizeof(double)));
+    if (dp->bp_keys_cap < n_pad * (size_t)W) {
+        cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bkeys); cudaFree(dp->bp_bpair);
+        dp->bp_pkeys = dp->bp_bkeys = dp->bp_bpair = nullptr; dp->bp_keys_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->bp_pkeys, n_pad * (size_t)W * sizeof(unsigned)));
+        CUDA_TRY(cudaMalloc(&dp->bp_bkeys, (size_t)nb_pad * W * sizeof(unsigned)));
+        CUDA_TRY(cudaMalloc(&dp->bp_bpair, (size_t)(nb_pad / 2) * 32 * sizeof(unsigned)));
+        dp->bp_keys_cap = n_pad * (size_t)W;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_pts, sorted.data(), n_pad * (size_t)d * sizeof(double), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_piv, piv.data(), piv.size() * sizeof(double), cudaMemcpyHostToDevice, us));
+    k_bp_pkeys<<<(unsigned)((n_pad * W + 255) / 256), 256, 0, us>>>(dp->bp_pts, (ull)n, (ull)n_pad, d, W, dp->qdev, dp->qdev + 64, dp->bp_pkeys);
+    k_bp_bkeys<<<(unsigned)((nb * W + 255) / 256), 256, 0, us>>>(dp->bp_pkeys, nb, W, dp->bp_bkeys);
+    k_bp_pairs<<<(unsigned)(((nb_pad / 2) * d + 255) / 256), 256, 0, us>>>(dp->bp_bkeys, nb, nb_pad, d, W, dp->bp_bpair);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(us));              // host vectors go out of scope
+    dp->bp_nb = nb;
+    dp->bp_nb_pad = nb_pad;
+    dp->bp_npiv = (int)npiv;
+    int seg = d <= 12 ? 1024 : 512;
+    if (nb_pad < seg) seg = (nb_pad + 31) / 32 * 32;
+    dp->bp_seg_blocks = seg;
+    // keep all block bounds in shared memory when they fit next to the masks: the warps of a CTA then
+    // never synchronise after start-up
+    const size_t all_bounds = (size_t)(nb_pad / 2) * d * 4;
+    dp->bp_resident = all_bounds <= 64 * 1024 ? 1 : 0;
+    dp->bp_smem = (dp->bp_resident ? all_bounds : (size_t)(seg / 2) * d * 4) + (size_t)kBpThreads * kBpR * (seg / 32) * 4 +
+                  (size_t)kBpPivots * d * 8 + 8 + 8 * 8 + 64;
+    dp->bp_ready = true;
+    return 0;
+}
 
 // Sort the plan's points by how often they win a probe direction (see k_probe_argmax).  Runs once per
 // plan, only for jobs large enough to amortise it (~0.5 ms at n = 1e4).
@@ -1677,12 +1788,19 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     int mode = MODE_DPX;
     if (plan->kernel == HVB200_KERNEL_EXACT) mode = MODE_EXACT;
     else if (plan->kernel == HVB200_KERNEL_SCREEN) mode = MODE_SCREEN;
+    else if (plan->kernel == HVB200_KERNEL_BP) mode = MODE_BP;
     else if (plan->kernel == HVB200_KERNEL_AUTO && dp->n < 256) mode = MODE_EXACT;
     if (d > 32) mode = MODE_EXACT;
     dp->kernel_used = mode;
-    const size_t smem = mode == MODE_DPX ? dp->k_smem_bytes : dp->smem_bytes;
+    if (mode == MODE_BP && !dp->bp_ready && bp_prepare(dp)) return -1;
+    const size_t smem = mode == MODE_DPX ? dp->k_smem_bytes : (mode == MODE_BP ? dp->bp_smem : dp->smem_bytes);
     int occ = 1;
-    if (mode == MODE_DPX) {
+    if (mode == MODE_BP) {
+        bp_fn fn = pick_bp<32>(d);
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBpThreads, smem));
+    } else if (mode == MODE_DPX) {
         dpx_fn fn = pick_dpx<32>(d);
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -1705,7 +1823,7 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
         dp->cta_cap = dp->grid;
     }
     CUDA_TRY(cudaMemsetAsync(dp->cta_sums, 0, dp->cta_cap * sizeof(double), dp->stream));
-    CUDA_TRY(cudaMemsetAsync(dp->counters, 0, 2 * sizeof(ull), dp->stream));
+    CUDA_TRY(cudaMemsetAsync(dp->counters, 0, 8 * sizeof(ull), dp->stream));
     dp->pipelined = false;
     dp->pending_buf = -1;
     dp->used_recorded[0] = dp->used_recorded[1] = false;
@@ -1939,13 +2057,37 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     a.cta_sums = dp->cta_sums;
     a.values = values_host ? dp->values : nullptr;
     a.slow_counter = dp->counters + 1;
-    const bool dpx = dp->kernel_used == MODE_DPX;
-    const size_t smem = dpx ? dp->k_smem_bytes : dp->smem_bytes;
-    const ull chunk = (ull)kConsumerThreads * (dpx ? dp->kR : (dp->kernel_used == MODE_EXACT ? dp->R_exact : dp->R));
+    const bool dpx = dp->kernel_used == MODE_DPX, bp = dp->kernel_used == MODE_BP;
+    const size_t smem = dpx ? dp->k_smem_bytes : (bp ? dp->bp_smem : dp->smem_bytes);
+    const ull chunk = bp ? (ull)kBpThreads * kBpR
+                         : (ull)kConsumerThreads * (dpx ? dp->kR : (dp->kernel_used == MODE_EXACT ? dp->R_exact : dp->R));
     const ull n_chunks = (count + chunk - 1) / chunk;
     const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks ? n_chunks : 1);
     const int b = span_begin(dp, 0);
-    if (dpx) {
+    if (bp) {
+        BpArgs ka;
+        ka.pts = dp->bp_pts;
+        ka.pivots = dp->bp_piv;
+        ka.n_piv = dp->bp_npiv;
+        ka.pkeys = dp->bp_pkeys;
+        ka.bkeys = dp->bp_bkeys;
+        ka.bpair = dp->bp_bpair;
+        ka.nb = dp->bp_nb;
+        ka.nb_pad = dp->bp_nb_pad;
+        ka.seg_blocks = dp->bp_seg_blocks;
+        ka.resident = dp->bp_resident;
+        ka.dirs = dp->dirs;
+        ka.count = count;
+        ka.cta_sums = dp->cta_sums;
+        ka.values = a.values;
+        ka.slow_counter = dp->counters + 1;
+        for (int k = 0; k < 32; k++) {
+            ka.qscale[k] = dp->qscale[k];
+            ka.qlos[k] = k < d ? dp->qlo[k] * dp->qscale[k] * (1.0 + 0x1p-20) + 0x1p-10 : 0.0;
+        }
+        bp_fn fn = pick_bp<32>(d);
+        fn<<<grid, kBpThreads, smem, dp->stream>>>(ka);
+    } else if (dpx) {
         DpxArgs ka;
         ka.keys = dp->keys;
         ka.n_tiles = dp->k_n_tiles;
@@ -2001,15 +2143,17 @@ extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
         plan->stats.reduce_launches++;
     }
     double host[2];
-    ull counters[2];
+    ull counters[8];
     CUDA_TRY(cudaMemcpyAsync(host, dp->out_hilo, sizeof host, cudaMemcpyDeviceToHost, dp->stream));
     CUDA_TRY(cudaMemcpyAsync(counters, dp->counters, sizeof counters, cudaMemcpyDeviceToHost, dp->stream));
     CUDA_TRY(cudaStreamSynchronize(dp->stream));
     if (out_hilo) { out_hilo[0] = host[0]; out_hilo[1] = host[1]; }
     plan->stats.newton_capped = counters[0];
     plan->stats.slow_path = counters[1];
+    if (getenv("HVB200_DEBUG_COUNTERS"))
+        fprintf(stderr, "hvb200 counters: capped=%llu cand=%llu surv=%llu rounds=%llu live=%llu dirs_c=%llu\n", counters[0], counters[1], counters[2], counters[3], counters[4], counters[5]);
     plan->stats.npoints = dp->n;
-    plan->stats.kernel = dp->kernel_used == MODE_EXACT ? HVB200_KERNEL_EXACT : (dp->kernel_used == MODE_DPX ? HVB200_KERNEL_DPX : HVB200_KERNEL_SCREEN);
+    plan->stats.kernel = dp->kernel_used == MODE_EXACT ? HVB200_KERNEL_EXACT : (dp->kernel_used == MODE_DPX ? HVB200_KERNEL_DPX : (dp->kernel_used == MODE_BP ? HVB200_KERNEL_BP : HVB200_KERNEL_SCREEN));
     for (const auto &s : dp->spans) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, dp->ev_pool[s.a], dp->ev_pool[s.b]) != cudaSuccess) { cudaGetLastError(); continue; }

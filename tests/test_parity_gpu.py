@@ -84,7 +84,7 @@ def test_values_bit_exact_all_dims(mb, oracle, d):
     method = "DZ2019-HW" if d <= 20 else "DZ2019-MC"
     r = oracle_dirs(oracle, method, d, 50_000, 5, 777, 600)
     want = oracle_values(oracle, tp, r)
-    for kern in ("exact", "screen", "dpx"):
+    for kern in ("exact", "screen", "dpx", "pruned"):
         with mb.Plan(x, 1.1, kernel=kern, allow_extension=True) as plan:
             vals, hilo = plan.run_directions(r)
             assert np.array_equal(vals, want), f"d={d} kernel={kern}"
@@ -98,7 +98,7 @@ def test_values_bit_exact_ragged_point_counts(mb, oracle, n):
     tp = np.ascontiguousarray(1.1 - x)
     r = oracle_dirs(oracle, "DZ2019-MC", d, 10_000, 3, 0, 700 if n < 5000 else 300)
     want = oracle_values(oracle, tp, r)
-    for kern in ("exact", "screen", "dpx"):
+    for kern in ("exact", "screen", "dpx", "pruned"):
         with mb.Plan(x, 1.1, kernel=kern) as plan:
             assert plan.npoints == n
             vals, _ = plan.run_directions(r)
@@ -113,7 +113,7 @@ def test_extreme_directions_bit_exact(mb, oracle):
                   [2.5, 2.5, 2.5, 2.5], [1e150, 1e150, 1e150, 1e150], [1e-150, 1.0, 1.0, 1.0]])
     tp = np.ascontiguousarray(1.0 - x)
     want = oracle_values(oracle, tp, r)
-    for kern in ("exact", "screen", "dpx"):
+    for kern in ("exact", "screen", "dpx", "pruned"):
         with mb.Plan(x, 1.0, kernel=kern) as plan:
             vals, _ = plan.run_directions(r)
             assert np.array_equal(vals, want), kern
@@ -251,11 +251,12 @@ def test_screen_equals_exact_at_bench_size_slice(mb):
     x, ref, maxi = hvcases.config_inputs("cfg3")
     cnt = 1 << 21
     out = {}
-    for kern in ("exact", "screen", "dpx"):
+    for kern in ("exact", "screen", "dpx", "pruned"):
         with mb.Plan(x, ref, maxi, kernel=kern) as plan:
             out[kern] = plan.sample_values(c["method"], c["nsamples"], 0, 37_000_000, cnt)
     assert np.array_equal(out["exact"], out["screen"])
     assert np.array_equal(out["exact"], out["dpx"])
+    assert np.array_equal(out["exact"], out["pruned"])
     assert np.all(out["exact"] > 0)
 
 
@@ -343,7 +344,7 @@ def test_large_point_set(mb, oracle):
     tp = np.ascontiguousarray(1.1 - x)
     r = oracle_dirs(oracle, "DZ2019-HW", d, 100_000, 0, 40_000, 48)
     want = oracle_values(oracle, tp, r)
-    for kern in ("exact", "screen", "dpx"):
+    for kern in ("exact", "screen", "dpx", "pruned"):
         with mb.Plan(x, 1.1, kernel=kern) as plan:
             vals, _ = plan.run_directions(r)
             assert np.array_equal(vals, want), kern
