@@ -1,52 +1,84 @@
 // hvb200_bp.cuh — block-pruned max-min kernel (included by hvb200_kernels.cu).
 //
 // Generalises the reference's scalar early-out (c/hvapprox.c:104-108) into a two-level search that
-// keeps the reference's bits: max_p min_k p_k r_k only needs the points that can still raise the
-// running max, and whole blocks of points can be discarded by their per-objective maxima.
+// keeps the reference's bits: max_p min_k p_k r_k only needs the points that can still raise a lower
+// bound of the max, and whole blocks of 32 points can be discarded by their per-objective maxima.
+// Every phase runs with all lanes busy; the (direction, block) survivor matrix is transposed between
+// the phases so that the lane axis is always the long one.
 //
-//   order     points sorted by their weakest normalised objective (blocks of 32 consecutive points
-//             then share small coordinates in the same objective -> tight block bounds); the 64 points
-//             that win most probe directions (k_probe_argmax) form a separate warm-up set
+//   order     kd-tree order of the points (recursive median splits on the widest normalised
+//             objective): 32 consecutive points form a block with a tight bounding box
 //   keys      the DPX 16-bit keys of k_maxmin_dpx (same monotone map, same conservative rounding):
-//               pkeys [point][W]   two objectives per word            (lane = point)
-//               bkeys [block][W]   per-objective maximum of the block (lane = block)
-//               bpair [block pair][D]  two blocks per word            (lane = direction)
-//   phase A   lane = direction: exact max-min over the warm-up set -> best, threshold keys
-//   phase B   lane = direction: brute-force DPX screen of the BLOCK BOUNDS (n/32 virtual points) ->
-//             per-direction bitmask of blocks that may still hold an improving point
-//   phase C   warp = direction: the warp walks the direction's surviving blocks; 32 lanes re-check 32
-//             block bounds at a time against the current thresholds, then test the 32 points of each
-//             live block; candidates are evaluated exactly in FP64 by the warp (lane = objective,
-//             shuffle min), and the thresholds are refreshed when the max rises
+//               pkeys [block][W][32]     two objectives per word          (phase C, lane = point)
+//               bpair [block pair][D]    two block maxima per word        (phase B, lane = direction)
+//   phase A   lane = direction.  FP32 max-min over the pivots (the points that win most probe
+//             directions, k_probe_argmax) picks one pivot per direction; that pivot is evaluated in
+//             FP64 with the reference's arithmetic -> b0, a value some point really attains, hence a
+//             lower bound of the max whatever the FP32 ranking did.  Threshold keys from b0.
+//   phase B   lane = direction.  Brute-force DPX screen of the block bounds (n/32 virtual points):
+//             bitmask of the blocks that may hold a point above b0; 32x32 bit transposes (warp
+//             shuffles) turn it into one word per (block, 32 directions) in shared memory.
+//   phase C   warp = block, lane = point.  The block's keys sit in registers; the warp walks the set
+//             bits of the block's direction words, tests its 32 points against that direction's
+//             thresholds (W VIADDMNMX + one vote) and appends the (direction, point) candidates to a
+//             list in shared memory.
+//   phase D   lane = candidate.  Exact FP64 evaluation (the reference's products and comparisons),
+//             folded into the direction's max with a shared-memory atomicMax on the bit pattern
+//             (max is exact and order-free, values are >= 0).
+//   Large point sets are processed in segments of blocks; the thresholds are refreshed from the
+//   running max between segments.
 //
 // Every discarded point/block fails a conservative key test against thresholds derived from a value
 // that is <= the final max, so the final max — and s^d — is bit-identical to the brute-force kernels.
 #pragma once
 
 static constexpr int kBpBlock = 32;           // points per block = lanes per warp
-static constexpr int kBpThreads = 256;        // 8 warps, all of them consumers
-static constexpr int kBpR = 2;                // directions per thread in phases A and B
+static constexpr int kBpThreads = 256;        // 8 warps
 static constexpr int kBpG = 4;                // block pairs per group in phase B ((G*D) % 4 == 0)
-static constexpr int kBpPivots = 64;
+static constexpr int kBpMaxPivots = 256;
+static constexpr int kBpCandCap = 4096;       // candidate list entries per chunk (overflow is evaluated in place)
+static constexpr int kBpPtBits = 23;          // candidate entry = direction << 23 | point
 
 struct BpArgs {
     const double *pts;        // [n_pad][D] FP64, block order
-    const double *pivots;     // [n_piv][D] FP64 warm-up set
+    const float *piv32;       // [n_piv][D] FP32 copies of the pivots
+    const unsigned *piv_idx;  // [n_piv] row of each pivot in pts
     int n_piv;
-    const unsigned *pkeys;    // [n_pad][W]
-    const unsigned *bkeys;    // [nb][W]
+    const unsigned *pkeys;    // [nb][W][32]
     const unsigned *bpair;    // [nb_pad/2][D]
     int nb;                   // blocks
     int nb_pad;               // multiple of 2*kBpG
-    int seg_blocks;           // blocks per segment (multiple of 32 and of 2*kBpG)
-    int resident;             // 1: all block bounds stay in shared memory (loaded once per CTA, no CTA barriers later)
+    int seg_blocks;           // blocks per segment (multiple of 32)
     const double *dirs;       // [count][2][D]
     ull count;
     double *cta_sums;
     double *values;
     ull *slow_counter;
-    double qscale[32], qlos[32];
+    double qscale[HVB200_MAXD], qlos[HVB200_MAXD];
 };
+
+// shared-memory carve-up, used by the kernel and by the host to size the launch
+struct BpSmem {
+    size_t thr, bnd, mask, best, piv, cand, bar, red, total;
+    int mask_stride;
+};
+__host__ __device__ inline BpSmem bp_smem_layout(int D, int R, int seg_blocks, int n_piv)
+{
+    const int W = (D + 1) / 2, WP = (W + 3) & ~3, CH = kBpThreads * R, DW = CH / 32;
+    BpSmem s;
+    size_t o = 0;
+    s.thr = o;  o += (size_t)CH * WP * 4;
+    s.bnd = o;  o += (size_t)(seg_blocks / 2) * D * 4;
+    s.mask_stride = seg_blocks + 1;
+    s.mask = o; o += ((size_t)DW * s.mask_stride * 4 + 15) & ~(size_t)15;
+    s.best = o; o += (size_t)CH * 8;
+    s.piv = o;  o += ((size_t)n_piv * D * 4 + 15) & ~(size_t)15;
+    s.cand = o; o += (size_t)kBpCandCap * 4;
+    s.bar = o;  o += 16;
+    s.red = o;  o += 8 * 8;
+    s.total = o;
+    return s;
+}
 
 // key of one objective in "negated" form, single half-word (not duplicated)
 __device__ __forceinline__ unsigned bp_neg_key16(double best_m, double winv, double scale, double lo_s)
@@ -57,57 +89,72 @@ __device__ __forceinline__ unsigned bp_neg_key16(double best_m, double winv, dou
     return (unsigned)(-kt) & 0xffffu;
 }
 
-template <int D>
-struct BpW { static constexpr int value = (D + 1) / 2; };
-
 // mask bit -> block index within its 32-block word (phase B writes bit 4h+g of byte `grp` for block 8*grp + 2g + h)
 __device__ __forceinline__ int bp_block_of_bit(int bit)
 {
     return (bit & 24) | ((bit & 3) << 1) | ((bit >> 2) & 1);
 }
 
-// Thresholds of one direction in point packing (two objectives per word), computed by the whole warp:
-// lane j < W builds word j, then every lane collects all W words.
-template <int D>
-__device__ __forceinline__ void bp_point_thresholds(double best, const double *__restrict__ winv, const BpArgs &a,
-                                                    int lane, unsigned (&pT)[BpW<D>::value])
+// 32x32 bit-matrix transpose across a warp: on return bit i of lane j = bit j of lane i on entry.
+__device__ __forceinline__ unsigned bp_transpose32(unsigned x, int lane)
 {
-    constexpr int W = BpW<D>::value;
-    const double best_m = best * (1.0 - 0x1p-20);
-    unsigned mine = 0;
-    if (lane < W) {
-        const int k0 = 2 * lane, k1 = 2 * lane + 1;
-        const unsigned lo = bp_neg_key16(best_m, __ldg(winv + k0), a.qscale[k0 < 32 ? k0 : 0], a.qlos[k0 < 32 ? k0 : 0]);
-        unsigned hi = 0;                                       // dummy objective of an odd D: threshold key 0
-        if (k1 < D) hi = bp_neg_key16(best_m, __ldg(winv + k1), a.qscale[k1 < 32 ? k1 : 0], a.qlos[k1 < 32 ? k1 : 0]);
-        mine = lo | (hi << 16);
-    }
 #pragma unroll
-    for (int j = 0; j < W; j++) pT[j] = __shfl_sync(0xffffffffu, mine, j);
+    for (int j = 16; j >= 1; j >>= 1) {
+        const unsigned m = j == 16 ? 0x0000ffffu : (j == 8 ? 0x00ff00ffu : (j == 4 ? 0x0f0f0f0fu : (j == 2 ? 0x33333333u : 0x55555555u)));
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+    }
+    return x;
 }
 
+// exact value of one point for one direction, the reference's arithmetic (c/hvapprox.c:81-102)
 template <int D>
-__global__ void __launch_bounds__(kBpThreads, 3) k_maxmin_bp(const __grid_constant__ BpArgs a)
+__device__ __forceinline__ double bp_exact(const double *__restrict__ pp, const double *__restrict__ rr)
 {
-    constexpr int R = kBpR, G = kBpG, W = BpW<D>::value;
+    double m = __ldg(pp) * __ldg(rr);
+#pragma unroll
+    for (int k = 1; k < D; k++) {
+        const double t = __ldg(pp + k) * __ldg(rr + k);
+        m = (t < m) ? t : m;
+    }
+    return m;
+}
+
+template <int D, int R>
+__device__ __forceinline__ void bp_candidate(const BpArgs &a, ull chunk_base, unsigned dl, unsigned pt, long long *bestbits)
+{
+    const double m = bp_exact<D>(a.pts + (size_t)pt * D, a.dirs + (chunk_base + dl) * (2 * D));
+    if (m > 0.0) atomicMax(bestbits + dl, __double_as_longlong(m));
+}
+
+template <int D, int R>
+__global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(const __grid_constant__ BpArgs a)
+{
+    constexpr int G = kBpG, W = (D + 1) / 2, WP = (W + 3) & ~3, CH = kBpThreads * R, DW = CH / 32;
     static_assert((G * D) % 4 == 0, "group of block pairs must be whole 16-byte words");
+    static_assert(CH <= (1 << (32 - kBpPtBits)), "direction index must fit the candidate entry");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr ull CH = (ull)kBpThreads * R;
-    const int bnd_pairs = a.resident ? a.nb_pad / 2 : a.seg_blocks / 2;
-    const int seg_words = a.seg_blocks / 32;                       // mask words per direction and segment
-    unsigned *bnd = reinterpret_cast<unsigned *>(smem_raw);        // [bnd_pairs][D]
-    unsigned *mask = bnd + (size_t)bnd_pairs * D;                  // [CH][seg_words]
-    double *pivots = reinterpret_cast<double *>(mask + (size_t)CH * seg_words);
-    ull *bar = reinterpret_cast<ull *>(pivots + (size_t)kBpPivots * D);
-    double *red = reinterpret_cast<double *>(bar + 1);
+    const BpSmem L = bp_smem_layout(D, R, a.seg_blocks, a.n_piv);
+    unsigned *thr = reinterpret_cast<unsigned *>(smem_raw + L.thr);          // [CH][WP]
+    unsigned *bnd = reinterpret_cast<unsigned *>(smem_raw + L.bnd);          // [seg_blocks/2][D]
+    unsigned *maskT = reinterpret_cast<unsigned *>(smem_raw + L.mask);       // [DW][mask_stride]
+    long long *bestbits = reinterpret_cast<long long *>(smem_raw + L.best);  // [CH]
+    float *piv = reinterpret_cast<float *>(smem_raw + L.piv);                // [n_piv][D]
+    unsigned *cand = reinterpret_cast<unsigned *>(smem_raw + L.cand);        // [kBpCandCap]
+    ull *bar = reinterpret_cast<ull *>(smem_raw + L.bar);
+    unsigned *ctr = reinterpret_cast<unsigned *>(bar + 1);
+    double *red = reinterpret_cast<double *>(smem_raw + L.red);
+    const int mstride = L.mask_stride;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    for (int i = tid; i < a.n_piv * D; i += kBpThreads) pivots[i] = a.pivots[i];
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); *ctr = 0; }
+    for (int i = tid; i < a.n_piv * D; i += kBpThreads) piv[i] = a.piv32[i];
     __syncthreads();
     unsigned phase = 0;                                            // parity of the bounds barrier
-    if (a.resident) {
-        // all block bounds fit: one TMA bulk copy per CTA, after which the warps never meet again
+    const int n_seg = (a.nb_pad + a.seg_blocks - 1) / a.seg_blocks;
+    const bool resident = n_seg == 1;
+    if (resident) {
+        // all block bounds fit: one TMA bulk copy per CTA
         if (tid == 0) {
             const unsigned bytes = (unsigned)(a.nb_pad / 2) * D * 4u;
             mbar_arrive_expect_tx(bar, bytes);
@@ -118,277 +165,223 @@ __global__ void __launch_bounds__(kBpThreads, 3) k_maxmin_bp(const __grid_consta
     }
 
     const ull n_chunks = (a.count + CH - 1) / CH;
-    const int n_seg = (a.nb_pad + a.seg_blocks - 1) / a.seg_blocks;
     double acc = 0.0;
-    ull slow = 0, c_surv = 0, c_rounds = 0, c_live = 0, c_dirs = 0;
+    ull slow = 0;
 
     for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        ull sample[R];
+        const ull chunk_base = chunk * CH;
+        if (!resident && tid == 0) {
+            // first segment of this chunk; the previous chunk's phase B is behind several CTA barriers
+            const unsigned bytes = (unsigned)(min(a.seg_blocks, a.nb_pad) / 2) * D * 4u;
+            mbar_arrive_expect_tx(bar, bytes);
+            tma_load_1d(bnd, a.bpair, bytes, bar);
+        }
         bool valid[R];
-        double best[R];
-        unsigned negT[R][D];                                       // phase-B packing: key duplicated in both halves
+        // ---- phase A: FP32 ranking of the pivots, exact value of the best one
+        {
+            float rf[R][D];
+            float bv[R];
+            int bi[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            sample[r] = chunk * CH + (ull)r * kBpThreads + tid;
-            valid[r] = sample[r] < a.count;
-            best[r] = 0.0;
-            if (valid[r]) {
-                // ---- phase A: exact warm-up over the pivots
-                const double *dir = a.dirs + sample[r] * (2 * D);
-                double rr[D];
+            for (int r = 0; r < R; r++) {
+                const ull smp = chunk_base + (ull)r * kBpThreads + tid;
+                valid[r] = smp < a.count;
+                const double *dir = a.dirs + (valid[r] ? smp : 0) * (2 * D);
 #pragma unroll
-                for (int k = 0; k < D; k++) rr[k] = __ldg(dir + k);
-                double b = 0.0;
+                for (int k = 0; k < D; k++) rf[r][k] = (float)__ldg(dir + k);
+                bv[r] = -1.0f;
+                bi[r] = 0;
+            }
 #pragma unroll 2
-                for (int i = 0; i < a.n_piv; i++) {
-                    const double *pp = pivots + i * D;
-                    double m = pp[0] * rr[0];
+            for (int i = 0; i < a.n_piv; i++) {
+                const float *pp = piv + i * D;
+                float pk[D];
 #pragma unroll
-                    for (int k = 1; k < D; k++) {
-                        const double t = pp[k] * rr[k];
-                        m = (t < m) ? t : m;
-                    }
-                    b = (m > b) ? m : b;
+                for (int k = 0; k < D; k++) pk[k] = pp[k];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    float m = pk[0] * rf[r][0];
+#pragma unroll
+                    for (int k = 1; k < D; k++) m = fminf(m, pk[k] * rf[r][k]);
+                    if (m > bv[r]) { bv[r] = m; bi[r] = i; }
                 }
-                best[r] = b;
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                double b = 0.0;
+                if (valid[r] && a.n_piv > 0) {
+                    const ull smp = chunk_base + (ull)r * kBpThreads + tid;
+                    const double m = bp_exact<D>(a.pts + (size_t)__ldg(a.piv_idx + bi[r]) * D, a.dirs + smp * (2 * D));
+                    b = (m > 0.0) ? m : 0.0;
+                }
+                bestbits[r * kBpThreads + tid] = __double_as_longlong(b);
             }
         }
 
         for (int seg = 0; seg < n_seg; seg++) {
             const int seg0 = seg * a.seg_blocks;                                   // first block of the segment
             const int seg_nb = min(a.seg_blocks, a.nb_pad - seg0);                 // blocks in it (multiple of 2G)
-            // ---- stage the segment's block bounds (pair layout) with one TMA bulk copy
-            if (!a.resident) {
-                __syncthreads();                                                   // previous users of bnd are done
-                if (tid == 0) {
-                    const unsigned bytes = (unsigned)(seg_nb / 2) * D * 4u;
-                    mbar_arrive_expect_tx(bar, bytes);
-                    tma_load_1d(bnd, a.bpair + (size_t)(seg0 / 2) * D, bytes, bar);
-                }
-            }
-            // thresholds for phase B from the current best
+            // ---- thresholds from the current lower bound: phase-B packing in registers (key duplicated in
+            //      both halves), phase-C packing (two objectives per word) in shared memory
+            unsigned negT[R][D];
 #pragma unroll
             for (int r = 0; r < R; r++) {
+                const int dl = r * kBpThreads + tid;
                 if (valid[r]) {
-                    const double *winv = a.dirs + sample[r] * (2 * D) + D;
-                    const double best_m = best[r] * (1.0 - 0x1p-20);
+                    const double *winv = a.dirs + (chunk_base + dl) * (2 * D) + D;
+                    const double best_m = __longlong_as_double(bestbits[dl]) * (1.0 - 0x1p-20);
 #pragma unroll
-                    for (int k = 0; k < D; k++)
-                        negT[r][k] = bp_neg_key16(best_m, __ldg(winv + k), a.qscale[k], a.qlos[k]) * 0x10001u;
+                    for (int k = 0; k < D; k++) negT[r][k] = bp_neg_key16(best_m, __ldg(winv + k), a.qscale[k], a.qlos[k]);
+                    unsigned tw[WP];
+#pragma unroll
+                    for (int j = 0; j < WP; j++) {
+                        tw[j] = 0;
+                        if (2 * j < D) tw[j] = negT[r][2 * j];
+                        if (2 * j + 1 < D) tw[j] |= negT[r][2 * j + 1] << 16;   // dummy objective of an odd D: threshold key 0
+                    }
+                    uint4 *dst = reinterpret_cast<uint4 *>(thr + (size_t)dl * WP);
+#pragma unroll
+                    for (int q = 0; q < WP / 4; q++) dst[q] = make_uint4(tw[4 * q], tw[4 * q + 1], tw[4 * q + 2], tw[4 * q + 3]);
+#pragma unroll
+                    for (int k = 0; k < D; k++) negT[r][k] *= 0x10001u;
                 } else {
                     const unsigned v = ((unsigned)(-(kKeyScale + 1)) & 0xffffu) * 0x10001u;      // nothing passes
 #pragma unroll
                     for (int k = 0; k < D; k++) negT[r][k] = v;
                 }
             }
-            if (!a.resident) {
+            if (!resident) {
                 mbar_wait(bar, phase);
                 phase ^= 1u;
             }
-            __syncwarp();                 // the warp's mask rows of the previous segment/chunk are no longer read
 
             // ---- phase B: screen the block bounds, lane = direction
-            unsigned *row[R];
+            {
+                const uint4 *bnd4 = reinterpret_cast<const uint4 *>(bnd + (resident ? (size_t)(seg0 / 2) * D : 0));
+                unsigned wacc[R];
 #pragma unroll
-            for (int r = 0; r < R; r++) row[r] = mask + (size_t)(r * kBpThreads + tid) * seg_words;
-            const uint4 *bnd4 = reinterpret_cast<const uint4 *>(bnd + (a.resident ? (size_t)(seg0 / 2) * D : 0));
-            unsigned wacc[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) wacc[r] = 0;
-            const int n_groups = seg_nb / (2 * G);
+                for (int r = 0; r < R; r++) wacc[r] = 0;
+                const int n_groups = seg_nb / (2 * G);
 #pragma unroll 1
-            for (int gi = 0; gi < n_groups; gi++) {
-                const uint4 *gp = bnd4 + (size_t)gi * (G * D / 4);
-                unsigned am[R][G];
+                for (int gi = 0; gi < n_groups; gi++) {
+                    const uint4 *gp = bnd4 + (size_t)gi * (G * D / 4);
+                    unsigned am[R][G];
 #pragma unroll
-                for (int r = 0; r < R; r++)
+                    for (int r = 0; r < R; r++)
 #pragma unroll
-                    for (int g = 0; g < G; g++) am[r][g] = 0x7fff7fffu;
+                        for (int g = 0; g < G; g++) am[r][g] = 0x7fff7fffu;
 #pragma unroll
-                for (int j = 0; j < (G * D) / 4; j++) {
-                    const uint4 w = gp[j];
+                    for (int j = 0; j < (G * D) / 4; j++) {
+                        const uint4 w = gp[j];
 #pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const int e = 4 * j + h, g = e / D, k = e % D;
-                        const unsigned wh = h == 0 ? w.x : (h == 1 ? w.y : (h == 2 ? w.z : w.w));
+                        for (int h = 0; h < 4; h++) {
+                            const int e = 4 * j + h, g = e / D, k = e % D;
+                            const unsigned wh = h == 0 ? w.x : (h == 1 ? w.y : (h == 2 ? w.z : w.w));
 #pragma unroll
-                        for (int r = 0; r < R; r++) am[r][g] = __viaddmin_s16x2(wh, negT[r][k], am[r][g]);
+                            for (int r = 0; r < R; r++) am[r][g] = __viaddmin_s16x2(wh, negT[r][k], am[r][g]);
+                        }
+                    }
+                    // 2G = 8 blocks per group -> 8 mask bits; 4 groups fill one 32-bit mask word.  Bit layout of
+                    // a group's byte: bit (4h + g) <-> block 2g + h of the group (see bp_block_of_bit)
+                    const int shift = (gi & 3) * (2 * G);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        unsigned neg = 0;                                  // sign bits: low halves -> bits 0..3, high halves -> bits 16..19
+#pragma unroll
+                        for (int g = 0; g < G; g++) neg |= ((am[r][g] & 0x80008000u) >> 15) << g;
+                        const unsigned byte = ((neg | (neg >> 12)) & 0xffu) ^ 0xffu;      // live = sign clear
+                        wacc[r] |= byte << shift;
+                    }
+                    if ((gi & 3) == 3 || gi == n_groups - 1) {
+                        // 32 blocks x 32 directions of this warp: transpose, lane = block afterwards
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const unsigned t = bp_transpose32(wacc[r], lane);
+                            maskT[(r * (kBpThreads / 32) + warp) * mstride + (gi >> 2) * 32 + bp_block_of_bit(lane)] = t;
+                            wacc[r] = 0;
+                        }
                     }
                 }
-                // 2G = 8 blocks per group -> 8 mask bits; 4 groups fill one 32-bit mask word.  Bit layout of
-                // a group's byte: bit (4h + g) <-> block 2g + h of the group (see bp_block_of_bit)
-                const int shift = (gi & 3) * (2 * G);
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    unsigned neg = 0;                                  // sign bits: low halves -> bits 0..3, high halves -> bits 16..19
-#pragma unroll
-                    for (int g = 0; g < G; g++) neg |= ((am[r][g] & 0x80008000u) >> 15) << g;
-                    const unsigned byte = ((neg | (neg >> 12)) & 0xffu) ^ 0xffu;      // live = sign clear
-                    wacc[r] |= byte << shift;
-                    if ((gi & 3) == 3 || gi == n_groups - 1) { row[r][gi >> 2] = wacc[r]; wacc[r] = 0; }
-                }
             }
-            __syncwarp();                 // a warp's mask rows are written and read by that warp only
+            __syncthreads();                  // maskT, thr, bestbits complete; bnd no longer read
+            if (!resident && tid == 0 && seg + 1 < n_seg) {
+                const int nxt = min(a.seg_blocks, a.nb_pad - (seg0 + a.seg_blocks));
+                const unsigned bytes = (unsigned)(nxt / 2) * D * 4u;
+                mbar_arrive_expect_tx(bar, bytes);
+                tma_load_1d(bnd, a.bpair + (size_t)((seg0 + a.seg_blocks) / 2) * D, bytes, bar);
+            }
 
-            // ---- phase C: warp = direction
-            const int words_used = (seg_nb + 31) / 32;
-#pragma unroll
-            for (int r = 0; r < R; r++) {
+            // ---- phase C: warp = block, lane = point
+            const int seg_real = min(seg_nb, a.nb - seg0);                         // real (non-padding) blocks
 #pragma unroll 1
-                for (int owner = 0; owner < 32; owner++) {
-                    const ull smp = chunk * CH + (ull)r * kBpThreads + (ull)(warp * 32 + owner);
-                    if (smp >= a.count) continue;                                  // uniform in the warp
-                    const unsigned *mrow = mask + (size_t)(r * kBpThreads + warp * 32 + owner) * seg_words;
-                    // any surviving block at all?  (most directions are settled by the warm-up)
-                    unsigned any = 0;
-                    for (int wi = lane; wi < words_used; wi += 32) any |= mrow[wi];
-                    if (__ballot_sync(0xffffffffu, any != 0) == 0) continue;
-                    c_dirs++;
-                    double bcur = __shfl_sync(0xffffffffu, best[r], owner);
-                    const double *dir = a.dirs + smp * (2 * D);
-                    const double rlane = (lane < D) ? __ldg(dir + lane) : 0.0;     // lane k keeps r_k for the exact evaluations
-                    unsigned pT[W];
-                    bp_point_thresholds<D>(bcur, dir + D, a, lane, pT);
-#pragma unroll 1
-                    for (int wi = 0; wi < words_used; wi++) {
-                        const unsigned word = mrow[wi];
-                        if (word == 0) continue;
-                        c_surv += __popc(word); c_rounds++;
-                        // re-check 32 block bounds in parallel against the current thresholds (lane = mask bit)
-                        bool live = false;
-                        const int wblk = seg0 + wi * 32;                       // first block of this mask word
-                        const int blk = wblk + bp_block_of_bit(lane);
-                        if (((word >> lane) & 1u) && blk < a.nb) {
-                            const unsigned *bk = a.bkeys + (unsigned)blk * W;
-                            unsigned m16 = 0x7fff7fffu;
+            for (int b = warp; b < seg_real; b += kBpThreads / 32) {
+                const unsigned myw = (lane < DW) ? maskT[lane * mstride + b] : 0u;
+                unsigned nz = __ballot_sync(0xffffffffu, myw != 0u);
+                if (nz == 0) continue;
+                const unsigned blk = (unsigned)(seg0 + b);
+                unsigned kw[W];
 #pragma unroll
-                            for (int j = 0; j < W; j++) m16 = __viaddmin_s16x2(__ldg(bk + j), pT[j], m16);
-                            live = (m16 & 0x80008000u) == 0;
+                for (int j = 0; j < W; j++) kw[j] = __ldg(a.pkeys + ((size_t)blk * W + j) * 32 + lane);
+                while (nz) {
+                    const int dw = __ffs((int)nz) - 1;
+                    nz &= nz - 1;
+                    unsigned word = __shfl_sync(0xffffffffu, myw, dw);
+                    while (word) {
+                        const int bit = __ffs((int)word) - 1;
+                        word &= word - 1;
+                        const unsigned dl = (unsigned)(dw * 32 + bit);
+                        const uint4 *t4 = reinterpret_cast<const uint4 *>(thr + (size_t)dl * WP);
+                        unsigned m16 = 0x7fff7fffu;
+#pragma unroll
+                        for (int q = 0; q < WP / 4; q++) {
+                            const uint4 t = t4[q];
+                            if (4 * q + 0 < W) m16 = __viaddmin_s16x2(kw[4 * q + 0 < W ? 4 * q + 0 : 0], t.x, m16);
+                            if (4 * q + 1 < W) m16 = __viaddmin_s16x2(kw[4 * q + 1 < W ? 4 * q + 1 : 0], t.y, m16);
+                            if (4 * q + 2 < W) m16 = __viaddmin_s16x2(kw[4 * q + 2 < W ? 4 * q + 2 : 0], t.z, m16);
+                            if (4 * q + 3 < W) m16 = __viaddmin_s16x2(kw[4 * q + 3 < W ? 4 * q + 3 : 0], t.w, m16);
                         }
-                        unsigned lmask = __ballot_sync(0xffffffffu, live);
-                        c_live += __popc(lmask);
-                        // test the points of the live blocks, four blocks per round: the 4*W key loads are
-                        // issued back to back so that their L1/L2 latencies overlap
-                        while (lmask) {
-                            int bb[4];
-                            unsigned m16[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                bb[u] = lmask ? wblk + bp_block_of_bit(__ffs((int)lmask) - 1) : -1;
-                                lmask &= lmask - 1;                                     // (0 & anything) stays 0
-                            }
-                            unsigned kw[4][W];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const unsigned *pk = a.pkeys + ((unsigned)(bb[u] < 0 ? wblk : bb[u]) * kBpBlock + lane) * W;
-#pragma unroll
-                                for (int j = 0; j < W; j++) kw[u][j] = __ldg(pk + j);
-                            }
-                            unsigned cm[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                m16[u] = 0x7fff7fffu;
-#pragma unroll
-                                for (int j = 0; j < W; j++) m16[u] = __viaddmin_s16x2(kw[u][j], pT[j], m16[u]);
-                                cm[u] = __ballot_sync(0xffffffffu, bb[u] >= 0 && (m16[u] & 0x80008000u) == 0);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                unsigned cmask = cm[u];
-                                while (cmask) {
-                                    const int q = __ffs((int)cmask) - 1;
-                                    cmask &= cmask - 1;
-                                    // exact FP64 evaluation by the warp: lane = objective
-                                    const ull cp = (ull)bb[u] * kBpBlock + q;
-                                    double prod = __longlong_as_double(0x7ff0000000000000LL);
-                                    if (lane < D) prod = __ldg(a.pts + cp * D + lane) * rlane;
-#pragma unroll
-                                    for (int off = 16; off > 0; off >>= 1) {
-                                        const double o = __shfl_xor_sync(0xffffffffu, prod, off);
-                                        prod = (o < prod) ? o : prod;
-                                    }
-                                    slow++;
-                                    if (prod > bcur) {                             // uniform: every lane holds the min
-                                        bcur = prod;
-                                        bp_point_thresholds<D>(bcur, dir + D, a, lane, pT);
-                                    }
-                                }
-                            }
+                        if ((m16 & 0x80008000u) == 0u) {
+                            const unsigned pt = blk * kBpBlock + lane;
+                            const unsigned slot = atomicAdd(ctr, 1u);
+                            if (slot < (unsigned)kBpCandCap) cand[slot] = (dl << kBpPtBits) | pt;
+                            else { bp_candidate<D, R>(a, chunk_base, dl, pt, bestbits); slow++; }
                         }
                     }
-                    if (lane == owner) best[r] = bcur;
                 }
             }
+            __syncthreads();
+
+            // ---- phase D: lane = candidate
+            {
+                const unsigned nc = min(*ctr, (unsigned)kBpCandCap);
+                for (unsigned i = tid; i < nc; i += kBpThreads) {
+                    const unsigned e = cand[i];
+                    bp_candidate<D, R>(a, chunk_base, e >> kBpPtBits, e & ((1u << kBpPtBits) - 1u), bestbits);
+                    slow++;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) *ctr = 0;
         }
 
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const double v = pow_chain<D>(best[r]);
+            const double v = pow_chain<D>(__longlong_as_double(bestbits[r * kBpThreads + tid]));
             if (valid[r]) {
                 acc += v;
-                if (a.values) a.values[sample[r]] = v;
+                if (a.values) a.values[chunk_base + (ull)r * kBpThreads + tid] = v;
             }
         }
     }
 
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-    if (lane == 0) red[warp] = acc;
-    if (a.slow_counter) {
-        // `slow` was counted identically by all lanes of a warp: report lane 0's
-        if (lane == 0 && slow) atomicAdd(a.slow_counter, slow);
-        if (lane == 0) { atomicAdd(a.slow_counter + 1, c_surv); atomicAdd(a.slow_counter + 2, c_rounds); atomicAdd(a.slow_counter + 3, c_live); atomicAdd(a.slow_counter + 4, c_dirs); }
+    for (int off = 16; off > 0; off >>= 1) {
+        acc += __shfl_down_sync(0xffffffffu, acc, off);
+        slow += __shfl_down_sync(0xffffffffu, slow, off);
     }
+    if (lane == 0) red[warp] = acc;
+    if (a.slow_counter && lane == 0 && slow) atomicAdd(a.slow_counter, slow);
     __syncthreads();
     if (tid == 0)
         a.cta_sums[blockIdx.x] += ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-}
-
-// ---- key construction ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bp_pkeys(const double *__restrict__ pts, ull n, ull n_pad, int d, int W,
-                                                  const double *__restrict__ qlo, const double *__restrict__ qscale,
-                                                  unsigned *__restrict__ pkeys)
-{
-    const ull w = (ull)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_pad * (ull)W) return;
-    const ull i = w / W;
-    const int j = (int)(w - i * W);
-    unsigned word = 0;
-    for (int h = 0; h < 2; h++) {
-        const int k = 2 * j + h;
-        unsigned key;
-        if (i >= n) key = 0xffffu;                                   // padding point: -1, never a candidate
-        else if (k >= d) key = (unsigned)kKeyScale;                  // dummy objective of an odd d: always passes
-        else {
-            double f = ceil((pts[i * d + k] - qlo[k]) * qscale[k]);
-            f = f < 0.0 ? 0.0 : (f > (double)kKeyScale ? (double)kKeyScale : f);
-            key = (unsigned)(int)f;
-        }
-        word |= key << (16 * h);
-    }
-    pkeys[w] = word;
-}
-__global__ void __launch_bounds__(256) k_bp_bkeys(const unsigned *__restrict__ pkeys, int nb, int W, unsigned *__restrict__ bkeys)
-{
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nb * W) return;
-    const int b = w / W, j = w - b * W;
-    unsigned m = 0x80008000u;                                        // (-32768, -32768)
-    for (int q = 0; q < kBpBlock; q++) m = __vmaxs2(m, pkeys[((size_t)b * kBpBlock + q) * W + j]);
-    bkeys[w] = m;
-}
-__global__ void __launch_bounds__(256) k_bp_pairs(const unsigned *__restrict__ bkeys, int nb, int nb_pad, int d, int W,
-                                                  unsigned *__restrict__ bpair)
-{
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= (nb_pad / 2) * d) return;
-    const int pr = w / d, k = w - pr * d;
-    unsigned word = 0;
-    for (int h = 0; h < 2; h++) {
-        const int b = 2 * pr + h;
-        unsigned key = 0xffffu;                                      // padding block: -1
-        if (b < nb) key = (bkeys[(size_t)b * W + k / 2] >> (16 * (k & 1))) & 0xffffu;
-        word |= key << (16 * h);
-    }
-    bpair[w] = word;
 }

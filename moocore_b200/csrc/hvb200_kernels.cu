@@ -1237,10 +1237,12 @@ struct DevPlan {
     bool ordered = false;                // points already sorted by probe arg-max frequency
     // block-pruned kernel (hvb200_bp.cuh)
     bool bp_ready = false;
-    double *bp_pts = nullptr, *bp_piv = nullptr; size_t bp_pts_cap = 0;
-    unsigned *bp_pkeys = nullptr, *bp_bkeys = nullptr, *bp_bpair = nullptr; size_t bp_keys_cap = 0;
-    int bp_nb = 0, bp_nb_pad = 0, bp_seg_blocks = 0, bp_npiv = 0, bp_resident = 0;
+    double *bp_pts = nullptr; size_t bp_pts_cap = 0;
+    float *bp_piv32 = nullptr; unsigned *bp_pividx = nullptr;
+    unsigned *bp_pkeys = nullptr, *bp_bpair = nullptr; size_t bp_keys_cap = 0, bp_pair_cap = 0;
+    int bp_nb = 0, bp_nb_pad = 0, bp_seg_blocks = 0, bp_npiv = 0;
     size_t bp_smem = 0;
+    double bp_qscale[HVB200_MAXD] = {0}, bp_qlos[HVB200_MAXD] = {0};
     double *pts_tmp = nullptr; size_t pts_tmp_cap = 0;
     unsigned *wins = nullptr; size_t wins_cap = 0;      // 2n words: win counts, then the order
     int k_tile_pairs = 0, k_n_tiles = 0, k_stage_bytes = 0;
@@ -1558,7 +1560,7 @@ static void devplan_release(DevPlan *dp)
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
     cudaFree(dp->dirs_buf[1]); cudaFree(dp->pts_tmp); cudaFree(dp->wins);
-    cudaFree(dp->bp_pts); cudaFree(dp->bp_piv); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bkeys); cudaFree(dp->bp_bpair);
+    cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
     for (int i = 0; i < 2; i++) { if (dp->ev_gen[i]) cudaEventDestroy(dp->ev_gen[i]); if (dp->ev_used[i]) cudaEventDestroy(dp->ev_used[i]); }
     if (dp->ev_begin) cudaEventDestroy(dp->ev_begin);
     if (dp->gen_stream) cudaStreamDestroy(dp->gen_stream);
@@ -1603,18 +1605,46 @@ static int span_begin(DevPlan *dp, int kind)
 static void span_end(DevPlan *dp, int b) { if (b >= 0) cudaEventRecord(dp->ev_pool[b], dp->stream); }
 
 
-// Build the block-pruned kernel's inputs (hvb200_bp.cuh): warm-up set = the most frequent probe winners,
-// blocks = points sorted by weakest normalised objective, three key layouts.
+// Build the block-pruned kernel's inputs (hvb200_bp.cuh): pivots = the most frequent probe winners,
+// blocks = 32 consecutive points of a kd-tree order, two key layouts.  Host work is O(n d log n), once per plan.
 typedef void (*bp_fn)(const BpArgs);
+static constexpr int bp_R_of(int D) { return D <= 16 ? 2 : 1; }
 template <int D>
 static bp_fn pick_bp(int d)
 {
     if constexpr (D < 2) {
         return nullptr;
     } else {
-        if (d == D) return (bp_fn)k_maxmin_bp<D>;
+        if (d == D) return (bp_fn)k_maxmin_bp<D, bp_R_of(D)>;
         return pick_bp<D - 1>(d);
     }
+}
+static void bp_kd_order(const std::vector<double> &norm, int d, std::vector<unsigned> &idx, size_t lo, size_t hi)
+{
+    const size_t cnt = hi - lo;
+    if (cnt <= (size_t)kBpBlock) return;
+    int best_k = 0;
+    double best_spread = -1.0;
+    for (int k = 0; k < d; k++) {
+        double mn = INFINITY, mx = -INFINITY;
+        for (size_t i = lo; i < hi; i++) { const double v = norm[(size_t)idx[i] * d + k]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+        if (mx - mn > best_spread) { best_spread = mx - mn; best_k = k; }
+    }
+    size_t half = (cnt / 2 + kBpBlock - 1) / kBpBlock * kBpBlock;      // left part = whole blocks
+    if (half >= cnt) half = cnt / 2;
+    const int k = best_k;
+    std::nth_element(idx.begin() + lo, idx.begin() + lo + half, idx.begin() + hi, [&](unsigned x, unsigned y) {
+        const double vx = norm[(size_t)x * d + k], vy = norm[(size_t)y * d + k];
+        return vx != vy ? vx < vy : x < y;
+    });
+    bp_kd_order(norm, d, idx, lo, lo + half);
+    bp_kd_order(norm, d, idx, lo + half, hi);
+}
+static int bp_pivot_count()
+{
+    const char *e = getenv("HVB200_BP_PIVOTS");
+    const int v = e ? atoi(e) : 128;
+    return v < 1 ? 1 : (v > kBpMaxPivots ? kBpMaxPivots : v);
 }
 static int bp_prepare(DevPlan *dp)
 {
@@ -1637,69 +1667,120 @@ static int bp_prepare(DevPlan *dp)
     CUDA_TRY(cudaMemcpyAsync(wins.data(), dp->wins, n * sizeof(unsigned), cudaMemcpyDeviceToHost, us));
     CUDA_TRY(cudaMemcpyAsync(pts.data(), dp->pts, n * (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, us));
     CUDA_TRY(cudaStreamSynchronize(us));
-    // warm-up set: the points that won most probes
+    // key map of the point set (the same monotone map as the DPX screen, any d <= 64)
+    std::vector<double> qlo(d, INFINITY), qhi(d, -INFINITY), qscale(d, 0.0);
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < d; k++) {
+            const double v = pts[i * d + k];
+            if (v < qlo[k]) qlo[k] = v;
+            if (v > qhi[k]) qhi[k] = v;
+        }
+    for (int k = 0; k < d; k++) {
+        const double range = qhi[k] - qlo[k];
+        qscale[k] = (range > 0 && std::isfinite(range)) ? (double)kKeyScale / range : 0.0;
+        if (!std::isfinite(qscale[k])) qscale[k] = 0.0;
+        dp->bp_qscale[k] = qscale[k];
+        dp->bp_qlos[k] = qlo[k] * qscale[k] * (1.0 + 0x1p-20) + 0x1p-10;
+    }
+    // kd-tree order on the normalised coordinates
+    std::vector<double> norm(n * (size_t)d);
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < d; k++) norm[i * d + k] = qhi[k] > 0 ? pts[i * d + k] / qhi[k] : 0.0;
     std::vector<unsigned> idx(n);
     for (size_t i = 0; i < n; i++) idx[i] = (unsigned)i;
-    const size_t npiv = std::min<size_t>(n, (size_t)kBpPivots);
-    std::partial_sort(idx.begin(), idx.begin() + npiv, idx.end(),
+    bp_kd_order(norm, d, idx, 0, n);
+    std::vector<unsigned> pos(n);
+    for (size_t i = 0; i < n; i++) pos[idx[i]] = (unsigned)i;
+    // pivots: the points that won most probes
+    const size_t npiv = std::min<size_t>(n, (size_t)bp_pivot_count());
+    std::vector<unsigned> byw(n);
+    for (size_t i = 0; i < n; i++) byw[i] = (unsigned)i;
+    std::partial_sort(byw.begin(), byw.begin() + npiv, byw.end(),
                       [&](unsigned x, unsigned y) { return wins[x] != wins[y] ? wins[x] > wins[y] : x < y; });
-    std::vector<double> piv((size_t)kBpPivots * d, 0.0);
-    for (size_t i = 0; i < npiv; i++) memcpy(&piv[i * d], &pts[(size_t)idx[i] * d], d * sizeof(double));
-    // block order: weakest normalised objective, then its value
-    std::vector<double> colmax(d, 0.0);
-    for (size_t i = 0; i < n; i++) for (int k = 0; k < d; k++) colmax[k] = std::max(colmax[k], pts[i * d + k]);
-    std::vector<int> wk(n);
-    std::vector<double> wv(n);
-    for (size_t i = 0; i < n; i++) {
-        int bk = 0; double bv = INFINITY;
-        for (int k = 0; k < d; k++) { const double v = pts[i * d + k] / colmax[k]; if (v < bv) { bv = v; bk = k; } }
-        wk[i] = bk; wv[i] = bv;
+    std::vector<float> piv32(npiv * (size_t)d);
+    std::vector<unsigned> pividx(npiv);
+    for (size_t i = 0; i < npiv; i++) {
+        pividx[i] = pos[byw[i]];
+        for (int k = 0; k < d; k++) piv32[i * d + k] = (float)pts[(size_t)byw[i] * d + k];
     }
-    for (size_t i = 0; i < n; i++) idx[i] = (unsigned)i;
-    std::sort(idx.begin(), idx.end(), [&](unsigned x, unsigned y) {
-        if (wk[x] != wk[y]) return wk[x] < wk[y];
-        if (wv[x] != wv[y]) return wv[x] < wv[y];
-        return x < y;
-    });
     const int nb = (int)((n + kBpBlock - 1) / kBpBlock);
     const int nb_pad = (nb + 2 * kBpG - 1) / (2 * kBpG) * (2 * kBpG);
     const size_t n_pad = (size_t)nb_pad * kBpBlock;
     std::vector<double> sorted(n_pad * (size_t)d, 0.0);
     for (size_t i = 0; i < n; i++) memcpy(&sorted[i * d], &pts[(size_t)idx[i] * d], d * sizeof(double));
+    // point keys KP = clamp(ceil f_k(p), 0, S); padding points -1, dummy objective of an odd d = S (always passes)
+    std::vector<unsigned short> key(n_pad * (size_t)(2 * W));
+    for (size_t i = 0; i < n_pad; i++)
+        for (int k = 0; k < 2 * W; k++) {
+            unsigned short v;
+            if (i >= n) v = 0xffffu;
+            else if (k >= d) v = (unsigned short)kKeyScale;
+            else {
+                double f = ceil((sorted[i * d + k] - qlo[k]) * qscale[k]);
+                f = f < 0.0 ? 0.0 : (f > (double)kKeyScale ? (double)kKeyScale : f);
+                v = (unsigned short)(int)f;
+            }
+            key[i * (2 * W) + k] = v;
+        }
+    std::vector<unsigned> pkeys((size_t)nb_pad * W * 32);
+    for (int b = 0; b < nb_pad; b++)
+        for (int j = 0; j < W; j++)
+            for (int l = 0; l < 32; l++) {
+                const size_t i = (size_t)b * 32 + l;
+                pkeys[((size_t)b * W + j) * 32 + l] = (unsigned)key[i * (2 * W) + 2 * j] | ((unsigned)key[i * (2 * W) + 2 * j + 1] << 16);
+            }
+    // block bounds: per-objective maximum key (signed: padding -1 never raises it), two blocks per word
+    std::vector<unsigned> bpair((size_t)(nb_pad / 2) * d);
+    for (int pr = 0; pr < nb_pad / 2; pr++)
+        for (int k = 0; k < d; k++) {
+            unsigned word = 0;
+            for (int h = 0; h < 2; h++) {
+                const int b = 2 * pr + h;
+                int m = -1;
+                if (b < nb)
+                    for (int l = 0; l < 32; l++) m = std::max(m, (int)(short)key[((size_t)b * 32 + l) * (2 * W) + k]);
+                word |= ((unsigned)m & 0xffffu) << (16 * h);
+            }
+            bpair[(size_t)pr * d + k] = word;
+        }
     if (dp->bp_pts_cap < n_pad * (size_t)d) {
         cudaFree(dp->bp_pts);
         dp->bp_pts = nullptr; dp->bp_pts_cap = 0;
         CUDA_TRY(cudaMalloc(&dp->bp_pts, n_pad * (size_t)d * sizeof(double)));
         dp->bp_pts_cap = n_pad * (size_t)d;
     }
-    if (!dp->bp_piv) CUDA_TRY(cudaMalloc(&dp->bp_piv, (size_t)kBpPivots * 64 * sizeof(double)));
-    if (dp->bp_keys_cap < n_pad * (size_t)W) {
-        cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bkeys); cudaFree(dp->bp_bpair);
-        dp->bp_pkeys = dp->bp_bkeys = dp->bp_bpair = nullptr; dp->bp_keys_cap = 0;
-        CUDA_TRY(cudaMalloc(&dp->bp_pkeys, n_pad * (size_t)W * sizeof(unsigned)));
-        CUDA_TRY(cudaMalloc(&dp->bp_bkeys, (size_t)nb_pad * W * sizeof(unsigned)));
-        CUDA_TRY(cudaMalloc(&dp->bp_bpair, (size_t)(nb_pad / 2) * 32 * sizeof(unsigned)));
-        dp->bp_keys_cap = n_pad * (size_t)W;
+    if (!dp->bp_piv32) {
+        CUDA_TRY(cudaMalloc(&dp->bp_piv32, (size_t)kBpMaxPivots * HVB200_MAXD * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&dp->bp_pividx, (size_t)kBpMaxPivots * sizeof(unsigned)));
     }
-    CUDA_TRY(cudaMemcpyAsync(dp->bp_pts, sorted.data(), n_pad * (size_t)d * sizeof(double), cudaMemcpyHostToDevice, us));
-    CUDA_TRY(cudaMemcpyAsync(dp->bp_piv, piv.data(), piv.size() * sizeof(double), cudaMemcpyHostToDevice, us));
-    k_bp_pkeys<<<(unsigned)((n_pad * W + 255) / 256), 256, 0, us>>>(dp->bp_pts, (ull)n, (ull)n_pad, d, W, dp->qdev, dp->qdev + 64, dp->bp_pkeys);
-    k_bp_bkeys<<<(unsigned)((nb * W + 255) / 256), 256, 0, us>>>(dp->bp_pkeys, nb, W, dp->bp_bkeys);
-    k_bp_pairs<<<(unsigned)(((nb_pad / 2) * d + 255) / 256), 256, 0, us>>>(dp->bp_bkeys, nb, nb_pad, d, W, dp->bp_bpair);
-    CUDA_TRY(cudaGetLastError());
+    if (dp->bp_keys_cap < pkeys.size()) {
+        cudaFree(dp->bp_pkeys);
+        dp->bp_pkeys = nullptr; dp->bp_keys_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->bp_pkeys, pkeys.size() * sizeof(unsigned)));
+        dp->bp_keys_cap = pkeys.size();
+    }
+    if (dp->bp_pair_cap < bpair.size()) {
+        cudaFree(dp->bp_bpair);
+        dp->bp_bpair = nullptr; dp->bp_pair_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->bp_bpair, bpair.size() * sizeof(unsigned)));
+        dp->bp_pair_cap = bpair.size();
+    }
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_pts, sorted.data(), sorted.size() * sizeof(double), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_piv32, piv32.data(), piv32.size() * sizeof(float), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_pividx, pividx.data(), pividx.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_pkeys, pkeys.data(), pkeys.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_bpair, bpair.data(), bpair.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
     CUDA_TRY(cudaStreamSynchronize(us));              // host vectors go out of scope
     dp->bp_nb = nb;
     dp->bp_nb_pad = nb_pad;
     dp->bp_npiv = (int)npiv;
-    int seg = d <= 12 ? 1024 : 512;
-    if (nb_pad < seg) seg = (nb_pad + 31) / 32 * 32;
+    // segment = as many blocks as fit the shared-memory budget of one CTA (3 CTAs per SM up to d = 16, else 2)
+    const size_t budget = (d <= 16 ? 74 : 112) * 1024;
+    int seg = (nb_pad + 31) / 32 * 32;
+    while (seg > 32 && bp_smem_layout(d, bp_R_of(d), seg, (int)npiv).total > budget) seg -= 32;
+    if (const char *e = getenv("HVB200_BP_SEG")) { const int v = atoi(e) / 32 * 32; if (v >= 32 && v < seg) seg = v; }
     dp->bp_seg_blocks = seg;
-    // keep all block bounds in shared memory when they fit next to the masks: the warps of a CTA then
-    // never synchronise after start-up
-    const size_t all_bounds = (size_t)(nb_pad / 2) * d * 4;
-    dp->bp_resident = all_bounds <= 64 * 1024 ? 1 : 0;
-    dp->bp_smem = (dp->bp_resident ? all_bounds : (size_t)(seg / 2) * d * 4) + (size_t)kBpThreads * kBpR * (seg / 32) * 4 +
-                  (size_t)kBpPivots * d * 8 + 8 + 8 * 8 + 64;
+    dp->bp_smem = bp_smem_layout(d, bp_R_of(d), seg, (int)npiv).total;
     dp->bp_ready = true;
     return 0;
 }
@@ -1790,13 +1871,14 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     else if (plan->kernel == HVB200_KERNEL_SCREEN) mode = MODE_SCREEN;
     else if (plan->kernel == HVB200_KERNEL_BP) mode = MODE_BP;
     else if (plan->kernel == HVB200_KERNEL_AUTO && dp->n < 256) mode = MODE_EXACT;
-    if (d > 32) mode = MODE_EXACT;
+    if (mode == MODE_BP && dp->n + 256 >= ((size_t)1 << kBpPtBits)) mode = MODE_DPX;   // candidate entries hold 23-bit point indices
+    if (d > 32 && mode != MODE_BP) mode = MODE_EXACT;
     dp->kernel_used = mode;
     if (mode == MODE_BP && !dp->bp_ready && bp_prepare(dp)) return -1;
     const size_t smem = mode == MODE_DPX ? dp->k_smem_bytes : (mode == MODE_BP ? dp->bp_smem : dp->smem_bytes);
     int occ = 1;
     if (mode == MODE_BP) {
-        bp_fn fn = pick_bp<32>(d);
+        bp_fn fn = pick_bp<HVB200_MAXD>(d);
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBpThreads, smem));
@@ -2059,7 +2141,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     a.slow_counter = dp->counters + 1;
     const bool dpx = dp->kernel_used == MODE_DPX, bp = dp->kernel_used == MODE_BP;
     const size_t smem = dpx ? dp->k_smem_bytes : (bp ? dp->bp_smem : dp->smem_bytes);
-    const ull chunk = bp ? (ull)kBpThreads * kBpR
+    const ull chunk = bp ? (ull)kBpThreads * bp_R_of(d)
                          : (ull)kConsumerThreads * (dpx ? dp->kR : (dp->kernel_used == MODE_EXACT ? dp->R_exact : dp->R));
     const ull n_chunks = (count + chunk - 1) / chunk;
     const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks ? n_chunks : 1);
@@ -2067,25 +2149,24 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     if (bp) {
         BpArgs ka;
         ka.pts = dp->bp_pts;
-        ka.pivots = dp->bp_piv;
+        ka.piv32 = dp->bp_piv32;
+        ka.piv_idx = dp->bp_pividx;
         ka.n_piv = dp->bp_npiv;
         ka.pkeys = dp->bp_pkeys;
-        ka.bkeys = dp->bp_bkeys;
         ka.bpair = dp->bp_bpair;
         ka.nb = dp->bp_nb;
         ka.nb_pad = dp->bp_nb_pad;
         ka.seg_blocks = dp->bp_seg_blocks;
-        ka.resident = dp->bp_resident;
         ka.dirs = dp->dirs;
         ka.count = count;
         ka.cta_sums = dp->cta_sums;
         ka.values = a.values;
         ka.slow_counter = dp->counters + 1;
-        for (int k = 0; k < 32; k++) {
-            ka.qscale[k] = dp->qscale[k];
-            ka.qlos[k] = k < d ? dp->qlo[k] * dp->qscale[k] * (1.0 + 0x1p-20) + 0x1p-10 : 0.0;
+        for (int k = 0; k < HVB200_MAXD; k++) {
+            ka.qscale[k] = k < d ? dp->bp_qscale[k] : 0.0;
+            ka.qlos[k] = k < d ? dp->bp_qlos[k] : 0.0;
         }
-        bp_fn fn = pick_bp<32>(d);
+        bp_fn fn = pick_bp<HVB200_MAXD>(d);
         fn<<<grid, kBpThreads, smem, dp->stream>>>(ka);
     } else if (dpx) {
         DpxArgs ka;
