@@ -35,8 +35,9 @@
 static constexpr int kBpBlock = 32;           // points per block = lanes per warp
 static constexpr int kBpThreads = 256;        // 8 warps
 static constexpr int kBpG = 4;                // block pairs per group in phase B ((G*D) % 4 == 0)
-static constexpr int kBpMaxPivots = 256;
-static constexpr int kBpCandCap = 4096;       // candidate list entries per chunk (overflow is evaluated in place)
+static constexpr int kBpMaxPivots = 512;
+static constexpr int kBpCandCap = 3072;       // candidate entries per chunk in shared memory ...
+static constexpr int kBpOvfCap = 16384;       // ... then in a per-CTA global list, then evaluated in place
 static constexpr int kBpPtBits = 23;          // candidate entry = direction << 23 | point
 
 struct BpArgs {
@@ -54,26 +55,34 @@ struct BpArgs {
     double *cta_sums;
     double *values;
     ull *slow_counter;
+    unsigned *ovf;            // [grid][kBpOvfCap] candidate overflow lists
     double qscale[HVB200_MAXD], qlos[HVB200_MAXD];
 };
 
-// shared-memory carve-up, used by the kernel and by the host to size the launch
+// shared-memory carve-up, used by the kernel and by the host to size the launch.
+// Thresholds for phase C are stored as planes of 16-byte words [plane][CH + 1] (row CH = "nothing
+// passes", the padding entry of the pair lists) plus one tail plane of 1, 2 or 4 words per row.
 struct BpSmem {
-    size_t thr, bnd, mask, best, piv, cand, bar, red, total;
-    int mask_stride;
+    size_t thr, tail, bnd, mask, best, piv, cand, list, bar, red, total;
+    int mask_stride, Q, TW;
 };
 __host__ __device__ inline BpSmem bp_smem_layout(int D, int R, int seg_blocks, int n_piv)
 {
-    const int W = (D + 1) / 2, WP = (W + 3) & ~3, CH = kBpThreads * R, DW = CH / 32;
+    const int W = (D + 1) / 2, CH = kBpThreads * R, DW = CH / 32;
     BpSmem s;
+    s.Q = W / 4;
+    const int rem = W - 4 * s.Q;
+    s.TW = rem == 3 ? 4 : rem;
     size_t o = 0;
-    s.thr = o;  o += (size_t)CH * WP * 4;
+    s.thr = o;  o += (size_t)s.Q * (CH + 1) * 16;
+    s.tail = o; o += ((size_t)(CH + 1) * s.TW * 4 + 15) & ~(size_t)15;
     s.bnd = o;  o += (size_t)(seg_blocks / 2) * D * 4;
     s.mask_stride = seg_blocks + 1;
     s.mask = o; o += ((size_t)DW * s.mask_stride * 4 + 15) & ~(size_t)15;
     s.best = o; o += (size_t)CH * 8;
     s.piv = o;  o += ((size_t)n_piv * D * 4 + 15) & ~(size_t)15;
     s.cand = o; o += (size_t)kBpCandCap * 4;
+    s.list = o; o += (size_t)(kBpThreads / 32) * (CH + 8) * 2;
     s.bar = o;  o += 16;
     s.red = o;  o += 8 * 8;
     s.total = o;
@@ -127,15 +136,28 @@ __device__ __forceinline__ void bp_candidate(const BpArgs &a, ull chunk_base, un
     if (m > 0.0) atomicMax(bestbits + dl, __double_as_longlong(m));
 }
 
+// append one candidate: shared list, then the CTA's global overflow list, then evaluate in place
+template <int D, int R>
+__device__ __forceinline__ void bp_append(const BpArgs &a, ull chunk_base, unsigned slot, unsigned dl, unsigned pt,
+                                          unsigned *cand, long long *bestbits, ull &slow)
+{
+    const unsigned e = (dl << kBpPtBits) | pt;
+    if (slot < (unsigned)kBpCandCap) cand[slot] = e;
+    else if (slot < (unsigned)(kBpCandCap + kBpOvfCap)) a.ovf[(size_t)blockIdx.x * kBpOvfCap + (slot - kBpCandCap)] = e;
+    else { bp_candidate<D, R>(a, chunk_base, dl, pt, bestbits); slow++; }
+}
+
 template <int D, int R>
 __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(const __grid_constant__ BpArgs a)
 {
-    constexpr int G = kBpG, W = (D + 1) / 2, WP = (W + 3) & ~3, CH = kBpThreads * R, DW = CH / 32;
+    constexpr int G = kBpG, W = (D + 1) / 2, CH = kBpThreads * R, DW = CH / 32;
+    constexpr int Q = W / 4, REM = W - 4 * Q, TW = REM == 3 ? 4 : REM, CHP = CH + 1, LCAP = CH + 8;
     static_assert((G * D) % 4 == 0, "group of block pairs must be whole 16-byte words");
     static_assert(CH <= (1 << (32 - kBpPtBits)), "direction index must fit the candidate entry");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BpSmem L = bp_smem_layout(D, R, a.seg_blocks, a.n_piv);
-    unsigned *thr = reinterpret_cast<unsigned *>(smem_raw + L.thr);          // [CH][WP]
+    uint4 *thr4 = reinterpret_cast<uint4 *>(smem_raw + L.thr);               // [Q][CHP]
+    unsigned *thrt = reinterpret_cast<unsigned *>(smem_raw + L.tail);        // [CHP][TW]
     unsigned *bnd = reinterpret_cast<unsigned *>(smem_raw + L.bnd);          // [seg_blocks/2][D]
     unsigned *maskT = reinterpret_cast<unsigned *>(smem_raw + L.mask);       // [DW][mask_stride]
     long long *bestbits = reinterpret_cast<long long *>(smem_raw + L.best);  // [CH]
@@ -147,8 +169,15 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
     const int mstride = L.mask_stride;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned short *slist = reinterpret_cast<unsigned short *>(smem_raw + L.list) + warp * LCAP;   // this warp's pair list
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); *ctr = 0; }
     for (int i = tid; i < a.n_piv * D; i += kBpThreads) piv[i] = a.piv32[i];
+    {
+        // row CH of the threshold planes: the key -(S+1) in every half-word -> no point passes
+        const unsigned v = ((unsigned)(-(kKeyScale + 1)) & 0xffffu) * 0x10001u;
+        if (tid < Q) thr4[tid * CHP + CH] = make_uint4(v, v, v, v);
+        if (tid < TW) thrt[CH * TW + tid] = v;
+    }
     __syncthreads();
     unsigned phase = 0;                                            // parity of the bounds barrier
     const int n_seg = (a.nb_pad + a.seg_blocks - 1) / a.seg_blocks;
@@ -232,16 +261,18 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
                     const double best_m = __longlong_as_double(bestbits[dl]) * (1.0 - 0x1p-20);
 #pragma unroll
                     for (int k = 0; k < D; k++) negT[r][k] = bp_neg_key16(best_m, __ldg(winv + k), a.qscale[k], a.qlos[k]);
-                    unsigned tw[WP];
+                    unsigned tw[4 * Q + 4];
 #pragma unroll
-                    for (int j = 0; j < WP; j++) {
+                    for (int j = 0; j < 4 * Q + 4; j++) {
                         tw[j] = 0;
                         if (2 * j < D) tw[j] = negT[r][2 * j];
                         if (2 * j + 1 < D) tw[j] |= negT[r][2 * j + 1] << 16;   // dummy objective of an odd D: threshold key 0
                     }
-                    uint4 *dst = reinterpret_cast<uint4 *>(thr + (size_t)dl * WP);
 #pragma unroll
-                    for (int q = 0; q < WP / 4; q++) dst[q] = make_uint4(tw[4 * q], tw[4 * q + 1], tw[4 * q + 2], tw[4 * q + 3]);
+                    for (int q = 0; q < Q; q++) thr4[q * CHP + dl] = make_uint4(tw[4 * q], tw[4 * q + 1], tw[4 * q + 2], tw[4 * q + 3]);
+                    if constexpr (TW == 1) thrt[dl] = tw[4 * Q];
+                    if constexpr (TW == 2) *reinterpret_cast<uint2 *>(thrt + 2 * dl) = make_uint2(tw[4 * Q], tw[4 * Q + 1]);
+                    if constexpr (TW == 4) *reinterpret_cast<uint4 *>(thrt + 4 * dl) = make_uint4(tw[4 * Q], tw[4 * Q + 1], tw[4 * Q + 2], tw[4 * Q + 3]);
 #pragma unroll
                     for (int k = 0; k < D; k++) negT[r][k] *= 0x10001u;
                 } else {
@@ -303,7 +334,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
                     }
                 }
             }
-            __syncthreads();                  // maskT, thr, bestbits complete; bnd no longer read
+            __syncthreads();                  // maskT, thresholds, bestbits complete; bnd no longer read
             if (!resident && tid == 0 && seg + 1 < n_seg) {
                 const int nxt = min(a.seg_blocks, a.nb_pad - (seg0 + a.seg_blocks));
                 const unsigned bytes = (unsigned)(nxt / 2) * D * 4u;
@@ -316,46 +347,99 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
 #pragma unroll 1
             for (int b = warp; b < seg_real; b += kBpThreads / 32) {
                 const unsigned myw = (lane < DW) ? maskT[lane * mstride + b] : 0u;
-                unsigned nz = __ballot_sync(0xffffffffu, myw != 0u);
-                if (nz == 0) continue;
+                // flat list of the block's surviving directions: lane = direction word, warp scan of the bit counts
+                const int cnt = __popc(myw);
+                int incl = cnt;
+#pragma unroll
+                for (int off = 1; off < DW; off <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, DW - 1);
+                if (total == 0) continue;
                 const unsigned blk = (unsigned)(seg0 + b);
                 unsigned kw[W];
 #pragma unroll
                 for (int j = 0; j < W; j++) kw[j] = __ldg(a.pkeys + ((size_t)blk * W + j) * 32 + lane);
-                while (nz) {
-                    const int dw = __ffs((int)nz) - 1;
-                    nz &= nz - 1;
-                    unsigned word = __shfl_sync(0xffffffffu, myw, dw);
-                    while (word) {
-                        const int bit = __ffs((int)word) - 1;
-                        word &= word - 1;
-                        const unsigned dl = (unsigned)(dw * 32 + bit);
-                        const uint4 *t4 = reinterpret_cast<const uint4 *>(thr + (size_t)dl * WP);
-                        unsigned m16 = 0x7fff7fffu;
+                {
+                    unsigned w = myw;
+                    int o = incl - cnt;
+                    while (w) {
+                        const int bit = __ffs((int)w) - 1;
+                        w &= w - 1;
+                        slist[o++] = (unsigned short)(lane * 32 + bit);
+                    }
+                    if (lane < 4) slist[total + lane] = (unsigned short)CH;      // padding: the "nothing passes" row
+                }
+                __syncwarp();
+                const unsigned pt = blk * kBpBlock + lane;
+#pragma unroll 1
+                for (int j = 0; j < total; j += 4) {
+                    const uint2 e = *reinterpret_cast<const uint2 *>(slist + j);
+                    unsigned dl[4] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16};
+                    unsigned m16[4] = {0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu};
 #pragma unroll
-                        for (int q = 0; q < WP / 4; q++) {
-                            const uint4 t = t4[q];
-                            if (4 * q + 0 < W) m16 = __viaddmin_s16x2(kw[4 * q + 0 < W ? 4 * q + 0 : 0], t.x, m16);
-                            if (4 * q + 1 < W) m16 = __viaddmin_s16x2(kw[4 * q + 1 < W ? 4 * q + 1 : 0], t.y, m16);
-                            if (4 * q + 2 < W) m16 = __viaddmin_s16x2(kw[4 * q + 2 < W ? 4 * q + 2 : 0], t.z, m16);
-                            if (4 * q + 3 < W) m16 = __viaddmin_s16x2(kw[4 * q + 3 < W ? 4 * q + 3 : 0], t.w, m16);
+                    for (int q = 0; q < Q; q++) {
+                        uint4 t[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) t[u] = thr4[q * CHP + dl[u]];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            m16[u] = __viaddmin_s16x2(kw[4 * q + 0], t[u].x, m16[u]);
+                            m16[u] = __viaddmin_s16x2(kw[4 * q + 1], t[u].y, m16[u]);
+                            m16[u] = __viaddmin_s16x2(kw[4 * q + 2], t[u].z, m16[u]);
+                            m16[u] = __viaddmin_s16x2(kw[4 * q + 3], t[u].w, m16[u]);
                         }
-                        if ((m16 & 0x80008000u) == 0u) {
-                            const unsigned pt = blk * kBpBlock + lane;
-                            const unsigned slot = atomicAdd(ctr, 1u);
-                            if (slot < (unsigned)kBpCandCap) cand[slot] = (dl << kBpPtBits) | pt;
-                            else { bp_candidate<D, R>(a, chunk_base, dl, pt, bestbits); slow++; }
+                    }
+                    if constexpr (TW == 1) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) m16[u] = __viaddmin_s16x2(kw[4 * Q], thrt[dl[u]], m16[u]);
+                    }
+                    if constexpr (TW == 2) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint2 t = *reinterpret_cast<const uint2 *>(thrt + 2 * dl[u]);
+                            m16[u] = __viaddmin_s16x2(kw[4 * Q], t.x, m16[u]);
+                            m16[u] = __viaddmin_s16x2(kw[4 * Q + 1], t.y, m16[u]);
+                        }
+                    }
+                    if constexpr (TW == 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint4 t = *reinterpret_cast<const uint4 *>(thrt + 4 * dl[u]);
+                            m16[u] = __viaddmin_s16x2(kw[4 * Q], t.x, m16[u]);
+                            m16[u] = __viaddmin_s16x2(kw[4 * Q + 1], t.y, m16[u]);
+                            m16[u] = __viaddmin_s16x2(kw[4 * Q + 2], t.z, m16[u]);
+                        }
+                    }
+                    // sign bits clear in both halves <=> candidate; OR of the four tests first (candidates are rare)
+                    const unsigned sg0 = m16[0] & 0x80008000u, sg1 = m16[1] & 0x80008000u, sg2 = m16[2] & 0x80008000u, sg3 = m16[3] & 0x80008000u;
+                    const bool anyc = (sg0 == 0u) | (sg1 == 0u) | (sg2 == 0u) | (sg3 == 0u);
+                    if (__any_sync(0xffffffffu, anyc)) {
+                        const unsigned sg[4] = {sg0, sg1, sg2, sg3};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const unsigned cm = __ballot_sync(0xffffffffu, sg[u] == 0u);
+                            if (cm) {
+                                const int leader = __ffs((int)cm) - 1;
+                                unsigned base = 0;
+                                if (lane == leader) base = atomicAdd(ctr, (unsigned)__popc(cm));
+                                base = __shfl_sync(0xffffffffu, base, leader);
+                                if (sg[u] == 0u)
+                                    bp_append<D, R>(a, chunk_base, base + __popc(cm & ((1u << lane) - 1u)), dl[u], pt, cand, bestbits, slow);
+                            }
                         }
                     }
                 }
+                __syncwarp();                 // the list is rewritten for the warp's next block
             }
             __syncthreads();
 
             // ---- phase D: lane = candidate
             {
-                const unsigned nc = min(*ctr, (unsigned)kBpCandCap);
+                const unsigned nc = min(*ctr, (unsigned)(kBpCandCap + kBpOvfCap));
                 for (unsigned i = tid; i < nc; i += kBpThreads) {
-                    const unsigned e = cand[i];
+                    const unsigned e = i < (unsigned)kBpCandCap ? cand[i] : a.ovf[(size_t)blockIdx.x * kBpOvfCap + (i - kBpCandCap)];
                     bp_candidate<D, R>(a, chunk_base, e >> kBpPtBits, e & ((1u << kBpPtBits) - 1u), bestbits);
                     slow++;
                 }
