@@ -116,6 +116,17 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def reference_rel_error(cfg, estimate):
+    """Relative error against the reference's own full-size result (tests/golden/golden_full.json, written by
+    tests/golden/make_golden.py --full-cfg3 from the compiled reference); None for configs without one."""
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_full.json")))
+        want = float.fromhex(g[cfg + "_full"])
+        return abs(estimate - want) / abs(want)
+    except Exception:
+        return None
+
+
 def workload_name(cfg):
     c = hvcases.CONFIGS[cfg]
     return (f"{cfg}: hv_approx {c['method']} d={c['d']} n={c['n']} {c['kind']} front nsamples={c['nsamples']:.0e} "
@@ -289,10 +300,12 @@ def run_ours(args, rank, local_rank, world):
             "hbm_gbs_needed": alg_bytes * mm_launches / (maxmin_ms_max / 1e3) / 1e9,
             "hbm_peak_gbs": peaks.get("hbm_gbs"),
             "traffic": None,
-            "note": "frac > 1 is expected for the screen kernels: they decide max-min with one compare per element "
-                    "(dpx: one VIADDMNMX.S16x2 per two elements on conservatively quantised keys, screen: one DSETP) "
-                    "instead of DMUL+min, evaluate only candidates in FP64, and are bit-identical per sample to the "
-                    "(2d+1)-operation loop; run with --kernel exact for the textbook loop",
+            "note": "achieved counts the ALGORITHMIC (2d+1) FP64 operations per sample*point of the textbook loop; frac > 1 "
+                    "is expected for the screening kernels, which return the same bits with less work: pruned discards "
+                    "whole 32-point blocks by their per-objective maxima and screens the rest with one VIADDMNMX.S16x2 "
+                    "per two elements on conservatively quantised keys, dpx does that screen on every point, screen "
+                    "uses one DSETP per element; only candidates are evaluated in FP64.  --kernel exact runs the "
+                    "textbook loop (frac ~0.6 of P64/2)",
         }
         # ncu-measured DRAM traffic of the profiled launch (profiles/), scaled to this run's launch size
         traffic = None
@@ -326,7 +339,7 @@ def run_ours(args, rank, local_rank, world):
                        "l2": "point set (0.8 MB) is L2/shared-memory resident by design; the per-batch direction "
                              "buffer (2 GiB) exceeds L2, no flush needed",
                        "timing": "CUDA events on the launching stream, max over ranks"},
-            "estimate": estimate, "estimate_e2e": est_e2e,
+            "estimate": estimate, "estimate_e2e": est_e2e, "rel_error_vs_reference": reference_rel_error(args.config, estimate),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes + ref.nbytes + maxi.nbytes),
                     "d2h_bytes_per_step": 32, "steps": e2e_steps},
             "gpu_launches": int(launches),

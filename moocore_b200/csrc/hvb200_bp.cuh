@@ -136,6 +136,12 @@ __device__ __forceinline__ void bp_candidate(const BpArgs &a, ull chunk_base, un
     if (m > 0.0) atomicMax(bestbits + dl, __double_as_longlong(m));
 }
 
+template <int D, int R>
+__device__ __noinline__ void bp_candidate_cold(const BpArgs &a, ull chunk_base, unsigned dl, unsigned pt, long long *bestbits)
+{
+    bp_candidate<D, R>(a, chunk_base, dl, pt, bestbits);
+}
+
 // append one candidate: shared list, then the CTA's global overflow list, then evaluate in place
 template <int D, int R>
 __device__ __forceinline__ void bp_append(const BpArgs &a, ull chunk_base, unsigned slot, unsigned dl, unsigned pt,
@@ -144,7 +150,7 @@ __device__ __forceinline__ void bp_append(const BpArgs &a, ull chunk_base, unsig
     const unsigned e = (dl << kBpPtBits) | pt;
     if (slot < (unsigned)kBpCandCap) cand[slot] = e;
     else if (slot < (unsigned)(kBpCandCap + kBpOvfCap)) a.ovf[(size_t)blockIdx.x * kBpOvfCap + (slot - kBpCandCap)] = e;
-    else { bp_candidate<D, R>(a, chunk_base, dl, pt, bestbits); slow++; }
+    else { bp_candidate_cold<D, R>(a, chunk_base, dl, pt, bestbits); slow++; }
 }
 
 template <int D, int R>
@@ -367,22 +373,24 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
                     while (w) {
                         const int bit = __ffs((int)w) - 1;
                         w &= w - 1;
-                        slist[o++] = (unsigned short)(lane * 32 + bit);
+                        slist[o++] = (unsigned short)((lane * 32 + bit) * 16);      // byte offset of the direction's threshold row
                     }
-                    if (lane < 4) slist[total + lane] = (unsigned short)CH;      // padding: the "nothing passes" row
+                    if (lane < 4) slist[total + lane] = (unsigned short)(CH * 16);      // padding: the "nothing passes" row
                 }
                 __syncwarp();
                 const unsigned pt = blk * kBpBlock + lane;
 #pragma unroll 1
                 for (int j = 0; j < total; j += 4) {
                     const uint2 e = *reinterpret_cast<const uint2 *>(slist + j);
-                    unsigned dl[4] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16};
+                    const unsigned off[4] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16};
                     unsigned m16[4] = {0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu};
+                    const unsigned char *tb = reinterpret_cast<const unsigned char *>(thr4);
+                    const unsigned char *tt = reinterpret_cast<const unsigned char *>(thrt);
 #pragma unroll
                     for (int q = 0; q < Q; q++) {
                         uint4 t[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) t[u] = thr4[q * CHP + dl[u]];
+                        for (int u = 0; u < 4; u++) t[u] = *reinterpret_cast<const uint4 *>(tb + q * CHP * 16 + off[u]);
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             m16[u] = __viaddmin_s16x2(kw[4 * q + 0], t[u].x, m16[u]);
@@ -393,12 +401,12 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
                     }
                     if constexpr (TW == 1) {
 #pragma unroll
-                        for (int u = 0; u < 4; u++) m16[u] = __viaddmin_s16x2(kw[4 * Q], thrt[dl[u]], m16[u]);
+                        for (int u = 0; u < 4; u++) m16[u] = __viaddmin_s16x2(kw[4 * Q], *reinterpret_cast<const unsigned *>(tt + (off[u] >> 2)), m16[u]);
                     }
                     if constexpr (TW == 2) {
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            const uint2 t = *reinterpret_cast<const uint2 *>(thrt + 2 * dl[u]);
+                            const uint2 t = *reinterpret_cast<const uint2 *>(tt + (off[u] >> 1));
                             m16[u] = __viaddmin_s16x2(kw[4 * Q], t.x, m16[u]);
                             m16[u] = __viaddmin_s16x2(kw[4 * Q + 1], t.y, m16[u]);
                         }
@@ -406,28 +414,23 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
                     if constexpr (TW == 4) {
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            const uint4 t = *reinterpret_cast<const uint4 *>(thrt + 4 * dl[u]);
+                            const uint4 t = *reinterpret_cast<const uint4 *>(tt + off[u]);
                             m16[u] = __viaddmin_s16x2(kw[4 * Q], t.x, m16[u]);
                             m16[u] = __viaddmin_s16x2(kw[4 * Q + 1], t.y, m16[u]);
                             m16[u] = __viaddmin_s16x2(kw[4 * Q + 2], t.z, m16[u]);
                         }
                     }
-                    // sign bits clear in both halves <=> candidate; OR of the four tests first (candidates are rare)
+                    // sign bits clear in both halves <=> candidate (rare): one vote for the four directions
                     const unsigned sg0 = m16[0] & 0x80008000u, sg1 = m16[1] & 0x80008000u, sg2 = m16[2] & 0x80008000u, sg3 = m16[3] & 0x80008000u;
-                    const bool anyc = (sg0 == 0u) | (sg1 == 0u) | (sg2 == 0u) | (sg3 == 0u);
-                    if (__any_sync(0xffffffffu, anyc)) {
-                        const unsigned sg[4] = {sg0, sg1, sg2, sg3};
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const unsigned cm = __ballot_sync(0xffffffffu, sg[u] == 0u);
-                            if (cm) {
-                                const int leader = __ffs((int)cm) - 1;
-                                unsigned base = 0;
-                                if (lane == leader) base = atomicAdd(ctr, (unsigned)__popc(cm));
-                                base = __shfl_sync(0xffffffffu, base, leader);
-                                if (sg[u] == 0u)
-                                    bp_append<D, R>(a, chunk_base, base + __popc(cm & ((1u << lane) - 1u)), dl[u], pt, cand, bestbits, slow);
-                            }
+                    if (__any_sync(0xffffffffu, min(min(sg0, sg1), min(sg2, sg3)) == 0u)) {
+                        const unsigned c = (sg0 == 0u) + (sg1 == 0u) + (sg2 == 0u) + (sg3 == 0u);
+                        if (c) {
+                            unsigned slot;
+                            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(smem_u32(ctr)), "r"(c) : "memory");
+                            if (sg0 == 0u) bp_append<D, R>(a, chunk_base, slot++, off[0] >> 4, pt, cand, bestbits, slow);
+                            if (sg1 == 0u) bp_append<D, R>(a, chunk_base, slot++, off[1] >> 4, pt, cand, bestbits, slow);
+                            if (sg2 == 0u) bp_append<D, R>(a, chunk_base, slot++, off[2] >> 4, pt, cand, bestbits, slow);
+                            if (sg3 == 0u) bp_append<D, R>(a, chunk_base, slot++, off[3] >> 4, pt, cand, bestbits, slow);
                         }
                     }
                 }

@@ -1693,7 +1693,9 @@ static int bp_prepare(DevPlan *dp)
     std::vector<unsigned> pos(n);
     for (size_t i = 0; i < n; i++) pos[idx[i]] = (unsigned)i;
     // pivots: the points that won most probes
-    const size_t npiv = std::min<size_t>(n, (size_t)bp_pivot_count());
+    // pivots: up to 256, about an eighth of a small set (n=1000: 128 pivots 3.75 Tsp/s, 256 pivots 3.1)
+    size_t npiv = std::min<size_t>(n, (size_t)bp_pivot_count());
+    if (!getenv("HVB200_BP_PIVOTS")) npiv = std::min<size_t>(npiv, std::max<size_t>(16, n / 8));
     std::vector<unsigned> byw(n);
     for (size_t i = 0; i < n; i++) byw[i] = (unsigned)i;
     std::partial_sort(byw.begin(), byw.begin() + npiv, byw.end(),
@@ -1839,9 +1841,6 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     DevPlan *dp = (DevPlan *)plan->dev;
     CUDA_TRY(cudaSetDevice(dp->device));
     dp->stream = stream ? (cudaStream_t)stream : dp->own_stream;
-    if (!dp->ordered && dp->n >= 1024 && dp->d <= 32 && plan->run_samples >= (1u << 20) && !getenv("HVB200_NO_ORDER")) {
-        if (order_points(dp)) return -1;
-    }
     dp->spans.clear();
     dp->ev_next = 0;
     memset(&plan->stats, 0, sizeof plan->stats);
@@ -1867,14 +1866,27 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     // AUTO: the screens pay a divergent exact evaluation per candidate, which only amortises over a
     // few hundred points (measured on B200: n=100,d=3 EXACT 602 / DPX 243 / SCREEN 371 Gsp/s;
     // n=1000,d=5 EXACT 734 / SCREEN 930 / DPX 1277; n=1e4,d=10 EXACT 484 / SCREEN 1240 / DPX 1946).
+    // The block-pruned kernel wins from n ~ 500 upwards (n=1000,d=5: 3.1 Tsp/s vs DPX 1.55; n=1e4,d=10: 8.5 vs
+    // 2.3; n=5e4,d=20: 4.4 vs 1.0; d=50: 0.64 vs 0.0045 for the runtime-d kernel) but its plan-time
+    // preparation (probe kernel, kd order and keys on the host: ~0.3 ms at n=1e3, ~3 ms at n=1e4) only pays
+    // for runs of a few 1e9 sample*point evaluations.
     int mode = MODE_DPX;
     if (plan->kernel == HVB200_KERNEL_EXACT) mode = MODE_EXACT;
     else if (plan->kernel == HVB200_KERNEL_SCREEN) mode = MODE_SCREEN;
     else if (plan->kernel == HVB200_KERNEL_BP) mode = MODE_BP;
-    else if (plan->kernel == HVB200_KERNEL_AUTO && dp->n < 256) mode = MODE_EXACT;
+    else if (plan->kernel == HVB200_KERNEL_AUTO) {
+        const double work = (double)plan->run_samples * (double)dp->n;
+        if (dp->n < 256) mode = MODE_EXACT;
+        else if (d > 32) mode = MODE_BP;
+        else if (dp->n >= 512 && (dp->bp_ready || work >= 4e9)) mode = MODE_BP;
+    }
     if (mode == MODE_BP && dp->n + 256 >= ((size_t)1 << kBpPtBits)) mode = MODE_DPX;   // candidate entries hold 23-bit point indices
     if (d > 32 && mode != MODE_BP) mode = MODE_EXACT;
     dp->kernel_used = mode;
+    if ((mode == MODE_DPX || mode == MODE_SCREEN) && !dp->ordered && dp->n >= 1024 && plan->run_samples >= (1u << 20) &&
+        !getenv("HVB200_NO_ORDER")) {
+        if (order_points(dp)) return -1;
+    }
     if (mode == MODE_BP && !dp->bp_ready && bp_prepare(dp)) return -1;
     const size_t smem = mode == MODE_DPX ? dp->k_smem_bytes : (mode == MODE_BP ? dp->bp_smem : dp->smem_bytes);
     int occ = 1;
