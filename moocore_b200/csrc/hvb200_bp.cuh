@@ -20,11 +20,11 @@
 //             shuffles) turn it into one word per (block, 32 directions) in shared memory.
 //   phase C   warp = block, lane = point.  The block's keys sit in registers; the warp walks the set
 //             bits of the block's direction words, tests its 32 points against that direction's
-//             thresholds (W VIADDMNMX + one vote) and appends the (direction, point) candidates to a
-//             list in shared memory.
-//   phase D   lane = candidate.  Exact FP64 evaluation (the reference's products and comparisons),
-//             folded into the direction's max with a shared-memory atomicMax on the bit pattern
-//             (max is exact and order-free, values are >= 0).
+//             thresholds (W VIADDMNMX + one vote) and appends {direction, block, candidate mask} to the
+//             CTA's hit list (global memory, L2 resident).
+//   phase D   lane = hit entry.  Exact FP64 evaluation of its candidate points (the reference's
+//             products and comparisons), folded into the direction's max with a shared-memory
+//             atomicMax on the bit pattern (max is exact and order-free, values are >= 0).
 //   Large point sets are processed in segments of blocks; the thresholds are refreshed from the
 //   running max between segments.
 //
@@ -36,9 +36,8 @@ static constexpr int kBpBlock = 32;           // points per block = lanes per wa
 static constexpr int kBpThreads = 256;        // 8 warps
 static constexpr int kBpG = 4;                // block pairs per group in phase B ((G*D) % 4 == 0)
 static constexpr int kBpMaxPivots = 512;
-static constexpr int kBpCandCap = 3072;       // candidate entries per chunk in shared memory ...
-static constexpr int kBpOvfCap = 16384;       // ... then in a per-CTA global list, then evaluated in place
-static constexpr int kBpPtBits = 23;          // candidate entry = direction << 23 | point
+static constexpr int kBpHitCap = 16384;       // (direction, block) pairs with candidates per chunk: per-CTA list in global memory (L2)
+static constexpr int kBpPtBits = 23;          // hit entry = {direction << 23 | block, 32-bit mask of candidate points}
 
 struct BpArgs {
     const double *pts;        // [n_pad][D] FP64, block order
@@ -55,7 +54,7 @@ struct BpArgs {
     double *cta_sums;
     double *values;
     ull *slow_counter;
-    unsigned *ovf;            // [grid][kBpOvfCap] candidate overflow lists
+    uint2 *hits;              // [grid][kBpHitCap] hit lists
     double qscale[HVB200_MAXD], qlos[HVB200_MAXD];
 };
 
@@ -63,7 +62,7 @@ struct BpArgs {
 // Thresholds for phase C are stored as planes of 16-byte words [plane][CH + 1] (row CH = "nothing
 // passes", the padding entry of the pair lists) plus one tail plane of 1, 2 or 4 words per row.
 struct BpSmem {
-    size_t thr, tail, bnd, mask, best, piv, cand, list, bar, red, total;
+    size_t thr, tail, bnd, mask, best, piv, list, bar, red, total;
     int mask_stride, Q, TW;
 };
 __host__ __device__ inline BpSmem bp_smem_layout(int D, int R, int seg_blocks, int n_piv)
@@ -81,7 +80,6 @@ __host__ __device__ inline BpSmem bp_smem_layout(int D, int R, int seg_blocks, i
     s.mask = o; o += ((size_t)DW * s.mask_stride * 4 + 15) & ~(size_t)15;
     s.best = o; o += (size_t)CH * 8;
     s.piv = o;  o += ((size_t)n_piv * D * 4 + 15) & ~(size_t)15;
-    s.cand = o; o += (size_t)kBpCandCap * 4;
     s.list = o; o += (size_t)(kBpThreads / 32) * (CH + 8) * 2;
     s.bar = o;  o += 16;
     s.red = o;  o += 8 * 8;
@@ -142,17 +140,6 @@ __device__ __noinline__ void bp_candidate_cold(const BpArgs &a, ull chunk_base, 
     bp_candidate<D, R>(a, chunk_base, dl, pt, bestbits);
 }
 
-// append one candidate: shared list, then the CTA's global overflow list, then evaluate in place
-template <int D, int R>
-__device__ __forceinline__ void bp_append(const BpArgs &a, ull chunk_base, unsigned slot, unsigned dl, unsigned pt,
-                                          unsigned *cand, long long *bestbits, ull &slow)
-{
-    const unsigned e = (dl << kBpPtBits) | pt;
-    if (slot < (unsigned)kBpCandCap) cand[slot] = e;
-    else if (slot < (unsigned)(kBpCandCap + kBpOvfCap)) a.ovf[(size_t)blockIdx.x * kBpOvfCap + (slot - kBpCandCap)] = e;
-    else { bp_candidate_cold<D, R>(a, chunk_base, dl, pt, bestbits); slow++; }
-}
-
 template <int D, int R>
 __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(const __grid_constant__ BpArgs a)
 {
@@ -168,15 +155,15 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
     unsigned *maskT = reinterpret_cast<unsigned *>(smem_raw + L.mask);       // [DW][mask_stride]
     long long *bestbits = reinterpret_cast<long long *>(smem_raw + L.best);  // [CH]
     float *piv = reinterpret_cast<float *>(smem_raw + L.piv);                // [n_piv][D]
-    unsigned *cand = reinterpret_cast<unsigned *>(smem_raw + L.cand);        // [kBpCandCap]
     ull *bar = reinterpret_cast<ull *>(smem_raw + L.bar);
-    unsigned *ctr = reinterpret_cast<unsigned *>(bar + 1);
+    unsigned *ctr = reinterpret_cast<unsigned *>(bar + 1);                   // [0] hit entries, [1] next block of phase C
     double *red = reinterpret_cast<double *>(smem_raw + L.red);
     const int mstride = L.mask_stride;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned short *slist = reinterpret_cast<unsigned short *>(smem_raw + L.list) + warp * LCAP;   // this warp's pair list
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); *ctr = 0; }
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); ctr[0] = 0; ctr[1] = kBpThreads / 32; }
+    uint2 *hits = a.hits + (size_t)blockIdx.x * kBpHitCap;
     for (int i = tid; i < a.n_piv * D; i += kBpThreads) piv[i] = a.piv32[i];
     {
         // row CH of the threshold planes: the key -(S+1) in every half-word -> no point passes
@@ -350,8 +337,12 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
 
             // ---- phase C: warp = block, lane = point
             const int seg_real = min(seg_nb, a.nb - seg0);                         // real (non-padding) blocks
+            // blocks are handed out dynamically (the first one per warp is fixed): their pair counts differ a lot
+            int b = warp;
 #pragma unroll 1
-            for (int b = warp; b < seg_real; b += kBpThreads / 32) {
+            while (b < seg_real) {
+                int b_next = 0;
+                if (lane == 0) b_next = (int)atomicAdd(ctr + 1, 1u);
                 const unsigned myw = (lane < DW) ? maskT[lane * mstride + b] : 0u;
                 // flat list of the block's surviving directions: lane = direction word, warp scan of the bit counts
                 const int cnt = __popc(myw);
@@ -362,8 +353,9 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
                     if (lane >= off) incl += t;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, DW - 1);
-                if (total == 0) continue;
                 const unsigned blk = (unsigned)(seg0 + b);
+                b = __shfl_sync(0xffffffffu, b_next, 0);
+                if (total == 0) continue;
                 unsigned kw[W];
 #pragma unroll
                 for (int j = 0; j < W; j++) kw[j] = __ldg(a.pkeys + ((size_t)blk * W + j) * 32 + lane);
@@ -378,8 +370,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
                     if (lane < 4) slist[total + lane] = (unsigned short)(CH * 16);      // padding: the "nothing passes" row
                 }
                 __syncwarp();
-                const unsigned pt = blk * kBpBlock + lane;
-#pragma unroll 1
+#pragma unroll 2
                 for (int j = 0; j < total; j += 4) {
                     const uint2 e = *reinterpret_cast<const uint2 *>(slist + j);
                     const unsigned off[4] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16};
@@ -420,17 +411,31 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
                             m16[u] = __viaddmin_s16x2(kw[4 * Q + 2], t.z, m16[u]);
                         }
                     }
-                    // sign bits clear in both halves <=> candidate (rare): one vote for the four directions
-                    const unsigned sg0 = m16[0] & 0x80008000u, sg1 = m16[1] & 0x80008000u, sg2 = m16[2] & 0x80008000u, sg3 = m16[3] & 0x80008000u;
-                    if (__any_sync(0xffffffffu, min(min(sg0, sg1), min(sg2, sg3)) == 0u)) {
-                        const unsigned c = (sg0 == 0u) + (sg1 == 0u) + (sg2 == 0u) + (sg3 == 0u);
-                        if (c) {
+                    // sign bits clear in both halves <=> candidate.  About a quarter of the pairs hold one: lanes 0..3
+                    // publish one {direction, block, candidate mask} entry per pair with candidates
+                    const unsigned c0 = __ballot_sync(0xffffffffu, (m16[0] & 0x80008000u) == 0u);
+                    const unsigned c1 = __ballot_sync(0xffffffffu, (m16[1] & 0x80008000u) == 0u);
+                    const unsigned c2 = __ballot_sync(0xffffffffu, (m16[2] & 0x80008000u) == 0u);
+                    const unsigned c3 = __ballot_sync(0xffffffffu, (m16[3] & 0x80008000u) == 0u);
+                    if (c0 | c1 | c2 | c3) {
+                        const unsigned cm = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : c3));
+                        const unsigned of = lane == 0 ? off[0] : (lane == 1 ? off[1] : (lane == 2 ? off[2] : off[3]));
+                        bool spilled = false;
+                        if (lane < 4 && cm) {
                             unsigned slot;
-                            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(smem_u32(ctr)), "r"(c) : "memory");
-                            if (sg0 == 0u) bp_append<D, R>(a, chunk_base, slot++, off[0] >> 4, pt, cand, bestbits, slow);
-                            if (sg1 == 0u) bp_append<D, R>(a, chunk_base, slot++, off[1] >> 4, pt, cand, bestbits, slow);
-                            if (sg2 == 0u) bp_append<D, R>(a, chunk_base, slot++, off[2] >> 4, pt, cand, bestbits, slow);
-                            if (sg3 == 0u) bp_append<D, R>(a, chunk_base, slot++, off[3] >> 4, pt, cand, bestbits, slow);
+                            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(smem_u32(ctr)) : "memory");
+                            if (slot < (unsigned)kBpHitCap) hits[slot] = make_uint2(((of >> 4) << kBpPtBits) | blk, cm);
+                            else spilled = true;
+                        }
+                        const unsigned sp = __ballot_sync(0xffffffffu, spilled);
+                        if (sp) {
+                            // the CTA's hit list is full (never seen in practice): evaluate in place
+#pragma unroll
+                            for (int u = 0; u < 4; u++)
+                                if (((sp >> u) & 1u) && (m16[u] & 0x80008000u) == 0u) {
+                                    bp_candidate_cold<D, R>(a, chunk_base, off[u] >> 4, blk * kBpBlock + lane, bestbits);
+                                    slow++;
+                                }
                         }
                     }
                 }
@@ -438,17 +443,23 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(con
             }
             __syncthreads();
 
-            // ---- phase D: lane = candidate
+            // ---- phase D: lane = hit entry, exact FP64 evaluation of its candidate points
             {
-                const unsigned nc = min(*ctr, (unsigned)(kBpCandCap + kBpOvfCap));
+                const unsigned nc = min(ctr[0], (unsigned)kBpHitCap);
                 for (unsigned i = tid; i < nc; i += kBpThreads) {
-                    const unsigned e = i < (unsigned)kBpCandCap ? cand[i] : a.ovf[(size_t)blockIdx.x * kBpOvfCap + (i - kBpCandCap)];
-                    bp_candidate<D, R>(a, chunk_base, e >> kBpPtBits, e & ((1u << kBpPtBits) - 1u), bestbits);
-                    slow++;
+                    const uint2 e = hits[i];
+                    const unsigned dl = e.x >> kBpPtBits, blk = e.x & ((1u << kBpPtBits) - 1u);
+                    unsigned cm = e.y;
+                    while (cm) {
+                        const int q = __ffs((int)cm) - 1;
+                        cm &= cm - 1;
+                        bp_candidate<D, R>(a, chunk_base, dl, blk * kBpBlock + q, bestbits);
+                        slow++;
+                    }
                 }
             }
             __syncthreads();
-            if (tid == 0) *ctr = 0;
+            if (tid == 0) { ctr[0] = 0; ctr[1] = kBpThreads / 32; }
         }
 
 #pragma unroll

@@ -1239,7 +1239,7 @@ struct DevPlan {
     bool bp_ready = false;
     double *bp_pts = nullptr; size_t bp_pts_cap = 0;
     float *bp_piv32 = nullptr; unsigned *bp_pividx = nullptr;
-    unsigned *bp_ovf = nullptr; size_t bp_ovf_cap = 0;   // per-CTA candidate overflow lists
+    uint2 *bp_hits = nullptr; size_t bp_hits_cap = 0;    // per-CTA hit lists of phase C
     unsigned *bp_pkeys = nullptr, *bp_bpair = nullptr; size_t bp_keys_cap = 0, bp_pair_cap = 0;
     int bp_nb = 0, bp_nb_pad = 0, bp_seg_blocks = 0, bp_npiv = 0;
     size_t bp_smem = 0;
@@ -1561,7 +1561,7 @@ static void devplan_release(DevPlan *dp)
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
     cudaFree(dp->dirs_buf[1]); cudaFree(dp->pts_tmp); cudaFree(dp->wins);
-    cudaFree(dp->bp_ovf); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
+    cudaFree(dp->bp_hits); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
     for (int i = 0; i < 2; i++) { if (dp->ev_gen[i]) cudaEventDestroy(dp->ev_gen[i]); if (dp->ev_used[i]) cudaEventDestroy(dp->ev_used[i]); }
     if (dp->ev_begin) cudaEventDestroy(dp->ev_begin);
     if (dp->gen_stream) cudaStreamDestroy(dp->gen_stream);
@@ -1912,11 +1912,11 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     }
     if (occ < 1) { hvb200_set_error("max-min kernel does not fit on an SM (d=%d)", d); return -1; }
     dp->grid = dp->sm_count * occ;
-    if (mode == MODE_BP && dp->bp_ovf_cap < (size_t)dp->grid * kBpOvfCap) {
-        cudaFree(dp->bp_ovf);
-        dp->bp_ovf = nullptr; dp->bp_ovf_cap = 0;
-        CUDA_TRY(cudaMalloc(&dp->bp_ovf, (size_t)dp->grid * kBpOvfCap * sizeof(unsigned)));
-        dp->bp_ovf_cap = (size_t)dp->grid * kBpOvfCap;
+    if (mode == MODE_BP && dp->bp_hits_cap < (size_t)dp->grid * kBpHitCap) {
+        cudaFree(dp->bp_hits);
+        dp->bp_hits = nullptr; dp->bp_hits_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->bp_hits, (size_t)dp->grid * kBpHitCap * sizeof(uint2)));
+        dp->bp_hits_cap = (size_t)dp->grid * kBpHitCap;
     }
     if (dp->cta_cap < dp->grid) {
         cudaFree(dp->cta_sums);
@@ -2181,7 +2181,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
         ka.cta_sums = dp->cta_sums;
         ka.values = a.values;
         ka.slow_counter = dp->counters + 1;
-        ka.ovf = dp->bp_ovf;
+        ka.hits = dp->bp_hits;
         for (int k = 0; k < HVB200_MAXD; k++) {
             ka.qscale[k] = k < d ? dp->bp_qscale[k] : 0.0;
             ka.qlos[k] = k < d ? dp->bp_qlos[k] : 0.0;
