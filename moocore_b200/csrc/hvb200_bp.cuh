@@ -32,6 +32,12 @@
 // that is <= the final max, so the final max — and s^d — is bit-identical to the brute-force kernels.
 #pragma once
 
+#ifndef HVB200_BP_R2
+#define HVB200_BP_R2 1
+#endif
+#ifndef HVB200_BP_MINB
+#define HVB200_BP_MINB 3
+#endif
 static constexpr int kBpBlock = 32;           // points per block = lanes per warp
 static constexpr int kBpThreads = 256;        // 8 warps
 static constexpr int kBpG = 4;                // block pairs per group in phase B ((G*D) % 4 == 0)
@@ -141,7 +147,7 @@ __device__ __noinline__ void bp_candidate_cold(const BpArgs &a, ull chunk_base, 
 }
 
 template <int D, int R>
-__global__ void __launch_bounds__(kBpThreads, (D <= 16 ? 3 : 2)) k_maxmin_bp(const __grid_constant__ BpArgs a)
+__global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_maxmin_bp(const __grid_constant__ BpArgs a)
 {
     constexpr int G = kBpG, W = (D + 1) / 2, CH = kBpThreads * R, DW = CH / 32;
     constexpr int Q = W / 4, REM = W - 4 * Q, TW = REM == 3 ? 4 : REM, CHP = CH + 1, LCAP = CH + 8;

@@ -993,15 +993,17 @@ __device__ __forceinline__ double ipow(double x, int e)
     return acc;
 }
 // solve_inverse_int_of_power_sin (c/hvapprox.c:551-564) in FP64; returns sin/cos of the angle.
-// Tabulated inverse theta = F_m^{-1}(u * I_m) on a uniform grid in u (kHwTab intervals per exponent m),
+// Tabulated inverse theta = F_m^{-1}(u * I_m) on a uniform grid in u (HVB200_HWTAB intervals per exponent m, default 2048;
+// 16384 and 131072 measured the same generator time on B200),
 // built once per device by k_hw_table_init with the reference-style Newton.  k_gen_hw uses the linear
 // interpolant only as the STARTING point of the same Newton iteration with the same stop rule
 // |F(x) - t| <= 1e-15 (c/hvapprox.c:558), which cuts the mean iteration count from 4.2 to about 2 and
 // makes it nearly uniform across a warp.  The first intervals (theta ~ u^(1/(m+1)) has unbounded slope
 // at 0) and zero targets keep the reference's start at pi/2.
-static constexpr int kHwTab = 2048;
+static constexpr int kHwTabDefault = 2048;
+static int g_hw_ntab = 0;                            // intervals per exponent (HVB200_HWTAB, fixed at the first plan)
 
-__device__ void hw_solve(double target, double u, int m, const double *__restrict__ tab,
+__device__ void hw_solve(double target, double u, int m, const double *__restrict__ tab, int ntab,
                          double &s_out, double &c_out, unsigned &capped)
 {
     if (target == 0.0 && m < 32 && c_theta0_bits[m] != ~0ull) {
@@ -1019,10 +1021,10 @@ __device__ void hw_solve(double target, double u, int m, const double *__restric
     double sb = 1.0, cb = 6.123233995736766e-17;     // sin, cos of (double)(pi/2)
     double f = c_Im[m] - target;
     if (tab != nullptr && fabs(f) > 1e-15) {
-        const double g = u * kHwTab;
+        const double g = u * ntab;
         const int gi = (int)g;
-        if (gi >= 4 && gi < kHwTab) {
-            const double *row = tab + (size_t)m * (kHwTab + 1);
+        if (gi >= 4 && gi < ntab) {
+            const double *row = tab + (size_t)m * (ntab + 1);
             const double a = __ldg(row + gi), b = __ldg(row + gi + 1);
             x = a + (b - a) * (g - gi);
             f = fm_eval(m, x, sb, cb) - target;
@@ -1038,17 +1040,17 @@ __device__ void hw_solve(double target, double u, int m, const double *__restric
     }
     s_out = sb; c_out = cb;
 }
-__global__ void __launch_bounds__(128) k_hw_table_init(double *__restrict__ tab, int mmax)
+__global__ void __launch_bounds__(128) k_hw_table_init(double *__restrict__ tab, int mmax, int ntab)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (mmax + 1) * (kHwTab + 1)) return;
-    const int m = idx / (kHwTab + 1), g = idx - m * (kHwTab + 1);
+    if (idx >= (mmax + 1) * (ntab + 1)) return;
+    const int m = idx / (ntab + 1), g = idx - m * (ntab + 1);
     double theta;
-    if (m == 0) theta = ((double)g / kHwTab) * c_Im[0];
+    if (m == 0) theta = ((double)g / ntab) * c_Im[0];
     else if (g == 0) theta = 0.0;
     else {
         // reference-style Newton from pi/2, run to a tighter residual than the generator needs
-        const double target = ((double)g / kHwTab) * c_Im[m];
+        const double target = ((double)g / ntab) * c_Im[m];
         double x = 1.57079632679489661923, sb = 1.0, cb = 6.123233995736766e-17;
         double f = c_Im[m] - target;
         for (int it = 0; it < kNewtonCap && fabs(f) > 2e-16; it++) {
@@ -1061,7 +1063,7 @@ __global__ void __launch_bounds__(128) k_hw_table_init(double *__restrict__ tab,
 }
 
 __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count, double *__restrict__ dirs,
-                                                ull *capped_counter, const double *__restrict__ tab)
+                                                ull *capped_counter, const double *__restrict__ tab, int ntab)
 {
     const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
@@ -1077,7 +1079,7 @@ __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count
         const int m = d - 2 - q;
         const double u = last ? 0.0 : x87_mul_frac(fac, P.a[q]);
         double s, c;
-        hw_solve(u * c_Im[m], u, m, tab, s, c, capped);
+        hw_solve(u * c_Im[m], u, m, tab, ntab, s, c, capped);
         // w_{d-1} = c_0; w_{d-1-q} = (s_0..s_{q-1}) c_q; w_0 = s_0..s_{d-2}  (c/hvapprox.c:632-638)
         const double w = (q == 0) ? c : prod * c;
         prod = (q == 0) ? s : s * prod;
@@ -1317,9 +1319,14 @@ static int upload_constants(int device)
     if (device < 16 && g_hw_tab[device] == nullptr && !getenv("HVB200_NO_HW_TABLE")) {
         const int mmax = 31;
         double *tab = nullptr;
-        CUDA_TRY(cudaMalloc(&tab, (size_t)(mmax + 1) * (kHwTab + 1) * sizeof(double)));
-        const int total = (mmax + 1) * (kHwTab + 1);
-        k_hw_table_init<<<(total + 127) / 128, 128>>>(tab, mmax);
+        if (g_hw_ntab == 0) {
+            const char *e = getenv("HVB200_HWTAB");
+            const int v = e ? atoi(e) : kHwTabDefault;
+            g_hw_ntab = v < 64 ? 64 : (v > (1 << 20) ? (1 << 20) : v);
+        }
+        CUDA_TRY(cudaMalloc(&tab, (size_t)(mmax + 1) * (g_hw_ntab + 1) * sizeof(double)));
+        const int total = (mmax + 1) * (g_hw_ntab + 1);
+        k_hw_table_init<<<(total + 127) / 128, 128>>>(tab, mmax, g_hw_ntab);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
         g_hw_tab[device] = tab;
@@ -1609,7 +1616,7 @@ static void span_end(DevPlan *dp, int b) { if (b >= 0) cudaEventRecord(dp->ev_po
 // Build the block-pruned kernel's inputs (hvb200_bp.cuh): pivots = the most frequent probe winners,
 // blocks = 32 consecutive points of a kd-tree order, two key layouts.  Host work is O(n d log n), once per plan.
 typedef void (*bp_fn)(const BpArgs);
-static constexpr int bp_R_of(int D) { return D <= 16 ? 2 : 1; }
+static constexpr int bp_R_of(int D) { return HVB200_BP_R2 && D <= 16 ? 2 : 1; }
 template <int D>
 static bp_fn pick_bp(int d)
 {
@@ -1778,7 +1785,7 @@ static int bp_prepare(DevPlan *dp)
     dp->bp_nb_pad = nb_pad;
     dp->bp_npiv = (int)npiv;
     // segment = as many blocks as fit the shared-memory budget of one CTA (3 CTAs per SM up to d = 16, else 2)
-    const size_t budget = (d <= 16 ? 74 : 112) * 1024;
+    const size_t budget = (d <= 16 ? (HVB200_BP_MINB >= 4 ? 55 : 74) : 112) * 1024;
     int seg = (nb_pad + 31) / 32 * 32;
     while (seg > 32 && bp_smem_layout(d, bp_R_of(d), seg, (int)npiv).total > budget) seg -= 32;
     if (const char *e = getenv("HVB200_BP_SEG")) { const int v = atoi(e) / 32 * 32; if (v >= 32 && v < seg) seg = v; }
@@ -1991,7 +1998,7 @@ extern "C" int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params 
     P.d = hw->d;
     for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
     const int b = span_begin(dp, 1);
-    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(P, i0, count, dp->dirs, dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr);
+    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(P, i0, count, dp->dirs, dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
     plan->stats.dirgen_launches++;
@@ -2036,7 +2043,7 @@ extern "C" int hvb200cu_hw_prefetch(struct hvb200_plan *plan, const hvb200_hw_pa
     P.d = hw->d;
     for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
     const int b = span_begin_on(dp, 1, dp->gen_stream);
-    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->gen_stream>>>(P, i0, count, dp->dirs_buf[buf], dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr);
+    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->gen_stream>>>(P, i0, count, dp->dirs_buf[buf], dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
     if (b >= 0) cudaEventRecord(dp->ev_pool[b], dp->gen_stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(dp->ev_gen[buf], dp->gen_stream));
