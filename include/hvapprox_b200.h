@@ -83,6 +83,14 @@ MOOCORE_API int hvb200_plan_set_kernel(hvb200_plan *plan, int kernel);
  * on the host. */
 MOOCORE_API int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint32_t seed,
                                 uint64_t i0, uint64_t i1, void *cuda_stream, double out_hilo[2]);
+/* The same sum over the direction blocks b = first, first + stride, first + 2 stride, ... where block b holds
+ * the samples [b*block, min((b+1)*block, nsamples)): the block-cyclic shard of rank `first` among `stride`
+ * ranks.  DZ2019-HW only (the lattice is index-addressable; its per-direction cost drifts along the index,
+ * so interleaved blocks balance the ranks where contiguous ranges do not). */
+#define HVB200_SHARD_BLOCK ((uint64_t)1 << 21)
+MOOCORE_API int hvb200_plan_run_blocks(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint32_t seed,
+                                       uint64_t block, uint64_t first, uint64_t stride, void *cuda_stream,
+                                       double out_hilo[2]);
 MOOCORE_API int hvb200_plan_last_stats(const hvb200_plan *plan, hvb200_stats *out);
 
 /* (double)(c_d * (sum / (long double)nsamples)), c/hvapprox.c:256-257,691-692,863-864; the

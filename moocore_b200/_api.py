@@ -84,6 +84,8 @@ def _load() -> ctypes.CDLL:
     L.hvb200_plan_set_kernel.argtypes = [vp, ctypes.c_int]
     L.hvb200_plan_run.restype = ctypes.c_int
     L.hvb200_plan_run.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, vp, _c_double_p]
+    L.hvb200_plan_run_blocks.restype = ctypes.c_int
+    L.hvb200_plan_run_blocks.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, u64, vp, _c_double_p]
     L.hvb200_plan_last_stats.restype = ctypes.c_int
     L.hvb200_plan_last_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.hvb200_finalize.restype = ctypes.c_double
@@ -265,6 +267,18 @@ class Plan:
             raise RuntimeError(f"hvb200_plan_run failed ({rc}): {_last_error()}")
         return (out[0], out[1])
 
+    def run_blocks(self, method: str, nsamples: int, first: int, stride: int, block: int = 1 << 21, seed: int = 0,
+                   stream: int | None = None):
+        """Partial sum over the block-cyclic shard `first` of `stride` (blocks of `block` directions; DZ2019-HW)."""
+        if self._h is None:
+            return (0.0, 0.0)
+        out = (ctypes.c_double * 2)()
+        rc = _load().hvb200_plan_run_blocks(self._h, METHOD_IDS[method], nsamples, seed, block, first, stride,
+                                            ctypes.c_void_p(stream) if stream else None, out)
+        if rc != 0:
+            raise RuntimeError(f"hvb200_plan_run_blocks failed ({rc}): {_last_error()}")
+        return (out[0], out[1])
+
     def stats(self) -> dict:
         s = Stats()
         if self._h is not None:
@@ -323,6 +337,18 @@ def hv_approx_range(points, ref, *, maximise=False, nsamples: int, seed: int = 0
                     device: int = 0, stream: int | None = None):
     """One shard of an estimate: the (hi, lo) partial sum over samples [i0, i1) on `device`."""
     with Plan(points, ref, maximise, device=device) as plan:
+        return plan.run(method, nsamples, seed, i0, i1, stream)
+
+
+def hv_approx_shard(points, ref, *, maximise=False, nsamples: int, seed: int = 0, method: str, rank: int, world: int,
+                    device: int = 0, stream: int | None = None):
+    """Shard `rank` of `world` of an estimate as a (hi, lo) partial sum: block-cyclic for DZ2019-HW (balanced),
+    a contiguous range for the sequential MC and Rphi streams."""
+    from .sharding import shard_range
+    with Plan(points, ref, maximise, device=device) as plan:
+        if method == "DZ2019-HW" and world > 1:
+            return plan.run_blocks(method, nsamples, rank, world, seed=seed, stream=stream)
+        i0, i1 = shard_range(nsamples, rank, world)
         return plan.run(method, nsamples, seed, i0, i1, stream)
 
 

@@ -359,6 +359,7 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
     /* host-fed streams: smaller batches so that producing batch b+1 overlaps the GPU work on batch b */
     if ((method == HVB200_METHOD_RPHI || (method == HVB200_METHOD_MC && !mc_on_device)) && want > (1u << 18)) want = 1u << 18;
     plan->run_samples = (values_out || dirs_out) ? 0 : i1 - i0;
+    plan->run_total = i1 - i0;
     if (hvb200cu_run_begin(plan, stream, want, &batch)) return -1;
 
     hvb200_hw_params hw;
@@ -423,6 +424,42 @@ int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint3
 {
     return run_range(plan, method, (uint64_t)nsamples, seed, i0, i1, cuda_stream, out_hilo, NULL, NULL);
 }
+/* Block-cyclic shard of a DZ2019-HW estimate: blocks b = first, first + stride, ... of `block` consecutive
+   directions.  The cost of a direction varies smoothly along a Hua-Wang lattice (its first angle grows with the
+   index), so contiguous shards are unbalanced (8 GPUs: 85 % efficiency) while interleaved blocks are not.
+   Only the lattice is index-addressable: the MC and Rphi streams are sequential and stay on contiguous ranges. */
+int hvb200_plan_run_blocks(hvb200_plan *plan, int method, uint_fast32_t nsamples_, uint32_t seed,
+                           uint64_t block, uint64_t first, uint64_t stride, void *cuda_stream, double out_hilo[2])
+{
+    (void)seed;
+    const uint64_t nsamples = (uint64_t)nsamples_;
+    const int d = plan->d;
+    tls_error[0] = 0;
+    if (method != HVB200_METHOD_HW) { hvb200_set_error("block-cyclic runs need an index-addressable direction set (DZ2019-HW)"); return -2; }
+    if (d > MOOCORE_HVAPPROX_DIMENSION_MAX + 1) { hvb200_set_error("DZ2019-HW supports at most %d objectives", MOOCORE_HVAPPROX_DIMENSION_MAX + 1); return -2; }
+    if (block == 0 || stride == 0 || first >= stride) { hvb200_set_error("bad block shard (block %llu, first %llu, stride %llu)",
+                                                                         (unsigned long long)block, (unsigned long long)first, (unsigned long long)stride); return -2; }
+    uint64_t total = 0;
+    for (uint64_t lo = first * block; lo < nsamples; lo += stride * block)
+        total += (nsamples - lo < block) ? nsamples - lo : block;
+    uint64_t batch = 0;
+    plan->run_samples = total;
+    plan->run_total = total;
+    if (hvb200cu_run_begin(plan, cuda_stream, block, &batch)) return -1;
+    hvb200_hw_params hw;
+    hw_params_init(&hw, d, nsamples);
+    for (uint64_t lo = first * block; lo < nsamples; lo += stride * block) {
+        const uint64_t hi = (nsamples - lo < block) ? nsamples : lo + block;
+        for (uint64_t b0 = lo; b0 < hi; b0 += batch) {
+            const uint64_t cnt = (hi - b0 < batch) ? hi - b0 : batch;
+            if (hvb200cu_gen_hw(plan, &hw, b0, cnt)) return -1;
+            if (plan->n && hvb200cu_maxmin(plan, cnt, NULL)) return -1;
+        }
+    }
+    if (hvb200cu_run_end(plan, out_hilo)) return -1;
+    plan->stats.samples = total;
+    return 0;
+}
 int hvb200_plan_sample_values(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint32_t seed,
                               uint64_t i0, uint64_t count, double *values_out)
 {
@@ -453,6 +490,7 @@ int hvb200_plan_run_directions(hvb200_plan *plan, const double *r_host, uint64_t
     uint64_t want = count ? count : 1;
     if (want > (1u << 20)) want = 1u << 20;
     plan->run_samples = 0;
+    plan->run_total = count;
     if (hvb200cu_run_begin(plan, NULL, want, &batch)) return -1;
     for (uint64_t b0 = 0; b0 < count; b0 += batch) {
         const uint64_t cnt = (count - b0 < batch) ? count - b0 : batch;
@@ -480,6 +518,7 @@ typedef struct {
     int method, device, rc;
     const double *data; size_t npoints; dimension_t nobjs; const double *ref; const boolvec *maximise;
     uint64_t nsamples, i0, i1; uint32_t seed;
+    int stride;             /* > 1: block-cyclic shard `device` of `stride` (DZ2019-HW) */
     double hilo[2];
     int empty;
     hvb200_plan *plan;      /* kept alive until the exchange step */
@@ -493,7 +532,9 @@ static void *shard_main(void *arg)
     j->hilo[0] = j->hilo[1] = 0.0;
     j->rc = hvb200_plan_create(&plan, j->data, j->npoints, j->nobjs, j->ref, j->maximise, j->device);
     if (j->rc == 0 && !plan) { j->empty = 1; return NULL; }
-    if (j->rc == 0) j->rc = hvb200_plan_run(plan, j->method, j->nsamples, j->seed, j->i0, j->i1, NULL, j->hilo);
+    if (j->rc == 0 && j->stride > 1 && j->method == HVB200_METHOD_HW)
+        j->rc = hvb200_plan_run_blocks(plan, j->method, j->nsamples, j->seed, HVB200_SHARD_BLOCK, (uint64_t)j->device, (uint64_t)j->stride, NULL, j->hilo);
+    else if (j->rc == 0) j->rc = hvb200_plan_run(plan, j->method, j->nsamples, j->seed, j->i0, j->i1, NULL, j->hilo);
     if (j->rc) snprintf(j->err, sizeof j->err, "%s", tls_error);
     j->plan = plan;
     return NULL;
@@ -520,6 +561,7 @@ double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, di
         j->nsamples = (uint64_t)nsamples; j->seed = seed;
         j->i0 = (uint64_t)nsamples * (uint64_t)g / (uint64_t)ndevices;
         j->i1 = (uint64_t)nsamples * (uint64_t)(g + 1) / (uint64_t)ndevices;
+        j->stride = ndevices;
     }
     if (ndevices == 1) {
         shard_main(&jobs[0]);

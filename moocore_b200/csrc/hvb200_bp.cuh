@@ -57,7 +57,9 @@ struct BpArgs {
     int seg_blocks;           // blocks per segment (multiple of 32)
     const double *dirs;       // [count][2][D]
     ull count;
-    double *cta_sums;
+    double *chunk_sums;       // one partial sum per chunk of this launch (fixed tree inside the chunk): the result does
+                              // not depend on which CTA ran which chunk
+    unsigned *chunk_counter;  // dynamic chunk hand-out (zeroed before the launch)
     double *values;
     ull *slow_counter;
     uint2 *hits;              // [grid][kBpHitCap] hit lists
@@ -87,7 +89,7 @@ __host__ __device__ inline BpSmem bp_smem_layout(int D, int R, int seg_blocks, i
     s.best = o; o += (size_t)CH * 8;
     s.piv = o;  o += ((size_t)n_piv * D * 4 + 15) & ~(size_t)15;
     s.list = o; o += (size_t)(kBpThreads / 32) * (CH + 8) * 2;
-    s.bar = o;  o += 16;
+    s.bar = o;  o += 32;
     s.red = o;  o += 8 * 8;
     s.total = o;
     return s;
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
     long long *bestbits = reinterpret_cast<long long *>(smem_raw + L.best);  // [CH]
     float *piv = reinterpret_cast<float *>(smem_raw + L.piv);                // [n_piv][D]
     ull *bar = reinterpret_cast<ull *>(smem_raw + L.bar);
-    unsigned *ctr = reinterpret_cast<unsigned *>(bar + 1);                   // [0] hit entries, [1] next block of phase C
+    unsigned *ctr = reinterpret_cast<unsigned *>(bar + 1);                   // [0] hit entries, [1] next block of phase C, [2] next chunk
     double *red = reinterpret_cast<double *>(smem_raw + L.red);
     const int mstride = L.mask_stride;
 
@@ -193,10 +195,12 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
     }
 
     const ull n_chunks = (a.count + CH - 1) / CH;
-    double acc = 0.0;
     ull slow = 0;
 
-    for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    // chunks are handed out dynamically (their cost varies with the directions); the first one is static
+    ull chunk = blockIdx.x;
+    while (chunk < n_chunks) {
+        if (tid == 0) ctr[2] = atomicAdd(a.chunk_counter, 1u);      // consumed after the barriers of this chunk
         const ull chunk_base = chunk * CH;
         if (!resident && tid == 0) {
             // first segment of this chunk; the previous chunk's phase B is behind several CTA barriers
@@ -468,6 +472,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
             if (tid == 0) { ctr[0] = 0; ctr[1] = kBpThreads / 32; }
         }
 
+        double acc = 0.0;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const double v = pow_chain<D>(__longlong_as_double(bestbits[r * kBpThreads + tid]));
@@ -476,16 +481,19 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                 if (a.values) a.values[chunk_base + (ull)r * kBpThreads + tid] = v;
             }
         }
+        // fixed-shape reduction of the chunk: lanes, then the 8 warps
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        const ull next = (ull)gridDim.x + ctr[2];
+        if (tid == 0)
+            a.chunk_sums[chunk] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+        __syncthreads();                       // red and ctr[2] are rewritten by the next chunk
+        chunk = next;
     }
 
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        acc += __shfl_down_sync(0xffffffffu, acc, off);
-        slow += __shfl_down_sync(0xffffffffu, slow, off);
-    }
-    if (lane == 0) red[warp] = acc;
+    for (int off = 16; off > 0; off >>= 1) slow += __shfl_down_sync(0xffffffffu, slow, off);
     if (a.slow_counter && lane == 0 && slow) atomicAdd(a.slow_counter, slow);
-    __syncthreads();
-    if (tid == 0)
-        a.cta_sums[blockIdx.x] += ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
 }

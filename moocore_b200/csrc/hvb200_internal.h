@@ -28,6 +28,7 @@ struct hvb200_plan {
     size_t n;              /* n' surviving points                                               */
     int kernel;            /* requested HVB200_KERNEL_*                                         */
     uint64_t run_samples;  /* size of the run being started (lets the device side amortise one-off work) */
+    uint64_t run_total;    /* samples of the run being started, whatever its outputs (sizes per-chunk buffers) */
     /* device side (owned by the CUDA TU) */
     void *dev;             /* struct dev_plan*                                                  */
     hvb200_stats stats;

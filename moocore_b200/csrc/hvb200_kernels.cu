@@ -1242,6 +1242,8 @@ struct DevPlan {
     double *bp_pts = nullptr; size_t bp_pts_cap = 0;
     float *bp_piv32 = nullptr; unsigned *bp_pividx = nullptr;
     uint2 *bp_hits = nullptr; size_t bp_hits_cap = 0;    // per-CTA hit lists of phase C
+    double *bp_chunk_sums = nullptr; size_t bp_chunk_cap = 0, bp_chunk_off = 0;   // one partial sum per chunk of the run
+    unsigned *bp_chunk_counter = nullptr;
     unsigned *bp_pkeys = nullptr, *bp_bpair = nullptr; size_t bp_keys_cap = 0, bp_pair_cap = 0;
     int bp_nb = 0, bp_nb_pad = 0, bp_seg_blocks = 0, bp_npiv = 0;
     size_t bp_smem = 0;
@@ -1568,7 +1570,7 @@ static void devplan_release(DevPlan *dp)
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
     cudaFree(dp->dirs_buf[1]); cudaFree(dp->pts_tmp); cudaFree(dp->wins);
-    cudaFree(dp->bp_hits); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
+    cudaFree(dp->bp_hits); cudaFree(dp->bp_chunk_sums); cudaFree(dp->bp_chunk_counter); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
     for (int i = 0; i < 2; i++) { if (dp->ev_gen[i]) cudaEventDestroy(dp->ev_gen[i]); if (dp->ev_used[i]) cudaEventDestroy(dp->ev_used[i]); }
     if (dp->ev_begin) cudaEventDestroy(dp->ev_begin);
     if (dp->gen_stream) cudaStreamDestroy(dp->gen_stream);
@@ -1920,10 +1922,22 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     if (occ < 1) { hvb200_set_error("max-min kernel does not fit on an SM (d=%d)", d); return -1; }
     dp->grid = dp->sm_count * occ;
     if (mode == MODE_BP && dp->bp_hits_cap < (size_t)dp->grid * kBpHitCap) {
-        cudaFree(dp->bp_hits);
+        cudaFree(dp->bp_hits); cudaFree(dp->bp_chunk_sums); cudaFree(dp->bp_chunk_counter);
         dp->bp_hits = nullptr; dp->bp_hits_cap = 0;
         CUDA_TRY(cudaMalloc(&dp->bp_hits, (size_t)dp->grid * kBpHitCap * sizeof(uint2)));
         dp->bp_hits_cap = (size_t)dp->grid * kBpHitCap;
+    }
+    if (mode == MODE_BP) {
+        const size_t ch = (size_t)kBpThreads * bp_R_of(d);
+        const size_t need = (size_t)(plan->run_total / ch) + (size_t)(plan->run_total / batch) + 8;
+        if (dp->bp_chunk_cap < need) {
+            cudaFree(dp->bp_chunk_sums);
+            dp->bp_chunk_sums = nullptr; dp->bp_chunk_cap = 0;
+            CUDA_TRY(cudaMalloc(&dp->bp_chunk_sums, need * sizeof(double)));
+            dp->bp_chunk_cap = need;
+        }
+        if (!dp->bp_chunk_counter) CUDA_TRY(cudaMalloc(&dp->bp_chunk_counter, sizeof(unsigned)));
+        dp->bp_chunk_off = 0;
     }
     if (dp->cta_cap < dp->grid) {
         cudaFree(dp->cta_sums);
@@ -2185,7 +2199,11 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
         ka.seg_blocks = dp->bp_seg_blocks;
         ka.dirs = dp->dirs;
         ka.count = count;
-        ka.cta_sums = dp->cta_sums;
+        if (dp->bp_chunk_off + n_chunks > dp->bp_chunk_cap) { hvb200_set_error("internal: chunk buffer too small"); return -1; }
+        ka.chunk_sums = dp->bp_chunk_sums + dp->bp_chunk_off;
+        dp->bp_chunk_off += (size_t)n_chunks;
+        ka.chunk_counter = dp->bp_chunk_counter;
+        CUDA_TRY(cudaMemsetAsync(dp->bp_chunk_counter, 0, sizeof(unsigned), dp->stream));
         ka.values = a.values;
         ka.slow_counter = dp->counters + 1;
         ka.hits = dp->bp_hits;
@@ -2245,7 +2263,8 @@ extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
     }
     {
         const int b = span_begin(dp, 2);
-        k_reduce<<<1, 1024, 0, dp->stream>>>(dp->cta_sums, dp->grid, dp->out_hilo);
+        if (dp->kernel_used == MODE_BP) k_reduce<<<1, 1024, 0, dp->stream>>>(dp->bp_chunk_sums, (int)dp->bp_chunk_off, dp->out_hilo);
+        else k_reduce<<<1, 1024, 0, dp->stream>>>(dp->cta_sums, dp->grid, dp->out_hilo);
         span_end(dp, b);
         CUDA_TRY(cudaGetLastError());
         plan->stats.reduce_launches++;

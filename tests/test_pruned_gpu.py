@@ -117,3 +117,27 @@ def test_auto_kernel_choice(mb):
     with mb.Plan(x[:200], ref, maxi) as plan:
         plan.run("DZ2019-HW", 10_000_000, 0, 0, 8_000_000)
         assert plan.stats()["kernel"] == 1
+
+
+def test_block_cyclic_shards_sum_to_the_full_run(mb):
+    # hvb200_plan_run_blocks: the interleaved shards of a DZ2019-HW lattice partition it exactly
+    x, ref, maxi = hvcases.config_inputs("cfg2")
+    N = 3_000_017
+    with mb.Plan(x, ref, maxi) as plan:
+        full = sum(plan.run("DZ2019-HW", N, 0, 0, N))
+        for world, block in ((4, 1 << 18), (3, 100_000), (8, 1 << 21)):
+            parts = [plan.run_blocks("DZ2019-HW", N, g, world, block=block) for g in range(world)]
+            assert abs(sum(hi + lo for hi, lo in parts) - full) <= 1e-13 * full
+            assert all(hi > 0 for hi, lo in parts) or block * (world - 1) >= N
+        with pytest.raises(RuntimeError):
+            plan.run_blocks("DZ2019-MC", N, 0, 2)
+        with pytest.raises(RuntimeError):
+            plan.run_blocks("DZ2019-HW", N, 2, 2)
+
+
+def test_results_do_not_depend_on_the_schedule(mb):
+    # per-chunk partial sums with a fixed tree: repeated runs (dynamic chunk hand-out) give identical bits
+    x, ref, maxi = hvcases.config_inputs("cfg2")
+    with mb.Plan(x, ref, maxi, kernel="pruned") as plan:
+        runs = {plan.run("DZ2019-HW", 5_000_000, 0, 1_000_000, 4_000_000) for _ in range(5)}
+    assert len(runs) == 1
