@@ -445,17 +445,27 @@ int hvb200_plan_run_blocks(hvb200_plan *plan, int method, uint_fast32_t nsamples
     uint64_t batch = 0;
     plan->run_samples = total;
     plan->run_total = total;
-    if (hvb200cu_run_begin(plan, cuda_stream, block, &batch)) return -1;
+    if (hvb200cu_run_begin(plan, cuda_stream, total ? total : 1, &batch)) return -1;
     hvb200_hw_params hw;
     hw_params_init(&hw, d, nsamples);
+    /* the blocks of this shard are generated side by side into the direction buffer and evaluated by ONE
+       max-min launch per full buffer: small launches lose ~15 % to start-up and tail */
+    uint64_t filled = 0;
     for (uint64_t lo = first * block; lo < nsamples; lo += stride * block) {
         const uint64_t hi = (nsamples - lo < block) ? nsamples : lo + block;
-        for (uint64_t b0 = lo; b0 < hi; b0 += batch) {
-            const uint64_t cnt = (hi - b0 < batch) ? hi - b0 : batch;
-            if (hvb200cu_gen_hw(plan, &hw, b0, cnt)) return -1;
-            if (plan->n && hvb200cu_maxmin(plan, cnt, NULL)) return -1;
+        for (uint64_t b0 = lo; b0 < hi; ) {
+            const uint64_t room = batch - filled;
+            const uint64_t cnt = (hi - b0 < room) ? hi - b0 : room;
+            if (hvb200cu_gen_hw_at(plan, &hw, b0, cnt, filled)) return -1;
+            filled += cnt;
+            b0 += cnt;
+            if (filled == batch) {
+                if (plan->n && hvb200cu_maxmin(plan, filled, NULL)) return -1;
+                filled = 0;
+            }
         }
     }
+    if (filled && plan->n && hvb200cu_maxmin(plan, filled, NULL)) return -1;
     if (hvb200cu_run_end(plan, out_hilo)) return -1;
     plan->stats.samples = total;
     return 0;

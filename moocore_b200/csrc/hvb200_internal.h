@@ -47,6 +47,7 @@ void hvb200cu_plan_free(struct hvb200_plan *plan);
 int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batch, uint64_t *batch_out);
 /* direction producers: fill the plan's direction buffer with `count` samples */
 int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
+int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count, uint64_t offset);
 /* pipelined DZ2019-HW: generate a batch on a second stream into the spare direction buffer, then swap */
 int hvb200cu_hw_prefetch(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
 int hvb200cu_hw_swap(struct hvb200_plan *plan);

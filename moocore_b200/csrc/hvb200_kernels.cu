@@ -41,6 +41,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <thread>
 #include <mutex>
 #include <algorithm>
 
@@ -1629,26 +1630,36 @@ static bp_fn pick_bp(int d)
         return pick_bp<D - 1>(d);
     }
 }
-static void bp_kd_order(const std::vector<double> &norm, int d, std::vector<unsigned> &idx, size_t lo, size_t hi)
+static void bp_kd_order(const std::vector<double> &norm, int d, std::vector<unsigned> &idx, size_t lo, size_t hi, int depth = 0)
 {
     const size_t cnt = hi - lo;
     if (cnt <= (size_t)kBpBlock) return;
-    int best_k = 0;
-    double best_spread = -1.0;
-    for (int k = 0; k < d; k++) {
-        double mn = INFINITY, mx = -INFINITY;
-        for (size_t i = lo; i < hi; i++) { const double v = norm[(size_t)idx[i] * d + k]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
-        if (mx - mn > best_spread) { best_spread = mx - mn; best_k = k; }
+    // widest objective of the node: one pass over its rows
+    double mn[HVB200_MAXD], mx[HVB200_MAXD];
+    for (int k = 0; k < d; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+    for (size_t i = lo; i < hi; i++) {
+        const double *row = &norm[(size_t)idx[i] * d];
+        for (int k = 0; k < d; k++) { mn[k] = row[k] < mn[k] ? row[k] : mn[k]; mx[k] = row[k] > mx[k] ? row[k] : mx[k]; }
     }
+    int best_k = 0;
+    for (int k = 1; k < d; k++) if (mx[k] - mn[k] > mx[best_k] - mn[best_k]) best_k = k;
     size_t half = (cnt / 2 + kBpBlock - 1) / kBpBlock * kBpBlock;      // left part = whole blocks
     if (half >= cnt) half = cnt / 2;
-    const int k = best_k;
-    std::nth_element(idx.begin() + lo, idx.begin() + lo + half, idx.begin() + hi, [&](unsigned x, unsigned y) {
-        const double vx = norm[(size_t)x * d + k], vy = norm[(size_t)y * d + k];
-        return vx != vy ? vx < vy : x < y;
-    });
-    bp_kd_order(norm, d, idx, lo, lo + half);
-    bp_kd_order(norm, d, idx, lo + half, hi);
+    // median split on (key, index) pairs: contiguous keys for nth_element, index as the tie-break
+    std::vector<std::pair<double, unsigned>> kv(cnt);
+    for (size_t i = 0; i < cnt; i++) kv[i] = {norm[(size_t)idx[lo + i] * d + best_k], idx[lo + i]};
+    std::nth_element(kv.begin(), kv.begin() + half, kv.end());
+    for (size_t i = 0; i < cnt; i++) idx[lo + i] = kv[i].second;
+    std::vector<std::pair<double, unsigned>>().swap(kv);
+    if (depth < 3 && cnt >= 8192) {
+        // the two halves touch disjoint index ranges: 8 host threads at the third level
+        std::thread left([&] { bp_kd_order(norm, d, idx, lo, lo + half, depth + 1); });
+        bp_kd_order(norm, d, idx, lo + half, hi, depth + 1);
+        left.join();
+    } else {
+        bp_kd_order(norm, d, idx, lo, lo + half, depth + 1);
+        bp_kd_order(norm, d, idx, lo + half, hi, depth + 1);
+    }
 }
 static int bp_pivot_count()
 {
@@ -1875,19 +1886,19 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     // AUTO: the screens pay a divergent exact evaluation per candidate, which only amortises over a
     // few hundred points (measured on B200: n=100,d=3 EXACT 602 / DPX 243 / SCREEN 371 Gsp/s;
     // n=1000,d=5 EXACT 734 / SCREEN 930 / DPX 1277; n=1e4,d=10 EXACT 484 / SCREEN 1240 / DPX 1946).
-    // The block-pruned kernel wins from n ~ 500 upwards (n=1000,d=5: 3.1 Tsp/s vs DPX 1.55; n=1e4,d=10: 8.5 vs
+    // The block-pruned kernel wins from n ~ 500 upwards (n=1000,d=5: 3.9 Tsp/s vs DPX 1.55; n=1e4,d=10: 9.8 vs
     // 2.3; n=5e4,d=20: 4.4 vs 1.0; d=50: 0.64 vs 0.0045 for the runtime-d kernel) but its plan-time
-    // preparation (probe kernel, kd order and keys on the host: ~0.3 ms at n=1e3, ~3 ms at n=1e4) only pays
-    // for runs of a few 1e9 sample*point evaluations.
+    // preparation (probe kernel, kd order and keys on the host) costs ~23 ns per coordinate of the point set
+    // (2.3 ms at n=1e4,d=10; 20 ms at n=5e4,d=20), which the ~3x faster kernel earns back after about
+    // 7e4*d directions whatever n is.
     int mode = MODE_DPX;
     if (plan->kernel == HVB200_KERNEL_EXACT) mode = MODE_EXACT;
     else if (plan->kernel == HVB200_KERNEL_SCREEN) mode = MODE_SCREEN;
     else if (plan->kernel == HVB200_KERNEL_BP) mode = MODE_BP;
     else if (plan->kernel == HVB200_KERNEL_AUTO) {
-        const double work = (double)plan->run_samples * (double)dp->n;
         if (dp->n < 256) mode = MODE_EXACT;
         else if (d > 32) mode = MODE_BP;
-        else if (dp->n >= 512 && (dp->bp_ready || work >= 4e9)) mode = MODE_BP;
+        else if (dp->n >= 512 && (dp->bp_ready || plan->run_samples >= (uint64_t)65536 * (uint64_t)d)) mode = MODE_BP;
     }
     if (mode == MODE_BP && dp->n + 256 >= ((size_t)1 << kBpPtBits)) mode = MODE_DPX;   // candidate entries hold 23-bit point indices
     if (d > 32 && mode != MODE_BP) mode = MODE_EXACT;
@@ -2005,14 +2016,20 @@ static int stage_to_device(struct hvb200_plan *plan, DevPlan *dp, const double *
 
 extern "C" int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count)
 {
+    return hvb200cu_gen_hw_at(plan, hw, i0, count, 0);
+}
+// directions [i0, i0 + count) of the lattice into rows [offset, offset + count) of the direction buffer
+extern "C" int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count, uint64_t offset)
+{
     DevPlan *dp = (DevPlan *)plan->dev;
+    if ((offset + count) * (uint64_t)(2 * hw->d) > dp->dirs_cap) { hvb200_set_error("internal: direction buffer overflow"); return -1; }
     if (hw->nsamples > (1ull << 32)) { hvb200_set_error("DZ2019-HW on the device supports nsamples <= 2^32"); return -1; }
     HwDev P;
     P.N = hw->nsamples;
     P.d = hw->d;
     for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
     const int b = span_begin(dp, 1);
-    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(P, i0, count, dp->dirs, dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
+    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(P, i0, count, dp->dirs + offset * (uint64_t)(2 * hw->d), dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
     plan->stats.dirgen_launches++;
