@@ -114,6 +114,14 @@ MOOCORE_API int hvb200_plan_run_directions(hvb200_plan *plan, const double *r_ho
  * count x (nobjs-1) doubles row-major, as produced by the library (one host thread per objective). */
 MOOCORE_API int hvb200_rphi_sequence(dimension_t nobjs, uint64_t i0, uint64_t count, double *u_out);
 
+/* Host-only parity/debug of the MT19937 jump-ahead that parallelises the DZ2019-MC stream generator
+ * (moocore_b200/csrc/hvb200_mtjump.c): poly = t^J mod phi(t) as 624 words (bit i of word w = coefficient
+ * 32 w + i, phi = characteristic polynomial of c/mt19937/mt19937.c:18-55); _double squares it (2 J);
+ * _apply_host returns the 624-word state window J words after state_in's. */
+MOOCORE_API int hvb200_mtjump_poly(uint64_t J, uint32_t poly_out[624]);
+MOOCORE_API int hvb200_mtjump_double(const uint32_t poly_in[624], uint32_t poly_out[624]);
+MOOCORE_API int hvb200_mtjump_apply_host(const uint32_t state_in[624], const uint32_t poly[624], uint32_t state_out[624]);
+
 /* Single-process multi-GPU: evaluate one estimate sharded over `ndevices` GPUs
  * (devices 0..ndevices-1, contiguous index ranges, partial sums combined with one NCCL
  * all-gather when libnccl can be loaded, else by per-device copies). */

@@ -44,6 +44,9 @@ struct McGen {
     ull *scalars_host = nullptr;              // pinned mirror
     size_t have_pairs = 0;                    // valid pairs at the head of `words`
     bool tables_ready = false;
+    // parallel MT19937 generation by jump-ahead (hvb200_mtjump.c): start states of the segments, state sequences
+    unsigned *seg_states = nullptr; size_t seg_cap = 0;      // [segments][624]
+    unsigned *xbuf = nullptr; size_t xbuf_cap = 0;           // [jumps of one round][34 * 624]
 };
 
 // ---- MT19937 block generation ------------------------------------------------------------------
@@ -60,26 +63,39 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y)
     y ^= y >> 18;
     return y;
 }
-// Generates `nblocks` further blocks of 624 tempered words after the current state.
-// x[n] = x[n-227] ^ twist(x[n-624], x[n-623]): 227 consecutive words are independent, so a block is
-// three dependent phases.  Old and new blocks live in two shared arrays (ping-pong), which leaves
-// one barrier per phase; tempering and the global store of a block overlap the next block's phases.
-__global__ void __launch_bounds__(256) k_mt_generate(unsigned *__restrict__ state, unsigned *__restrict__ out, int nblocks)
+// CTA s generates the blocks [s*seg_blocks, min((s+1)*seg_blocks, nblocks_total)) that follow ITS state
+// states[s] (624 words each) and writes them, tempered or raw, to out + s*out_stride (+624 when the state itself
+// is copied in front: the "state sequence" consumed by k_mt_jump).  The last CTA leaves its final state in
+// final_state.  x[n] = x[n-227] ^ twist(x[n-624], x[n-623]): 227 consecutive words are independent, so a
+// block is three dependent phases.  Old and new blocks live in two shared arrays (ping-pong), which leaves one
+// barrier per phase; tempering and the global store of a block overlap the next block's phases.
+__global__ void __launch_bounds__(256) k_mt_generate(const unsigned *states, unsigned *__restrict__ out,
+                                                     int nblocks_total, int seg_blocks, size_t out_stride,
+                                                     unsigned *final_state, int temper, int copy_state)   // final_state may alias states
 {
     __shared__ unsigned xs[2][kMtN];
     const int t = threadIdx.x;
-    for (int i = t; i < kMtN; i += 256) xs[0][i] = state[i];
+    const int first = blockIdx.x * seg_blocks;
+    const int nblocks = min(seg_blocks, nblocks_total - first);
+    const unsigned *state = states + (size_t)blockIdx.x * kMtN;
+    unsigned *obase = out + (size_t)blockIdx.x * out_stride;
+    for (int i = t; i < kMtN; i += 256) {
+        const unsigned v = state[i];
+        xs[0][i] = v;
+        if (copy_state) obase[i] = v;
+    }
+    if (copy_state) obase += kMtN;
     __syncthreads();
     int cur = 0;
     for (int b = 0; b < nblocks; b++) {
         const unsigned *xo = xs[cur];
         unsigned *xn = xs[cur ^ 1];
-        unsigned *o = out + (size_t)b * kMtN;
+        unsigned *o = obase + (size_t)b * kMtN;
         // phase 1: i in [0, 227)      old x[i], x[i+1], x[i+397]
         if (t < 227) {
             const unsigned v = mt_twist(xo[t], xo[t + 1], xo[t + kMtM]);
             xn[t] = v;
-            o[t] = mt_temper(v);
+            o[t] = temper ? mt_temper(v) : v;
         }
         __syncthreads();
         // phase 2: i in [227, 454)    old x[i], x[i+1], new x[i-227]
@@ -87,7 +103,7 @@ __global__ void __launch_bounds__(256) k_mt_generate(unsigned *__restrict__ stat
             const int i = 227 + t;
             const unsigned v = mt_twist(xo[i], xo[i + 1], xn[i - 227]);
             xn[i] = v;
-            o[i] = mt_temper(v);
+            o[i] = temper ? mt_temper(v) : v;
         }
         __syncthreads();
         // phase 3: i in [454, 624)    old x[i], x[i+1] (new x[0] for i = 623), new x[i-227]
@@ -96,12 +112,47 @@ __global__ void __launch_bounds__(256) k_mt_generate(unsigned *__restrict__ stat
             const unsigned nxt = (i + 1 == kMtN) ? xn[0] : xo[i + 1];
             const unsigned v = mt_twist(xo[i], nxt, xn[i - 227]);
             xn[i] = v;
-            o[i] = mt_temper(v);
+            o[i] = temper ? mt_temper(v) : v;
         }
         __syncthreads();
         cur ^= 1;
     }
-    for (int i = t; i < kMtN; i += 256) state[i] = xs[cur][i];
+    if (final_state != nullptr && blockIdx.x == gridDim.x - 1)
+        for (int i = t; i < kMtN; i += 256) final_state[i] = xs[cur][i];
+}
+
+// Jump-ahead (hvb200_mtjump.c): the state J words ahead is the GF(2) convolution of the state sequence X with
+// the polynomial t^J mod phi, given as the sorted list of its set coefficients:
+//     out[p] = XOR over listed i of X[i + p],   p = 0..623.
+// grid = (jumps, kMtSplits): CTA (j, sp) handles the coefficients in [sp*1248, (sp+1)*1248) — a 1872-word
+// window of X in shared memory — and XORs its partial result into out (zeroed by the caller).
+static constexpr int kMtSplits = 16, kMtSlice = 1248;       // 16 * 1248 = 19968 >= 19937
+static constexpr int kMtSeqBlocks = 33;                      // 624 + 33*624 = 21216 >= 19937 + 623 words
+static constexpr int kMtSeqWords = (kMtSeqBlocks + 1) * kMtN;
+__global__ void __launch_bounds__(256) k_mt_jump(const unsigned *__restrict__ X, const unsigned short *__restrict__ pos,
+                                                 const int *__restrict__ slice_off, unsigned *__restrict__ out)
+{
+    __shared__ unsigned xs[kMtSlice + kMtN];
+    __shared__ unsigned short ps[kMtSlice];
+    const int t = threadIdx.x, j = blockIdx.x, sp = blockIdx.y;
+    const int base = sp * kMtSlice;
+    const unsigned *x = X + (size_t)j * kMtSeqWords + base;
+    for (int i = t; i < kMtSlice + kMtN; i += 256) xs[i] = x[i];
+    const int p0 = slice_off[sp], n = slice_off[sp + 1] - p0;
+    for (int i = t; i < n; i += 256) ps[i] = (unsigned short)(pos[p0 + i] - base);
+    __syncthreads();
+    unsigned a0 = 0, a1 = 0, a2 = 0;
+    const bool third = t + 512 < kMtN;
+    for (int i = 0; i < n; i++) {
+        const int q = ps[i] + t;
+        a0 ^= xs[q];
+        a1 ^= xs[q + 256];
+        if (third) a2 ^= xs[q + 512];
+    }
+    unsigned *o = out + (size_t)j * kMtN;
+    atomicXor(o + t, a0);
+    atomicXor(o + t + 256, a1);
+    if (third) atomicXor(o + t + 512, a2);
 }
 
 // ---- ziggurat, one hypothetical attempt per pair -------------------------------------------------
@@ -256,6 +307,113 @@ static int mcgen_begin(DevPlan *dp, McGen *g, uint32_t seed)
     return 0;
 }
 
+// ---- parallel MT19937 generation -------------------------------------------------------------------
+// A run of blocks is cut into segments of kMtSegBlocks blocks.  The start states of the segments come from
+// log2(segments) rounds of jump-ahead: round k maps the states of segments [0, 2^k) to those of segments
+// [2^k, 2^(k+1)) with the polynomial of J * 2^k words, J = one segment (k_mt_generate in "state sequence" mode,
+// then k_mt_jump).  Then every segment is generated by its own CTA.  Bit-identical to the sequential
+// generator by construction (tests: the DZ2019-MC goldens and the host/device cross-checks).
+static constexpr int kMtSegBlocks = 256;                    // 159 744 words, ~65 us for one CTA
+static constexpr int kMtLevels = 10;                        // up to 1024 segments per pass
+struct MtJumpTables {
+    unsigned short *pos = nullptr;                          // [kMtLevels][20000] sorted set coefficients
+    int *slice_off = nullptr;                               // [kMtLevels][kMtSplits + 1]
+    bool ready = false, failed = false;
+};
+static MtJumpTables g_mtjump[16];
+static std::mutex g_mtjump_mutex;
+static constexpr int kMtPosStride = 20000;
+
+static int mtjump_tables(int device, MtJumpTables **out)
+{
+    *out = nullptr;
+    if (device < 0 || device >= 16 || getenv("HVB200_MT_SERIAL")) return 0;
+    std::lock_guard<std::mutex> lock(g_mtjump_mutex);
+    MtJumpTables *T = &g_mtjump[device];
+    if (T->failed) return 0;
+    if (!T->ready) {
+        static std::vector<unsigned short> h_pos;           // host copy, shared by all devices
+        static std::vector<int> h_off;
+        if (h_pos.empty()) {
+            std::vector<unsigned> poly(kMtN), nxt(kMtN);
+            if (hvb200_mtjump_poly((uint64_t)kMtSegBlocks * kMtN, poly.data())) { T->failed = true; return 0; }
+            h_pos.assign((size_t)kMtLevels * kMtPosStride, 0);
+            h_off.assign((size_t)kMtLevels * (kMtSplits + 1), 0);
+            for (int k = 0; k < kMtLevels; k++) {
+                int cnt = 0;
+                int *off = &h_off[(size_t)k * (kMtSplits + 1)];
+                for (int sp = 0; sp < kMtSplits; sp++) {
+                    off[sp] = cnt;
+                    for (int i = sp * kMtSlice; i < (sp + 1) * kMtSlice && i < 19937; i++)
+                        if ((poly[i >> 5] >> (i & 31)) & 1u) h_pos[(size_t)k * kMtPosStride + cnt++] = (unsigned short)i;
+                }
+                off[kMtSplits] = cnt;
+                if (k + 1 < kMtLevels) {
+                    if (hvb200_mtjump_double(poly.data(), nxt.data())) { h_pos.clear(); T->failed = true; return 0; }
+                    poly.swap(nxt);
+                }
+            }
+        }
+        CUDA_TRY(cudaMalloc(&T->pos, h_pos.size() * sizeof(unsigned short)));
+        CUDA_TRY(cudaMalloc(&T->slice_off, h_off.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(T->pos, h_pos.data(), h_pos.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(T->slice_off, h_off.data(), h_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+        T->ready = true;
+    }
+    *out = T;
+    return 0;
+}
+
+// `nblocks` further blocks of tempered words after g->state into `out`; g->state is advanced.
+static int mcgen_generate(struct hvb200_plan *plan, DevPlan *dp, McGen *g, unsigned *out, int nblocks)
+{
+    MtJumpTables *T = nullptr;
+    if (nblocks >= 2 * kMtSegBlocks && mtjump_tables(dp->device, &T)) return -1;
+    if (T == nullptr) {
+        k_mt_generate<<<1, 256, 0, dp->stream>>>(g->state, out, nblocks, nblocks, 0, g->state, 1, 0);
+        CUDA_TRY(cudaGetLastError());
+        plan->stats.dirgen_launches++;
+        return 0;
+    }
+    const int max_seg = 1 << kMtLevels;
+    while (nblocks > 0) {
+        const int pass_blocks = std::min(nblocks, max_seg * kMtSegBlocks);
+        const int nseg = (pass_blocks + kMtSegBlocks - 1) / kMtSegBlocks;
+        if (g->seg_cap < (size_t)nseg) {
+            cudaFree(g->seg_states);
+            g->seg_states = nullptr; g->seg_cap = 0;
+            CUDA_TRY(cudaMalloc(&g->seg_states, (size_t)nseg * kMtN * sizeof(unsigned)));
+            g->seg_cap = (size_t)nseg;
+        }
+        int max_jumps = 0;
+        for (int c = 1; c < nseg; c <<= 1) max_jumps = std::max(max_jumps, std::min(c, nseg - c));
+        if (g->xbuf_cap < (size_t)max_jumps) {
+            cudaFree(g->xbuf);
+            g->xbuf = nullptr; g->xbuf_cap = 0;
+            CUDA_TRY(cudaMalloc(&g->xbuf, (size_t)max_jumps * kMtSeqWords * sizeof(unsigned)));
+            g->xbuf_cap = (size_t)max_jumps;
+        }
+        CUDA_TRY(cudaMemcpyAsync(g->seg_states, g->state, kMtN * sizeof(unsigned), cudaMemcpyDeviceToDevice, dp->stream));
+        int level = 0;
+        for (int c = 1; c < nseg; c <<= 1, level++) {
+            const int cnt = std::min(c, nseg - c);
+            // state sequences of segments [0, cnt), then their windows c segments ahead
+            k_mt_generate<<<cnt, 256, 0, dp->stream>>>(g->seg_states, g->xbuf, cnt * kMtSeqBlocks, kMtSeqBlocks, (size_t)kMtSeqWords, nullptr, 0, 1);
+            CUDA_TRY(cudaMemsetAsync(g->seg_states + (size_t)c * kMtN, 0, (size_t)cnt * kMtN * sizeof(unsigned), dp->stream));
+            k_mt_jump<<<dim3((unsigned)cnt, kMtSplits), 256, 0, dp->stream>>>(g->xbuf, T->pos + (size_t)level * kMtPosStride,
+                                                                              T->slice_off + (size_t)level * (kMtSplits + 1),
+                                                                              g->seg_states + (size_t)c * kMtN);
+            plan->stats.dirgen_launches += 2;
+        }
+        k_mt_generate<<<nseg, 256, 0, dp->stream>>>(g->seg_states, out, pass_blocks, kMtSegBlocks, (size_t)kMtSegBlocks * kMtN, g->state, 1, 0);
+        CUDA_TRY(cudaGetLastError());
+        plan->stats.dirgen_launches++;
+        out += (size_t)pass_blocks * kMtN;
+        nblocks -= pass_blocks;
+    }
+    return 0;
+}
+
 // Produce the next `need` normals of the stream into `normals_dev` (nullptr = discard).
 static int mcgen_normals(struct hvb200_plan *plan, DevPlan *dp, McGen *g, ull need, double *normals_dev)
 {
@@ -268,11 +426,10 @@ static int mcgen_normals(struct hvb200_plan *plan, DevPlan *dp, McGen *g, ull ne
             const size_t missing_words = 2 * (target - g->have_pairs);
             const int nblocks = (int)((missing_words + kMtN - 1) / kMtN);
             const int b = span_begin(dp, 1);
-            k_mt_generate<<<1, 256, 0, dp->stream>>>(g->state, g->words + 2 * g->have_pairs, nblocks);
+            const int rc = mcgen_generate(plan, dp, g, g->words + 2 * g->have_pairs, nblocks);
             span_end(dp, b);
-            CUDA_TRY(cudaGetLastError());
+            if (rc) return -1;
             g->have_pairs += (size_t)nblocks * kMtN / 2;
-            plan->stats.dirgen_launches++;
         }
         const ull P = g->have_pairs;
         const unsigned grid = (unsigned)((P + 255) / 256);
@@ -320,6 +477,7 @@ static void mcgen_free(McGen *g)
 {
     cudaFree(g->state); cudaFree(g->words); cudaFree(g->L); cudaFree(g->emit); cudaFree(g->val); cudaFree(g->ftab);
     cudaFree(g->fscan); cudaFree(g->eflag); cudaFree(g->epos); cudaFree(g->cub_tmp); cudaFree(g->scalars);
+    cudaFree(g->seg_states); cudaFree(g->xbuf);
     if (g->scalars_host) cudaFreeHost(g->scalars_host);
     *g = McGen();
 }
