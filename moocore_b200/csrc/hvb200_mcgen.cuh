@@ -165,6 +165,13 @@ __global__ void __launch_bounds__(256) k_zig_classify(const unsigned *__restrict
                                                       unsigned char *__restrict__ Lout, unsigned char *__restrict__ emit,
                                                       double *__restrict__ val, ull *__restrict__ ftab, ull *scalars)
 {
+    // the 256-layer tables are indexed by random bits: constant memory would serialise the 32 lanes of a warp
+    __shared__ double s_wi[256], s_fi[256];
+    __shared__ ull s_ki[256];
+    s_wi[threadIdx.x] = c_zig_wi[threadIdx.x];
+    s_fi[threadIdx.x] = c_zig_fi[threadIdx.x];
+    s_ki[threadIdx.x] = c_zig_ki[threadIdx.x];
+    __syncthreads();
     const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= npairs) return;
     const double R = __longlong_as_double((long long)HVB200_ZIG_R_BITS);
@@ -172,11 +179,11 @@ __global__ void __launch_bounds__(256) k_zig_classify(const unsigned *__restrict
     const ull r = ((ull)words[2 * j] << 32) | words[2 * j + 1];
     const int layer = (int)(r & 0xff);
     const ull mag = (r >> 9) & 0x000fffffffffffffull;
-    double x = (double)mag * c_zig_wi[layer];
+    double x = (double)mag * s_wi[layer];
     if ((r >> 8) & 1) x = -x;
     int L = 1, em = 1;
     double v = x;
-    if (!(mag < c_zig_ki[layer])) {
+    if (!(mag < s_ki[layer])) {
         if (layer == 0) {               // tail: pairs j+1, j+2, then j+3, j+4, ...
             L = 0;
             for (int t = 0; 1 + 2 * (t + 1) <= kZigMaxL; t++) {
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(256) k_zig_classify(const unsigned *__restrict
             if (j + 1 >= npairs) { L = 0; em = 0; }
             else {
                 const double u = pair_to_unit(words[2 * j + 2], words[2 * j + 3]);
-                const double f_hi = c_zig_fi[layer - 1], f_lo = c_zig_fi[layer];
+                const double f_hi = s_fi[layer - 1], f_lo = s_fi[layer];
                 L = 2;
                 em = ((f_hi - f_lo) * u + f_lo < exp(-0.5 * x * x)) ? 1 : 0;
             }
