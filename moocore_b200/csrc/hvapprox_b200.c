@@ -86,24 +86,40 @@ int hvb200_plan_create(hvb200_plan **plan_out, const double *data, size_t npoint
                          device, hvb200cu_device_count());
         return -3;
     }
-    double *pts = malloc((npoints ? npoints : 1) * (size_t)d * sizeof *pts);
-    if (!pts) { hvb200_set_error("out of host memory"); return -4; }
-    const size_t n = transform_and_filter(data, npoints, d, ref, maximise, pts);
-    if (n == 0) { free(pts); return 0; }         /* caller returns 0.0, c/hvapprox.c:228-229 */
     hvb200_plan *plan = calloc(1, sizeof *plan);
-    if (!plan) { free(pts); hvb200_set_error("out of host memory"); return -4; }
+    if (!plan) { hvb200_set_error("out of host memory"); return -4; }
     plan->device = device;
     plan->d = d;
-    plan->n = n;
     plan->kernel = HVB200_KERNEL_AUTO;
     const char *env = getenv("HVB200_KERNEL");
     if (env && !strcmp(env, "exact")) plan->kernel = HVB200_KERNEL_EXACT;
     if (env && !strcmp(env, "screen")) plan->kernel = HVB200_KERNEL_SCREEN;
     if (env && !strcmp(env, "dpx")) plan->kernel = HVB200_KERNEL_DPX;
     if (env && !strcmp(env, "pruned")) plan->kernel = HVB200_KERNEL_BP;
-    const int rc = hvb200cu_plan_upload(plan, pts);
-    free(pts);
-    if (rc) { hvb200cu_plan_free(plan); free(plan); return -1; }
+    /* transform_and_filter (c/hvapprox.c:30-66): on the device for large inputs (the reference flags its host
+       loop as slow at 1M points, :35-42), on the host below 2^18 coordinates where a kernel launch, a scan and
+       two synchronisations cost more than the loop.  HVB200_TRANSFORM=host|device forces one.  Same bits. */
+    const char *tf = getenv("HVB200_TRANSFORM");
+    int on_device = (uint64_t)npoints * (uint64_t)d >= (1u << 18);
+    if (tf && !strcmp(tf, "host")) on_device = 0;
+    if (tf && !strcmp(tf, "device")) on_device = 1;
+    int rc;
+    if (on_device) {
+        unsigned char mx[HVB200_MAXD];
+        for (int k = 0; k < d; k++) mx[k] = maximise[k] ? 1 : 0;
+        size_t n = 0;
+        rc = hvb200cu_plan_upload_raw(plan, data, npoints, ref, mx, &n);
+        if (rc == 0 && n == 0) { if (plan->dev) hvb200cu_plan_free(plan); free(plan); return 0; }   /* caller returns 0.0, c/hvapprox.c:228-229 */
+    } else {
+        double *pts = malloc((npoints ? npoints : 1) * (size_t)d * sizeof *pts);
+        if (!pts) { free(plan); hvb200_set_error("out of host memory"); return -4; }
+        const size_t n = transform_and_filter(data, npoints, d, ref, maximise, pts);
+        if (n == 0) { free(pts); free(plan); return 0; }     /* caller returns 0.0, c/hvapprox.c:228-229 */
+        plan->n = n;
+        rc = hvb200cu_plan_upload(plan, pts);
+        free(pts);
+    }
+    if (rc) { if (plan->dev) hvb200cu_plan_free(plan); free(plan); return -1; }
     *plan_out = plan;
     return 0;
 }

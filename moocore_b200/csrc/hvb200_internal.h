@@ -41,6 +41,8 @@ void hvb200_set_error(const char *fmt, ...);
 int hvb200cu_device_count(void);
 /* upload n x d transformed points (host, row-major) */
 int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host);
+int hvb200cu_plan_upload_raw(struct hvb200_plan *plan, const double *data_host, size_t npoints,
+                             const double *ref, const unsigned char *maximise, size_t *kept_out);
 void hvb200cu_plan_free(struct hvb200_plan *plan);
 
 /* A run = begin, then per batch {generate directions, maxmin}, then end. */

@@ -41,6 +41,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <chrono>
 #include <thread>
 #include <mutex>
 #include <algorithm>
@@ -1223,6 +1224,58 @@ __global__ void __launch_bounds__(256) k_fp64_bench(double *out, int iters, doub
 }
 
 // ------------------------------------------------------------------------------------------------
+// transform_and_filter on the device (c/hvapprox.c:30-66): p' = maximise_k ? p - ref : ref - p,
+// rows with any p'_k <= 0 are dropped, the survivors keep their order.  One flag per point, an exclusive sum of
+// the flags (cub), a scatter of the surviving rows.  The subtraction is the reference's single IEEE operation,
+// so the compacted set is bit-identical to the host path.
+// ------------------------------------------------------------------------------------------------
+struct TfArgs {
+    double ref[HVB200_MAXD];
+    unsigned char maxi[HVB200_MAXD];
+    int d;
+};
+__global__ void __launch_bounds__(256) k_tf_flags(const double *__restrict__ data, ull n, const TfArgs a, unsigned *__restrict__ flags)
+{
+    const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *src = data + i * (ull)a.d;
+    unsigned keep = 1u;
+    for (int k = 0; k < a.d; k++) {
+        const double v = a.maxi[k] ? src[k] - a.ref[k] : a.ref[k] - src[k];
+        if (!(v > 0)) keep = 0u;
+    }
+    flags[i] = keep;
+}
+__global__ void __launch_bounds__(256) k_tf_scatter(const double *__restrict__ data, ull n, const TfArgs a,
+                                                    const unsigned *__restrict__ flags, const unsigned *__restrict__ pos,
+                                                    double *__restrict__ out, ull *__restrict__ kept)
+{
+    const ull w = (ull)blockIdx.x * blockDim.x + threadIdx.x;       // element index = point * d + k
+    if (w >= n * (ull)a.d) return;
+    const ull i = w / (ull)a.d;
+    const int k = (int)(w - i * (ull)a.d);
+    if (flags[i]) out[(ull)pos[i] * (ull)a.d + k] = a.maxi[k] ? data[w] - a.ref[k] : a.ref[k] - data[w];
+    if (w == 0) *kept = (ull)pos[n - 1] + flags[n - 1];
+}
+// per-objective minimum and maximum of a set of positive coordinates (bit patterns of positive doubles order
+// like unsigned integers): lo initialised to +inf bits, hi to 0
+__global__ void __launch_bounds__(256) k_colrange(const double *__restrict__ pts, ull n, int d, ull *__restrict__ lo, ull *__restrict__ hi)
+{
+    __shared__ ull slo[HVB200_MAXD], shi[HVB200_MAXD];
+    for (int k = threadIdx.x; k < d; k += blockDim.x) { slo[k] = 0x7ff0000000000000ull; shi[k] = 0ull; }
+    __syncthreads();
+    const ull total = n * (ull)d;
+    for (ull w = (ull)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (ull)gridDim.x * blockDim.x) {
+        const int k = (int)(w % (ull)d);
+        const ull bits = (ull)__double_as_longlong(pts[w]);
+        atomicMin(&slo[k], bits);
+        atomicMax(&shi[k], bits);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < d; k += blockDim.x) { atomicMin(&lo[k], slo[k]); atomicMax(&hi[k], shi[k]); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 struct DevPlan {
@@ -1453,7 +1506,79 @@ static bool pool_give(DevPlan *dp)
     return true;
 }
 
+static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, const double *pts_dev);
 extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host)
+{
+    return plan_upload_impl(plan, pts_host, nullptr);
+}
+
+// transform_and_filter on the device: raw caller data -> compacted transformed set -> plan.  *kept_out = 0
+// means no point strictly dominates ref (no plan is built: the caller returns 0.0, c/hvapprox.c:228-229).
+extern "C" int hvb200cu_plan_upload_raw(struct hvb200_plan *plan, const double *data_host, size_t npoints,
+                                        const double *ref, const unsigned char *maximise, size_t *kept_out)
+{
+    *kept_out = 0;
+    CUDA_TRY(cudaSetDevice(plan->device));
+    const int d = plan->d;
+    if (npoints == 0) return 0;
+    if (npoints >= 0x7fffffffull) { hvb200_set_error("on-device transform_and_filter supports < 2^31 points"); return -1; }
+    // one cached scratch allocation per device (cudaMalloc/cudaFree cost more than the kernels: 1.3 of 2.1 ms at
+    // n = 5e4, d = 20); released again when it grew beyond 256 MB
+    static std::mutex tf_mutex;
+    static void *tf_scratch[16] = {nullptr};
+    static size_t tf_cap[16] = {0};
+    std::lock_guard<std::mutex> lock(tf_mutex);
+    const int dev = plan->device < 16 ? plan->device : 15;
+    const size_t elems = npoints * (size_t)d;
+    size_t tmp_bytes = 0;
+    if (cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr, (int)npoints, (cudaStream_t)0) != cudaSuccess) {
+        hvb200_set_error("cub scan sizing failed"); cudaGetLastError(); return -1;
+    }
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t need = 2 * up(elems * sizeof(double)) + 2 * up(npoints * sizeof(unsigned)) + up(sizeof(ull)) + up(tmp_bytes ? tmp_bytes : 16);
+    if (tf_cap[dev] < need) {
+        cudaFree(tf_scratch[dev]);
+        tf_scratch[dev] = nullptr; tf_cap[dev] = 0;
+        if (cudaMalloc(&tf_scratch[dev], need) != cudaSuccess) {
+            cudaGetLastError();
+            hvb200_set_error("out of device memory (transform_and_filter, %zu points)", npoints);
+            return -1;
+        }
+        tf_cap[dev] = need;
+    }
+    unsigned char *base = (unsigned char *)tf_scratch[dev];
+    double *raw = (double *)base;                          base += up(elems * sizeof(double));
+    double *out = (double *)base;                          base += up(elems * sizeof(double));
+    unsigned *flags = (unsigned *)base;                    base += up(npoints * sizeof(unsigned));
+    unsigned *pos = (unsigned *)base;                      base += up(npoints * sizeof(unsigned));
+    ull *kept_dev = (ull *)base;                           base += up(sizeof(ull));
+    void *tmp = (void *)base;
+    int rc = -1;
+    ull kept = 0;
+    TfArgs a;
+    a.d = d;
+    for (int k = 0; k < HVB200_MAXD; k++) { a.ref[k] = k < d ? ref[k] : 0.0; a.maxi[k] = k < d ? (maximise[k] ? 1 : 0) : 0; }
+    do {
+        if (cudaMemcpy(raw, data_host, elems * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        k_tf_flags<<<(unsigned)((npoints + 255) / 256), 256>>>(raw, (ull)npoints, a, flags);
+        if (cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, pos, (int)npoints, (cudaStream_t)0) != cudaSuccess) break;
+        k_tf_scatter<<<(unsigned)((elems + 255) / 256), 256>>>(raw, (ull)npoints, a, flags, pos, out, kept_dev);
+        if (cudaMemcpy(&kept, kept_dev, sizeof kept, cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc) {
+        const cudaError_t e = cudaGetLastError();
+        hvb200_set_error("on-device transform_and_filter failed: %s", cudaGetErrorString(e));
+    } else if (kept) {
+        plan->n = (size_t)kept;
+        rc = plan_upload_impl(plan, nullptr, out);      // ends with a stream synchronisation: `out` is free afterwards
+        *kept_out = (size_t)kept;
+    }
+    if (tf_cap[dev] > ((size_t)256 << 20)) { cudaFree(tf_scratch[dev]); tf_scratch[dev] = nullptr; tf_cap[dev] = 0; }
+    return rc;
+}
+
+static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, const double *pts_dev)
 {
     CUDA_TRY(cudaSetDevice(plan->device));
     if (upload_constants(plan->device)) return -1;
@@ -1506,18 +1631,31 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
         dp->pts_cap = padded;
     }
     // zero only the padding rows behind the real points
-    CUDA_TRY(cudaMemcpyAsync(dp->pts, pts_host, plan->n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice, us));
+    if (pts_dev) CUDA_TRY(cudaMemcpyAsync(dp->pts, pts_dev, plan->n * (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, us));
+    else CUDA_TRY(cudaMemcpyAsync(dp->pts, pts_host, plan->n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice, us));
     if (padded > plan->n * (size_t)d)
         CUDA_TRY(cudaMemsetAsync(dp->pts + plan->n * (size_t)d, 0, (padded - plan->n * (size_t)d) * sizeof(double), us));
     if (d <= 32) {
         // ---- DPX keys: per-objective range of the point set, monotone 16-bit quantisation on the device
         for (int k = 0; k < d; k++) { dp->qlo[k] = INFINITY; dp->qhi[k] = -INFINITY; }
-        for (size_t i = 0; i < plan->n; i++)
-            for (int k = 0; k < d; k++) {
-                const double v = pts_host[i * (size_t)d + k];
-                if (v < dp->qlo[k]) dp->qlo[k] = v;
-                if (v > dp->qhi[k]) dp->qhi[k] = v;
-            }
+        if (pts_dev) {
+            // per-objective range by a device reduction (the set never visits the host)
+            ull init[2 * 32], res[2 * 32];
+            for (int k = 0; k < 32; k++) { init[k] = 0x7ff0000000000000ull; init[32 + k] = 0ull; }
+            ull *rng = reinterpret_cast<ull *>(dp->qdev);               // 64 of its 96 doubles, overwritten below
+            CUDA_TRY(cudaMemcpyAsync(rng, init, sizeof init, cudaMemcpyHostToDevice, us));
+            k_colrange<<<dp->sm_count * 4, 256, 0, us>>>(dp->pts, (ull)plan->n, d, rng, rng + 32);
+            CUDA_TRY(cudaMemcpyAsync(res, rng, sizeof res, cudaMemcpyDeviceToHost, us));
+            CUDA_TRY(cudaStreamSynchronize(us));
+            for (int k = 0; k < d; k++) { memcpy(&dp->qlo[k], &res[k], 8); memcpy(&dp->qhi[k], &res[32 + k], 8); }
+        } else {
+            for (size_t i = 0; i < plan->n; i++)
+                for (int k = 0; k < d; k++) {
+                    const double v = pts_host[i * (size_t)d + k];
+                    if (v < dp->qlo[k]) dp->qlo[k] = v;
+                    if (v > dp->qhi[k]) dp->qhi[k] = v;
+                }
+        }
         for (int k = 0; k < d; k++) {
             const double range = dp->qhi[k] - dp->qlo[k];
             dp->qscale[k] = (range > 0 && std::isfinite(range)) ? (double)kKeyScale / range : 0.0;

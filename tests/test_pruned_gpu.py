@@ -141,3 +141,29 @@ def test_results_do_not_depend_on_the_schedule(mb):
     with mb.Plan(x, ref, maxi, kernel="pruned") as plan:
         runs = {plan.run("DZ2019-HW", 5_000_000, 0, 1_000_000, 4_000_000) for _ in range(5)}
     assert len(runs) == 1
+
+
+@pytest.mark.parametrize("d,n", [(3, 5000), (10, 40000), (40, 9000)])
+def test_device_transform_and_filter_matches_host(mb, d, n, monkeypatch):
+    # transform_and_filter (c/hvapprox.c:30-66) on the device vs the host loop: same survivors, same order, same bits
+    rng = np.random.default_rng(d)
+    x = rng.random((n, d))
+    maxi = rng.random(d) < 0.4
+    ref = np.where(maxi, 0.25, 0.8)                  # about half of the coordinates fail -> most points are filtered
+    x[:, :2] = np.where(maxi[:2], 0.25 + 0.7 * x[:, :2], 0.8 * x[:, :2])    # keep a few thousand points alive
+    x[::2, 2:] = np.where(maxi[2:], 0.3 + 0.6 * x[::2, 2:], 0.7 * x[::2, 2:])
+    x[5] = ref                                       # exactly on the reference point: dropped (not > 0)
+    out = {}
+    for mode in ("host", "device"):
+        monkeypatch.setenv("HVB200_TRANSFORM", mode)
+        with mb.Plan(x, ref, maxi, kernel="exact", allow_extension=True) as plan:
+            out[mode] = (plan.npoints, plan.sample_values("DZ2019-MC", 4000, 7, 0, 4000))
+    want = hvcases.transformed(x, ref, maxi).shape[0]
+    assert out["host"][0] == out["device"][0] == want and 0 < want < n
+    assert np.array_equal(out["host"][1], out["device"][1])
+    # nothing survives: the entry point returns 0 like the reference (c/hvapprox.c:228-229)
+    monkeypatch.setenv("HVB200_TRANSFORM", "device")
+    if d <= 31:
+        assert mb.hv_approx(x, ref=np.where(maxi, 2.0, -1.0), maximise=maxi, nsamples=1000, method="DZ2019-MC", seed=1) == 0.0
+    with mb.Plan(x, np.where(maxi, 2.0, -1.0), maxi, allow_extension=True) as plan:
+        assert plan.empty and plan.npoints == 0
