@@ -1810,6 +1810,9 @@ static int bp_prepare(DevPlan *dp)
     const size_t n = dp->n;
     const int d = dp->d, W = (d + 1) / 2;
     cudaStream_t us = dp->own_stream;
+    const bool dbg = getenv("HVB200_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     unsigned nprobe = 4096;
     while (nprobe > 256 && (double)nprobe * (double)n > 6e8) nprobe /= 2;
     if (dp->wins_cap < 2 * n) {
@@ -1826,6 +1829,7 @@ static int bp_prepare(DevPlan *dp)
     CUDA_TRY(cudaMemcpyAsync(wins.data(), dp->wins, n * sizeof(unsigned), cudaMemcpyDeviceToHost, us));
     CUDA_TRY(cudaMemcpyAsync(pts.data(), dp->pts, n * (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, us));
     CUDA_TRY(cudaStreamSynchronize(us));
+    if (dbg) fprintf(stderr, "bp_prepare: probe+d2h %.2f ms\n", now() - t0);
     // key map of the point set (the same monotone map as the DPX screen, any d <= 64)
     std::vector<double> qlo(d, INFINITY), qhi(d, -INFINITY), qscale(d, 0.0);
     for (size_t i = 0; i < n; i++)
@@ -1847,7 +1851,9 @@ static int bp_prepare(DevPlan *dp)
         for (int k = 0; k < d; k++) norm[i * d + k] = qhi[k] > 0 ? pts[i * d + k] / qhi[k] : 0.0;
     std::vector<unsigned> idx(n);
     for (size_t i = 0; i < n; i++) idx[i] = (unsigned)i;
+    if (dbg) fprintf(stderr, "bp_prepare: ranges+norm %.2f ms\n", now() - t0);
     bp_kd_order(norm, d, idx, 0, n);
+    if (dbg) fprintf(stderr, "bp_prepare: kd %.2f ms\n", now() - t0);
     std::vector<unsigned> pos(n);
     for (size_t i = 0; i < n; i++) pos[idx[i]] = (unsigned)i;
     // pivots: the points that won most probes
@@ -1869,6 +1875,7 @@ static int bp_prepare(DevPlan *dp)
     const size_t n_pad = (size_t)nb_pad * kBpBlock;
     std::vector<double> sorted(n_pad * (size_t)d, 0.0);
     for (size_t i = 0; i < n; i++) memcpy(&sorted[i * d], &pts[(size_t)idx[i] * d], d * sizeof(double));
+    if (dbg) fprintf(stderr, "bp_prepare: pivots+sorted %.2f ms\n", now() - t0);
     // point keys KP = clamp(ceil f_k(p), 0, S); padding points -1, dummy objective of an odd d = S (always passes)
     std::vector<unsigned short> key(n_pad * (size_t)(2 * W));
     for (size_t i = 0; i < n_pad; i++)
@@ -1904,6 +1911,7 @@ static int bp_prepare(DevPlan *dp)
             }
             bpair[(size_t)pr * d + k] = word;
         }
+    if (dbg) fprintf(stderr, "bp_prepare: keys %.2f ms\n", now() - t0);
     if (dp->bp_pts_cap < n_pad * (size_t)d) {
         cudaFree(dp->bp_pts);
         dp->bp_pts = nullptr; dp->bp_pts_cap = 0;
@@ -1932,6 +1940,7 @@ static int bp_prepare(DevPlan *dp)
     CUDA_TRY(cudaMemcpyAsync(dp->bp_pkeys, pkeys.data(), pkeys.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
     CUDA_TRY(cudaMemcpyAsync(dp->bp_bpair, bpair.data(), bpair.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
     CUDA_TRY(cudaStreamSynchronize(us));              // host vectors go out of scope
+    if (dbg) fprintf(stderr, "bp_prepare: uploads %.2f ms\n", now() - t0);
     dp->bp_nb = nb;
     dp->bp_nb_pad = nb_pad;
     dp->bp_npiv = (int)npiv;
