@@ -122,6 +122,15 @@ MOOCORE_API int hvb200_mtjump_poly(uint64_t J, uint32_t poly_out[624]);
 MOOCORE_API int hvb200_mtjump_double(const uint32_t poly_in[624], uint32_t poly_out[624]);
 MOOCORE_API int hvb200_mtjump_apply_host(const uint32_t state_in[624], const uint32_t poly[624], uint32_t state_out[624]);
 
+/* Batched point sets: the estimates of `nsets` sets that share ref, maximise and ONE direction set.  Set i holds
+ * the rows [cumsizes[i-1], cumsizes[i]) of `data` — the layout and the loop of c/main-hvapprox.c:149-174, which a
+ * caller replaces by this one call.  volumes_out[i] = 0.0 when no point of set i strictly dominates ref, NaN on
+ * failure (return value != 0).  Every volume equals the single-set entry point's up to the summation order
+ * (<= 1e-14 relative). */
+MOOCORE_API int hvb200_hv_approx_sets(int method, const double *data, const size_t *cumsizes, size_t nsets,
+                                      dimension_t nobjs, const double *ref, const boolvec *maximise,
+                                      uint_fast32_t nsamples, uint32_t seed, int device, double *volumes_out);
+
 /* Single-process multi-GPU: evaluate one estimate sharded over `ndevices` GPUs
  * (devices 0..ndevices-1, contiguous index ranges, partial sums combined with one NCCL
  * all-gather when libnccl can be loaded, else by per-device copies). */

@@ -10,6 +10,7 @@ from ._api import (  # noqa: F401
     HVAPPROX_DIMENSION_MAX,
     hv_approx,
     hv_approx_range,
+    hv_approx_sets,
     hv_approx_shard,
     hv_approx_finalize,
     Plan,
@@ -22,6 +23,7 @@ from ._api import (  # noqa: F401
 __all__ = [
     "hv_approx",
     "hv_approx_range",
+    "hv_approx_sets",
     "hv_approx_shard",
     "hv_approx_finalize",
     "Plan",

@@ -84,6 +84,9 @@ def _load() -> ctypes.CDLL:
     L.hvb200_plan_set_kernel.argtypes = [vp, ctypes.c_int]
     L.hvb200_plan_run.restype = ctypes.c_int
     L.hvb200_plan_run.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, vp, _c_double_p]
+    L.hvb200_hv_approx_sets.restype = ctypes.c_int
+    L.hvb200_hv_approx_sets.argtypes = [ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.c_uint8,
+                                        _c_double_p, _c_u8_p, u64, u32, ctypes.c_int, _c_double_p]
     L.hvb200_plan_run_blocks.restype = ctypes.c_int
     L.hvb200_plan_run_blocks.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, u64, vp, _c_double_p]
     L.hvb200_plan_last_stats.restype = ctypes.c_int
@@ -221,6 +224,50 @@ def hv_approx(
     if hv != hv:
         raise RuntimeError(f"moocore_b200: CUDA hv_approx failed: {_last_error()}")
     return float(hv)
+
+
+def hv_approx_sets(
+    sets,
+    /,
+    ref,
+    *,
+    maximise: bool | Sequence[bool] = False,
+    nsamples: int = 262_144,
+    seed: int | np.random.Generator | None = None,
+    method: Literal["DZ2019-HW", "DZ2019-MC", "Rphi-FWE+"] = "Rphi-FWE+",
+    device: int = 0,
+) -> np.ndarray:
+    """``hv_approx`` of many point sets that share ``ref``, ``maximise`` and ONE direction set, in one call.
+
+    ``sets`` is a sequence of (n_i, m) arrays (or a ``(data, cumsizes)`` pair in the layout of the reference's
+    command line tool, c/main-hvapprox.c:149-174).  Returns one estimate per set, each equal to
+    ``hv_approx(set_i, ...)`` up to the summation order; 0.0 for sets without a point that strictly dominates
+    ``ref``.  The directions are generated once and small sets share one kernel launch."""
+    if method not in METHOD_IDS:
+        raise ValueError(f"Unknown method = {method}")
+    if isinstance(sets, tuple) and len(sets) == 2 and np.ndim(sets[1]) == 1 and np.ndim(sets[0]) == 2:
+        data = np.ascontiguousarray(sets[0], dtype=float)
+        cum = np.ascontiguousarray(sets[1], dtype=np.uint64)
+    else:
+        arrs = [np.ascontiguousarray(a, dtype=float) for a in sets]
+        if not arrs:
+            return np.zeros(0)
+        if any(a.ndim != 2 or a.shape[1] != arrs[0].shape[1] for a in arrs):
+            raise ValueError("all sets must be 2-D arrays with the same number of columns")
+        data = np.ascontiguousarray(np.concatenate(arrs, axis=0))
+        cum = np.cumsum([a.shape[0] for a in arrs]).astype(np.uint64)
+    probe = data if data.shape[0] else np.zeros((1, data.shape[1]))
+    _, ref, maxi, nsamples, nobj = _prepare(probe, ref, maximise, nsamples)
+    if nobj < 2:
+        raise ValueError("hv_approx_sets needs at least 2 objectives")
+    out = np.zeros(cum.size)
+    L = _load()
+    rc = L.hvb200_hv_approx_sets(METHOD_IDS[method], _dp(data), cum.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t)), cum.size,
+                                 nobj, _dp(ref), maxi.ctypes.data_as(_c_u8_p), nsamples,
+                                 _get_seed_for_c(seed) if method == "DZ2019-MC" else 0, device, _dp(out))
+    if rc != 0:
+        raise RuntimeError(f"moocore_b200: hv_approx_sets failed ({rc}): {_last_error()}")
+    return out
 
 
 class Plan:

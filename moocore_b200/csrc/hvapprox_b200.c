@@ -353,8 +353,16 @@ int hvb200_rphi_sequence(dimension_t nobjs, uint64_t i0, uint64_t count, double 
 /* ------------------------------------------------------------------------------------------ */
 /* run                                                                                         */
 /* ------------------------------------------------------------------------------------------ */
+static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t seed, uint64_t i0, uint64_t i1,
+                        void *stream, double out_hilo[2], double *values_out, double *dirs_out, void *sets_ctx);
 static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t seed, uint64_t i0, uint64_t i1,
                      void *stream, double out_hilo[2], double *values_out, double *dirs_out)
+{
+    return run_range_ex(plan, method, nsamples, seed, i0, i1, stream, out_hilo, values_out, dirs_out, NULL);
+}
+/* sets_ctx != NULL: the batch of directions is handed to the batched-sets kernel instead of the plan's own */
+static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t seed, uint64_t i0, uint64_t i1,
+                        void *stream, double out_hilo[2], double *values_out, double *dirs_out, void *sets_ctx)
 {
     const int d = plan->d;
     tls_error[0] = 0;
@@ -427,8 +435,11 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
             if (hvb200cu_gen_rphi(plan, uu, cnt)) return -1;
         }
         if (dirs_out && hvb200cu_read_dirs(plan, cnt, dirs_out + (b0 - i0) * (size_t)d)) return -1;
-        if (!dirs_out || values_out || out_hilo)
+        if (sets_ctx) {
+            if (hvb200cu_sets_maxmin(plan, sets_ctx, cnt)) return -1;
+        } else if (!dirs_out || values_out || out_hilo) {
             if (plan->n && hvb200cu_maxmin(plan, cnt, values_out ? values_out + (b0 - i0) : NULL)) return -1;
+        }
     }
     if (hvb200cu_run_end(plan, out_hilo)) return -1;
     plan->stats.samples = i1 - i0;
@@ -535,6 +546,87 @@ double hvb200_finalize(dimension_t nobjs, uint_fast32_t nsamples, const double *
     for (int i = 0; i < npairs; i++) sum += (long double)hilo_pairs[2 * i] + (long double)hilo_pairs[2 * i + 1];
     const long double c_d = hvb200_cd[(int)nobjs];
     return (double)(c_d * (sum / (long double)nsamples));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* batched point sets                                                      */
+/* ------------------------------------------------------------------------------------------ */
+/* The estimates of `nsets` point sets that share ref, maximise and the direction set: set i holds the rows
+   [cumsizes[i-1], cumsizes[i]) of `data` (cumsizes[-1] = 0), the layout and the loop of the reference's command
+   line tool (c/main-hvapprox.c:149-174).  Directions are generated once; sets that fit a CTA's shared memory
+   share one kernel launch per batch of directions, larger ones go through the single-set path.
+   volumes_out[i] = 0.0 when no point of set i strictly dominates ref (c/hvapprox.c:228-229), NaN on failure. */
+int hvb200_hv_approx_sets(int method, const double *data, const size_t *cumsizes, size_t nsets, dimension_t nobjs,
+                          const double *ref, const boolvec *maximise, uint_fast32_t nsamples_, uint32_t seed,
+                          int device, double *volumes_out)
+{
+    tls_error[0] = 0;
+    const int d = (int)nobjs;
+    const uint64_t nsamples = (uint64_t)nsamples_;
+    for (size_t i = 0; i < nsets; i++) volumes_out[i] = NAN;
+    if (d < 2 || d > HVB200_DIMENSION_MAX) { hvb200_set_error("nobjs = %d outside [2, %d]", d, HVB200_DIMENSION_MAX); return -2; }
+    if (nsamples == 0) { hvb200_set_error("nsamples must be positive"); return -2; }
+    if (nsets == 0) return 0;
+    if (nsets > 65535) { hvb200_set_error("at most 65535 sets per call"); return -2; }
+    const size_t total_rows = cumsizes[nsets - 1];
+    double *pts = malloc((total_rows ? total_rows : 1) * (size_t)d * sizeof *pts);
+    unsigned *off = malloc((nsets + 1) * sizeof *off);
+    int *batched = malloc(nsets * sizeof *batched);
+    if (!pts || !off || !batched) { free(pts); free(off); free(batched); hvb200_set_error("out of host memory"); return -4; }
+    const size_t fit = hvb200cu_sets_max_points(d);
+    size_t kept_total = 0, first_batched = nsets;
+    int rc = 0;
+    off[0] = 0;
+    for (size_t i = 0; i < nsets; i++) {
+        const size_t r0 = i ? cumsizes[i - 1] : 0, r1 = cumsizes[i];
+        if (r1 < r0 || r1 > total_rows) { hvb200_set_error("cumsizes must be non-decreasing"); rc = -2; break; }
+        size_t kept = transform_and_filter(data + r0 * (size_t)d, r1 - r0, d, ref, maximise, pts + kept_total * (size_t)d);
+        batched[i] = kept > 0 && kept <= fit;
+        if (kept == 0) volumes_out[i] = 0.0;
+        if (!batched[i]) kept = 0;                       /* large sets: single-set path below */
+        else if (first_batched == nsets) first_batched = i;
+        kept_total += kept;
+        off[i + 1] = (unsigned)kept_total;
+    }
+    if (rc == 0 && first_batched < nsets) {
+        /* a plan on the first batched set owns the stream, the direction buffers and the generator state */
+        hvb200_plan *plan = calloc(1, sizeof *plan);
+        void *ctx = NULL;
+        double *hilo = malloc(nsets * 2 * sizeof *hilo);
+        if (!plan || !hilo) { hvb200_set_error("out of host memory"); rc = -4; }
+        if (rc == 0) {
+            plan->device = device;
+            plan->d = d;
+            plan->kernel = HVB200_KERNEL_EXACT;
+            plan->n = off[first_batched + 1] - off[first_batched];
+            if (device < 0 || device >= hvb200cu_device_count()) {
+                hvb200_set_error("CUDA device %d not available (%d visible); this library has no CPU fallback", device, hvb200cu_device_count());
+                rc = -3;
+            } else if (hvb200cu_plan_upload(plan, pts + (size_t)off[first_batched] * d)) rc = -1;
+        }
+        if (rc == 0 && hvb200cu_sets_begin(plan, pts, off, (int)nsets, &ctx)) rc = -1;
+        if (rc == 0 && run_range_ex(plan, method, nsamples, seed, 0, nsamples, NULL, NULL, NULL, NULL, ctx)) rc = -1;
+        if (ctx && hvb200cu_sets_end(plan, ctx, rc == 0 ? hilo : NULL)) rc = -1;
+        if (rc == 0)
+            for (size_t i = 0; i < nsets; i++)
+                if (batched[i]) volumes_out[i] = hvb200_finalize(nobjs, nsamples_, hilo + 2 * i, 1);
+        if (plan && plan->dev) hvb200cu_plan_free(plan);
+        free(plan);
+        free(hilo);
+    }
+    /* sets too large for the batched kernel */
+    for (size_t i = 0; rc == 0 && i < nsets; i++) {
+        if (batched[i] || volumes_out[i] == 0.0) continue;
+        const size_t r0 = i ? cumsizes[i - 1] : 0, r1 = cumsizes[i];
+        hvb200_plan *plan = NULL;
+        double hl[2];
+        if (hvb200_plan_create(&plan, data + r0 * (size_t)d, r1 - r0, nobjs, ref, maximise, device) || !plan) { rc = -1; break; }
+        if (run_range(plan, method, nsamples, seed, 0, nsamples, NULL, hl, NULL, NULL)) rc = -1;
+        else volumes_out[i] = hvb200_finalize(nobjs, nsamples_, hl, 1);
+        hvb200_plan_destroy(plan);
+    }
+    free(pts); free(off); free(batched);
+    return rc;
 }
 
 /* ------------------------------------------------------------------------------------------ */

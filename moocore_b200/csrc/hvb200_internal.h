@@ -65,6 +65,11 @@ int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double *values_hos
 /* copy the generated reciprocal directions of the current batch to the host (count x d) */
 int hvb200cu_read_dirs(struct hvb200_plan *plan, uint64_t count, double *r_host);
 int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2]);
+/* batched point sets against one direction set */
+size_t hvb200cu_sets_max_points(int d);
+int hvb200cu_sets_begin(struct hvb200_plan *plan, const double *pts_host, const unsigned *off_host, int nsets, void **ctx_out);
+int hvb200cu_sets_maxmin(struct hvb200_plan *plan, void *ctx, uint64_t count);
+int hvb200cu_sets_end(struct hvb200_plan *plan, void *ctx, double *hilo_host);
 
 /* pinned staging buffer for host-produced streams (MC normals, Rphi u); grows on demand */
 double *hvb200cu_staging(struct hvb200_plan *plan, size_t ndoubles);

@@ -138,6 +138,20 @@ __device__ __forceinline__ double pow_chain(double x)
     }
 }
 
+// runtime exponent (1..31) through the same tabulated multiplication programs
+__device__ __forceinline__ double pow_chain_runtime(double x, int e)
+{
+    switch (e) {
+#define HVB200_PC(E) case E: return pow_chain<E>(x);
+        HVB200_PC(1) HVB200_PC(2) HVB200_PC(3) HVB200_PC(4) HVB200_PC(5) HVB200_PC(6) HVB200_PC(7) HVB200_PC(8)
+        HVB200_PC(9) HVB200_PC(10) HVB200_PC(11) HVB200_PC(12) HVB200_PC(13) HVB200_PC(14) HVB200_PC(15) HVB200_PC(16)
+        HVB200_PC(17) HVB200_PC(18) HVB200_PC(19) HVB200_PC(20) HVB200_PC(21) HVB200_PC(22) HVB200_PC(23) HVB200_PC(24)
+        HVB200_PC(25) HVB200_PC(26) HVB200_PC(27) HVB200_PC(28) HVB200_PC(29) HVB200_PC(30) HVB200_PC(31)
+#undef HVB200_PC
+    }
+    return 1.0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: SYNCS.*, UBLKCP)
 // ------------------------------------------------------------------------------------------------
@@ -1273,6 +1287,97 @@ __global__ void __launch_bounds__(256) k_colrange(const double *__restrict__ pts
     }
     __syncthreads();
     for (int k = threadIdx.x; k < d; k += blockDim.x) { atomicMin(&lo[k], slo[k]); atomicMax(&hi[k], shi[k]); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched point sets: many small sets against ONE direction set — the loop of the
+// reference's command line tool (c/main-hvapprox.c:149-174) and of optimisers that score a population of
+// fronts per generation.  CTA (x, set) keeps its set in shared memory and evaluates the direction chunks
+// x, x + gridDim.x, ... with the textbook arithmetic (get_expected_value, c/hvapprox.c:68-117); the chunk
+// -> CTA map is static and every CTA owns one slot of `partial`, so the sums are deterministic.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kSetsThreads = 256, kSetsR = 2;
+template <int D>
+__global__ void __launch_bounds__(kSetsThreads) k_maxmin_sets(const double *__restrict__ pts_all, const unsigned *__restrict__ set_off,
+                                                              const double *__restrict__ dirs, ull count, int d_runtime,
+                                                              double *__restrict__ partial)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sp = reinterpret_cast<double *>(smem_raw);
+    __shared__ double red[kSetsThreads / 32];
+    const int d = D ? D : d_runtime;
+    const int set = blockIdx.y;
+    const unsigned p0 = set_off[set], n = set_off[set + 1] - p0;
+    for (unsigned i = threadIdx.x; i < n * (unsigned)d; i += kSetsThreads) sp[i] = pts_all[(size_t)p0 * d + i];
+    __syncthreads();
+    constexpr ull CH = (ull)kSetsThreads * kSetsR;
+    const ull n_chunks = (count + CH - 1) / CH;
+    double acc = 0.0;
+    for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+#pragma unroll
+        for (int r = 0; r < kSetsR; r++) {
+            const ull smp = chunk * CH + (ull)r * kSetsThreads + threadIdx.x;
+            if (smp >= count || n == 0) continue;
+            const double *dir = dirs + smp * (ull)(2 * d);
+            double best = 0.0;
+            if constexpr (D > 0) {
+                double rr[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) rr[k] = __ldg(dir + k);
+                for (unsigned i = 0; i < n; i++) {
+                    const double *pp = sp + (size_t)i * D;
+                    double m = pp[0] * rr[0];
+#pragma unroll
+                    for (int k = 1; k < D; k++) {
+                        const double t = pp[k] * rr[k];
+                        m = (t < m) ? t : m;
+                    }
+                    best = (m > best) ? m : best;
+                }
+                acc += pow_chain<D>(best);
+            } else {
+                for (unsigned i = 0; i < n; i++) {
+                    const double *pp = sp + (size_t)i * d;
+                    double m = pp[0] * __ldg(dir);
+                    for (int k = 1; k < d; k++) {
+                        const double t = pp[k] * __ldg(dir + k);
+                        m = (t < m) ? t : m;
+                    }
+                    best = (m > best) ? m : best;
+                }
+                // pow_uint (c/pow_int.h:59-74): tabulated chains up to 31, square-and-multiply above
+                double x = best, v = (d & 1) ? best : 1.0;
+                if (d <= 31) v = pow_chain_runtime(best, d);
+                else for (unsigned e = (unsigned)d >> 1; e; e >>= 1) { x *= x; if (e & 1u) v *= x; }
+                acc += v;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        partial[(size_t)set * gridDim.x + blockIdx.x] += ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+}
+// one CTA per set: fixed-shape double-double tree over the set's CTA partials
+__global__ void __launch_bounds__(256) k_reduce_sets(const double *__restrict__ partial, int per_set, double *__restrict__ out_hilo)
+{
+    __shared__ double sh[256], sl[256];
+    const int tid = threadIdx.x, set = blockIdx.x;
+    double hi = 0.0, lo = 0.0;
+    for (int i = tid; i < per_set; i += 256) dd_add(hi, lo, partial[(size_t)set * per_set + i], 0.0);
+    sh[tid] = hi; sl[tid] = lo;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) {
+            double h = sh[tid], l = sl[tid];
+            dd_add(h, l, sh[tid + off], sl[tid + off]);
+            sh[tid] = h; sl[tid] = l;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { out_hilo[2 * set] = sh[0]; out_hilo[2 * set + 1] = sl[0]; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2415,6 +2520,85 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
         CUDA_TRY(cudaStreamSynchronize(dp->stream));
     }
     return 0;
+}
+
+// ---- batched point sets ------------------------------------------------------------------------
+struct SetsCtx {
+    double *pts = nullptr;
+    unsigned *off = nullptr;
+    double *partial = nullptr, *hilo = nullptr;
+    int nsets = 0, grid_x = 0, d = 0;
+    size_t smem = 0;
+};
+typedef void (*sets_fn)(const double *, const unsigned *, const double *, ull, int, double *);
+template <int D>
+static sets_fn pick_sets(int d)
+{
+    if constexpr (D < 2) {
+        return (sets_fn)k_maxmin_sets<0>;
+    } else {
+        if (d == D) return (sets_fn)k_maxmin_sets<D>;
+        return pick_sets<D - 1>(d);
+    }
+}
+extern "C" size_t hvb200cu_sets_max_points(int d)
+{
+    return (size_t)(200 * 1024) / ((size_t)d * sizeof(double));     // one set must fit the shared memory of a CTA
+}
+extern "C" int hvb200cu_sets_begin(struct hvb200_plan *plan, const double *pts_host, const unsigned *off_host, int nsets, void **ctx_out)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    CUDA_TRY(cudaSetDevice(dp->device));
+    SetsCtx *c = new SetsCtx();
+    *ctx_out = c;
+    c->nsets = nsets;
+    c->d = dp->d;
+    const size_t total = off_host[nsets];
+    unsigned nmax = 0;
+    for (int i = 0; i < nsets; i++) nmax = std::max(nmax, off_host[i + 1] - off_host[i]);
+    c->smem = (size_t)nmax * dp->d * sizeof(double) + 16;
+    // about 4 CTAs per SM over all sets, at least one per set
+    c->grid_x = std::max(1, (dp->sm_count * 4 + nsets - 1) / nsets);
+    CUDA_TRY(cudaMalloc(&c->pts, std::max<size_t>(1, total) * dp->d * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->off, (size_t)(nsets + 1) * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&c->partial, (size_t)nsets * c->grid_x * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->hilo, (size_t)nsets * 2 * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(c->pts, pts_host, total * dp->d * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->off, off_host, (size_t)(nsets + 1) * sizeof(unsigned), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(c->partial, 0, (size_t)nsets * c->grid_x * sizeof(double)));
+    sets_fn fn = pick_sets<16>(dp->d);
+    CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    return 0;
+}
+extern "C" int hvb200cu_sets_maxmin(struct hvb200_plan *plan, void *ctx, uint64_t count)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    SetsCtx *c = (SetsCtx *)ctx;
+    sets_fn fn = pick_sets<16>(dp->d);
+    const int b = span_begin(dp, 0);
+    // always grid_x CTAs per set (idle ones add 0): the partial slots keep one stride over all launches of a run
+    fn<<<dim3((unsigned)c->grid_x, (unsigned)c->nsets), kSetsThreads, c->smem, dp->stream>>>(c->pts, c->off, dp->dirs, (ull)count, dp->d, c->partial);
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.maxmin_launches++;
+    return 0;
+}
+extern "C" int hvb200cu_sets_end(struct hvb200_plan *plan, void *ctx, double *hilo_host)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    SetsCtx *c = (SetsCtx *)ctx;
+    int rc = 0;
+    if (hilo_host) {
+        k_reduce_sets<<<c->nsets, 256, 0, dp->stream>>>(c->partial, c->grid_x, c->hilo);
+        if (cudaMemcpyAsync(hilo_host, c->hilo, (size_t)c->nsets * 2 * sizeof(double), cudaMemcpyDeviceToHost, dp->stream) != cudaSuccess ||
+            cudaStreamSynchronize(dp->stream) != cudaSuccess) {
+            hvb200_set_error("batched sets: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = -1;
+        }
+    }
+    cudaFree(c->pts); cudaFree(c->off); cudaFree(c->partial); cudaFree(c->hilo);
+    delete c;
+    return rc;
 }
 
 extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])

@@ -1,0 +1,65 @@
+"""hvb200_hv_approx_sets: many point sets against one direction set (the loop of c/main-hvapprox.c:149-174)
+must return, per set, what the single-set entry points return."""
+import time
+
+import numpy as np
+import pytest
+
+import hvcases
+
+pytestmark = pytest.mark.gpu
+METHODS = ["DZ2019-HW", "DZ2019-MC", "Rphi-FWE+"]
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_sets_match_single_calls(mb, method):
+    rng = np.random.default_rng(5)
+    d = 4
+    sets = [hvcases.front("sphere", int(n), d, 100 + i) for i, n in enumerate(rng.integers(1, 400, 25))]
+    sets.append(np.full((3, d), 2.0))                     # nothing dominates ref -> 0.0
+    sets.append(hvcases.front("simplex", 1, d, 7))        # a single point
+    sets.append(np.zeros((0, d)))                         # an empty set
+    got = mb.hv_approx_sets(sets, 1.1, nsamples=20000, seed=42, method=method)
+    assert got.shape == (len(sets),)
+    for s, g in zip(sets, got):
+        want = mb.hv_approx(s, ref=1.1, nsamples=20000, seed=42, method=method) if s.shape[0] else 0.0
+        assert g == pytest.approx(want, rel=1e-13, abs=0.0)
+    assert got[-3] == 0.0 and got[-1] == 0.0 and got[-2] > 0
+
+
+def test_sets_mixed_sizes_and_maximise(mb):
+    # one set too large for the batched kernel (shared memory) goes through the single-set path
+    d = 6
+    maxi = np.array([True, False, False, True, False, False])
+    rng = np.random.default_rng(9)
+    sets = [rng.random((n, d)) for n in (50, 9000, 700, 3)]
+    ref = np.where(maxi, -0.1, 1.1)
+    got = mb.hv_approx_sets(sets, ref, maximise=maxi, nsamples=30000, method="DZ2019-HW")
+    for s, g in zip(sets, got):
+        assert g == pytest.approx(mb.hv_approx(s, ref=ref, maximise=maxi, nsamples=30000, method="DZ2019-HW"), rel=1e-13)
+
+
+def test_sets_data_cumsizes_layout_and_high_d(mb):
+    d = 20
+    rng = np.random.default_rng(3)
+    sizes = [10, 0, 120, 33]
+    data = rng.random((sum(sizes), d))
+    got = mb.hv_approx_sets((data, np.cumsum(sizes)), 1.05, nsamples=5000, seed=3, method="DZ2019-MC")
+    lo = 0
+    for n, g in zip(sizes, got):
+        want = mb.hv_approx(data[lo:lo + n], ref=1.05, nsamples=5000, seed=3, method="DZ2019-MC") if n else 0.0
+        assert g == pytest.approx(want, rel=1e-13, abs=0.0)
+        lo += n
+
+
+def test_sets_amortise_the_per_call_cost(mb):
+    sets = [hvcases.front("sphere", 100, 3, i) for i in range(200)]
+    mb.hv_approx_sets(sets[:2], 1.1, nsamples=100_000, method="DZ2019-HW")       # warm-up
+    t0 = time.perf_counter()
+    a = mb.hv_approx_sets(sets, 1.1, nsamples=100_000, method="DZ2019-HW")
+    t1 = time.perf_counter()
+    b = [mb.hv_approx(s, ref=1.1, nsamples=100_000, method="DZ2019-HW") for s in sets]
+    t2 = time.perf_counter()
+    assert np.allclose(a, b, rtol=1e-13, atol=0)
+    print("batched %.2f ms, looped %.2f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1)))
+    assert t1 - t0 < t2 - t1
