@@ -1907,7 +1907,7 @@ static void bp_kd_order(const std::vector<double> &norm, int d, std::vector<unsi
 static int bp_pivot_count()
 {
     const char *e = getenv("HVB200_BP_PIVOTS");
-    const int v = e ? atoi(e) : 256;
+    const int v = e ? atoi(e) : 320;
     return v < 1 ? 1 : (v > kBpMaxPivots ? kBpMaxPivots : v);
 }
 static int bp_prepare(DevPlan *dp)
@@ -1995,12 +1995,12 @@ static int bp_prepare(DevPlan *dp)
             }
             key[i * (2 * W) + k] = v;
         }
-    std::vector<unsigned> pkeys((size_t)nb_pad * W * 32);
+    std::vector<unsigned> pkeys((size_t)nb_pad * W * kBpBlock);
     for (int b = 0; b < nb_pad; b++)
         for (int j = 0; j < W; j++)
-            for (int l = 0; l < 32; l++) {
-                const size_t i = (size_t)b * 32 + l;
-                pkeys[((size_t)b * W + j) * 32 + l] = (unsigned)key[i * (2 * W) + 2 * j] | ((unsigned)key[i * (2 * W) + 2 * j + 1] << 16);
+            for (int l = 0; l < kBpBlock; l++) {
+                const size_t i = (size_t)b * kBpBlock + l;
+                pkeys[((size_t)b * W + j) * kBpBlock + l] = (unsigned)key[i * (2 * W) + 2 * j] | ((unsigned)key[i * (2 * W) + 2 * j + 1] << 16);
             }
     // block bounds: per-objective maximum key (signed: padding -1 never raises it), two blocks per word
     std::vector<unsigned> bpair((size_t)(nb_pad / 2) * d);
@@ -2011,7 +2011,7 @@ static int bp_prepare(DevPlan *dp)
                 const int b = 2 * pr + h;
                 int m = -1;
                 if (b < nb)
-                    for (int l = 0; l < 32; l++) m = std::max(m, (int)(short)key[((size_t)b * 32 + l) * (2 * W) + k]);
+                    for (int l = 0; l < kBpBlock; l++) m = std::max(m, (int)(short)key[((size_t)b * kBpBlock + l) * (2 * W) + k]);
                 word |= ((unsigned)m & 0xffffu) << (16 * h);
             }
             bpair[(size_t)pr * d + k] = word;
@@ -2152,7 +2152,7 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
         else if (d > 32) mode = MODE_BP;
         else if (dp->n >= 512 && (dp->bp_ready || plan->run_samples >= (uint64_t)65536 * (uint64_t)d)) mode = MODE_BP;
     }
-    if (mode == MODE_BP && dp->n + 256 >= ((size_t)1 << kBpPtBits)) mode = MODE_DPX;   // candidate entries hold 23-bit point indices
+    if (mode == MODE_BP && dp->n / 32 + 64 >= ((size_t)1 << kBpPtBits)) mode = MODE_DPX;   // hit entries hold 23-bit granule (32-point) indices
     if (d > 32 && mode != MODE_BP) mode = MODE_EXACT;
     dp->kernel_used = mode;
     if ((mode == MODE_DPX || mode == MODE_SCREEN) && !dp->ordered && dp->n >= 1024 && plan->run_samples >= (1u << 20) &&
