@@ -319,6 +319,9 @@ def run_ours(args, rank, local_rank, world):
                 traffic = per_dir * shard_samples / max(1, mm_launches // max(1, args.steps))
                 roofline["traffic"] = traffic
                 roofline["traffic_source"] = tj["source"]
+                if "pipe_utilisation" in tj and plan.stats()["kernel"] == 4:
+                    # what actually bounds the pruned kernel (ncu capture under profiles/, not measured in this run)
+                    roofline["pipe_utilisation_ncu"] = tj["pipe_utilisation"]
         except Exception:
             pass
         # CPU baseline: bounded sample of the same workload on 1 host core (N=1 runs only)
