@@ -1,7 +1,8 @@
 """Multi-GPU sharding of one hv_approx estimate.
 
-The N directions are independent, so rank g of G evaluates the contiguous index range
-[g*N/G, (g+1)*N/G) on its own GPU and produces one (hi, lo) FP64 pair; the only exchange step
+The N directions are independent, so rank g of G evaluates its share — block-cyclic blocks for DZ2019-HW
+(shard_blocks), the contiguous index range [g*N/G, (g+1)*N/G) for the sequential MC and Rphi streams
+(shard_range) — on its own GPU and produces one (hi, lo) FP64 pair; the only exchange step
 is an all-gather of those 16 bytes per rank (NCCL over NVLink when the process group is
 "nccl", gloo in the CPU tests), followed by a fixed-order long double sum and the c_d/N
 scaling of c/hvapprox.c:691-692.  An all-gather + ordered sum is used instead of an all-reduce
@@ -17,6 +18,20 @@ def shard_range(nsamples: int, rank: int, world: int) -> Tuple[int, int]:
     if not (0 <= rank < world):
         raise ValueError(f"rank {rank} outside [0, {world})")
     return (nsamples * rank) // world, (nsamples * (rank + 1)) // world
+
+
+SHARD_BLOCK = 1 << 21      # HVB200_SHARD_BLOCK of include/hvapprox_b200.h
+
+
+def shard_blocks(nsamples: int, rank: int, world: int, block: int = SHARD_BLOCK):
+    """Block-cyclic shard of `rank`: the index ranges [b*block, min((b+1)*block, nsamples)) for b = rank,
+    rank + world, ...  — what hvb200_plan_run_blocks evaluates for (first=rank, stride=world).  Used for
+    DZ2019-HW, whose per-direction cost drifts along the lattice index."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    if block <= 0:
+        raise ValueError("block must be positive")
+    return [(lo, min(lo + block, nsamples)) for lo in range(rank * block, nsamples, world * block)]
 
 
 def gather_partials(hilo: Sequence[float], group=None, device=None):

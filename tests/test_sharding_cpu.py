@@ -26,6 +26,17 @@ def test_shard_ranges_partition(N, world):
     assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("N,world,block", [(1, 1, 8), (100, 3, 7), (10_000_019, 8, 1 << 21), (4096, 4, 1024), (5, 8, 2)])
+def test_shard_blocks_partition(N, world, block):
+    from moocore_b200.sharding import shard_blocks
+    ranges = sorted(r for g in range(world) for r in shard_blocks(N, g, world, block))
+    assert ranges[0][0] == 0 and ranges[-1][1] == N
+    assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert all(0 < hi - lo <= block for lo, hi in ranges)
+    for g in range(world):
+        assert all((lo // block) % world == g for lo, hi in shard_blocks(N, g, world, block))
+
+
 def test_shard_range_rejects_bad_rank():
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
@@ -41,7 +52,7 @@ import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import hvcases, moocore_b200 as mb
-from moocore_b200.sharding import gather_partials, shard_range
+from moocore_b200.sharding import gather_partials, shard_blocks, shard_range
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 O = ctypes.CDLL(os.path.join(ROOT, "oracle", "libhvoracle.so"))
@@ -59,6 +70,11 @@ est = mb.hv_approx_finalize(d, N, flat)
 ref = np.full(d, 1.1); mx = np.zeros(d, np.uint8)
 full = O.orc_hv_approx_hua_wang(x.ctypes.data_as(dp), ctypes.c_size_t(64), ctypes.c_uint8(d), ref.ctypes.data_as(dp), mx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.c_uint64(N))
 assert abs(est - full) / full < 1e-13, (est, full)
+# block-cyclic shards (DZ2019-HW on the GPU path): same estimate
+part = sum(O.orc_hw_window(tp.ctypes.data_as(dp), ctypes.c_size_t(64), d, ctypes.c_uint64(N), ctypes.c_uint64(a), ctypes.c_uint64(b - a), None)
+           for a, b in shard_blocks(N, rank, world, block=4096))
+est2 = mb.hv_approx_finalize(d, N, gather_partials((part, 0.0)))
+assert abs(est2 - full) / full < 1e-13, (est2, full)
 ests = [None] * world
 dist.all_gather_object(ests, est)
 assert all(e == ests[0] for e in ests)          # every rank finalises to the same bits
