@@ -17,6 +17,7 @@ from ._api import (  # noqa: F401
     lib,
     library_path,
     device_count,
+    directions,
     measure_fp64,
 )
 
@@ -31,6 +32,7 @@ __all__ = [
     "lib",
     "library_path",
     "device_count",
+    "directions",
     "measure_fp64",
 ]
 __version__ = "0.1.0"

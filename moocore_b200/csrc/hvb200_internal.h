@@ -65,6 +65,12 @@ int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double *values_hos
 /* copy the generated reciprocal directions of the current batch to the host (count x d) */
 int hvb200cu_read_dirs(struct hvb200_plan *plan, uint64_t count, double *r_host);
 int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2]);
+/* cached direction sets */
+int hvb200cu_dev_alloc(int device, size_t bytes, void **out);
+void hvb200cu_dev_free(int device, void *p);
+int hvb200cu_copy_dirs_out(struct hvb200_plan *plan, double *dst, uint64_t count, int wait);
+int hvb200cu_copy_dev(struct hvb200_plan *plan, double *dst, const double *src, size_t doubles);
+void hvb200cu_set_dirs_view(struct hvb200_plan *plan, const double *view);
 /* batched point sets against one direction set */
 size_t hvb200cu_sets_max_points(int d);
 int hvb200cu_sets_begin(struct hvb200_plan *plan, const double *pts_host, const unsigned *off_host, int nsets, void **ctx_out);

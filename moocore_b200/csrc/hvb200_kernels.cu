@@ -1414,6 +1414,7 @@ struct DevPlan {
     int kR = 1, kG = 2;
     double qlo[32] = {0}, qhi[32] = {0}, qscale[32] = {0};
     double *dirs = nullptr;      size_t dirs_cap = 0;      // doubles (the workspace may serve plans of different d)
+    const double *dirs_view = nullptr;   // when set, the consumers read this (cached direction sets) instead of `dirs`
     // DZ2019-HW pipelining: the generator of batch b+1 runs on gen_stream into the other buffer while
     // the max-min kernel of batch b runs on the main stream (different pipes: FP64 vs ALU for the DPX screen)
     double *dirs_buf[2] = {nullptr, nullptr}; size_t dirs_buf_cap[2] = {0, 0};
@@ -2403,6 +2404,37 @@ extern "C" int hvb200cu_gen_rphi(struct hvb200_plan *plan, const double *u_host,
     plan->stats.dirgen_launches++;
     return 0;
 }
+// ---- cached direction sets (Rphi-FWE+ directions depend on d and the sample index only) ----------
+extern "C" int hvb200cu_dev_alloc(int device, size_t bytes, void **out)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(out, bytes));
+    return 0;
+}
+extern "C" void hvb200cu_dev_free(int device, void *p)
+{
+    if (cudaSetDevice(device) == cudaSuccess) cudaFree(p);
+    cudaGetLastError();
+}
+// rows [0, count) of the plan's direction buffer -> dst (device), then wait: dst is published to other streams
+extern "C" int hvb200cu_copy_dirs_out(struct hvb200_plan *plan, double *dst, uint64_t count, int wait)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    CUDA_TRY(cudaMemcpyAsync(dst, dp->dirs, count * (size_t)(2 * dp->d) * sizeof(double), cudaMemcpyDeviceToDevice, dp->stream));
+    if (wait) CUDA_TRY(cudaStreamSynchronize(dp->stream));
+    return 0;
+}
+extern "C" int hvb200cu_copy_dev(struct hvb200_plan *plan, double *dst, const double *src, size_t doubles)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, doubles * sizeof(double), cudaMemcpyDeviceToDevice, dp->stream));
+    CUDA_TRY(cudaStreamSynchronize(dp->stream));
+    return 0;
+}
+extern "C" void hvb200cu_set_dirs_view(struct hvb200_plan *plan, const double *view)
+{
+    ((DevPlan *)plan->dev)->dirs_view = view;
+}
 extern "C" int hvb200cu_gen_uploaded(struct hvb200_plan *plan, const double *r_host, uint64_t count)
 {
     DevPlan *dp = (DevPlan *)plan->dev;
@@ -2419,7 +2451,7 @@ extern "C" int hvb200cu_read_dirs(struct hvb200_plan *plan, uint64_t count, doub
     DevPlan *dp = (DevPlan *)plan->dev;
     double *tmp = nullptr;
     CUDA_TRY(cudaMalloc(&tmp, count * (size_t)dp->d * sizeof(double)));
-    k_extract_r<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->dirs, count, dp->d, tmp);
+    k_extract_r<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->dirs_view ? dp->dirs_view : dp->dirs, count, dp->d, tmp);
     cudaError_t e = cudaMemcpyAsync(r_host, tmp, count * (size_t)dp->d * sizeof(double), cudaMemcpyDeviceToHost, dp->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(dp->stream);
     cudaFree(tmp);
@@ -2443,7 +2475,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     a.tile_points = dp->tile_points;
     a.stage_bytes = dp->stage_bytes;
     a.staged = dp->staged;
-    a.dirs = dp->dirs;
+    a.dirs = dp->dirs_view ? dp->dirs_view : dp->dirs;
     a.count = count;
     a.cta_sums = dp->cta_sums;
     a.values = values_host ? dp->values : nullptr;
@@ -2466,7 +2498,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
         ka.nb = dp->bp_nb;
         ka.nb_pad = dp->bp_nb_pad;
         ka.seg_blocks = dp->bp_seg_blocks;
-        ka.dirs = dp->dirs;
+        ka.dirs = dp->dirs_view ? dp->dirs_view : dp->dirs;
         ka.count = count;
         if (dp->bp_chunk_off + n_chunks > dp->bp_chunk_cap) { hvb200_set_error("internal: chunk buffer too small"); return -1; }
         ka.chunk_sums = dp->bp_chunk_sums + dp->bp_chunk_off;
@@ -2491,7 +2523,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
         ka.npoints = dp->n;
         ka.n_pivots = (int)std::min<size_t>(dp->n, (size_t)dpx_pivots());
         ka.pts = dp->pts;
-        ka.dirs = dp->dirs;
+        ka.dirs = dp->dirs_view ? dp->dirs_view : dp->dirs;
         ka.count = count;
         ka.cta_sums = dp->cta_sums;
         ka.values = a.values;
@@ -2577,7 +2609,7 @@ extern "C" int hvb200cu_sets_maxmin(struct hvb200_plan *plan, void *ctx, uint64_
     sets_fn fn = pick_sets<16>(dp->d);
     const int b = span_begin(dp, 0);
     // always grid_x CTAs per set (idle ones add 0): the partial slots keep one stride over all launches of a run
-    fn<<<dim3((unsigned)c->grid_x, (unsigned)c->nsets), kSetsThreads, c->smem, dp->stream>>>(c->pts, c->off, dp->dirs, (ull)count, dp->d, c->partial);
+    fn<<<dim3((unsigned)c->grid_x, (unsigned)c->nsets), kSetsThreads, c->smem, dp->stream>>>(c->pts, c->off, dp->dirs_view ? dp->dirs_view : dp->dirs, (ull)count, dp->d, c->partial);
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
     plan->stats.maxmin_launches++;

@@ -63,3 +63,25 @@ def test_sets_amortise_the_per_call_cost(mb):
     assert np.allclose(a, b, rtol=1e-13, atol=0)
     print("batched %.2f ms, looped %.2f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1)))
     assert t1 - t0 < t2 - t1
+
+
+def test_rphi_direction_cache_is_transparent(mb, monkeypatch):
+    # Rphi-FWE+ directions depend on (d, index) only and are kept on the device: growing runs, windows and other
+    # dimensions in between must give the bits of the uncached streaming path
+    x5 = hvcases.front("sphere", 300, 5, 1)
+    x3 = hvcases.front("simplex", 300, 3, 2)
+    calls = [(x5, 1000, 0, 1000), (x5, 400_000, 0, 400_000), (x3, 70_000, 10_000, 60_000), (x5, 400_000, 333_333, 399_999),
+             (x5, 900_000, 250_000, 900_000), (x3, 300_000, 0, 300_000), (x5, 2000, 5, 1999)]
+    got = []
+    for x, N, i0, i1 in calls:
+        with mb.Plan(x, 1.1) as plan:
+            got.append(plan.run("Rphi-FWE+", N, 0, i0, i1))
+    monkeypatch.setenv("HVB200_NO_DIRCACHE", "1")
+    for (x, N, i0, i1), g in zip(calls, got):
+        with mb.Plan(x, 1.1) as plan:
+            assert plan.run("Rphi-FWE+", N, 0, i0, i1) == g
+    r_cached = None
+    monkeypatch.delenv("HVB200_NO_DIRCACHE")
+    r_cached = mb.directions("Rphi-FWE+", 5, 500_000, 0, 123_456, 1000)
+    monkeypatch.setenv("HVB200_NO_DIRCACHE", "1")
+    assert np.array_equal(r_cached, mb.directions("Rphi-FWE+", 5, 500_000, 0, 123_456, 1000))
