@@ -934,14 +934,24 @@ __global__ void __launch_bounds__(1024) k_reduce(const double *__restrict__ cta_
 // ------------------------------------------------------------------------------------------------
 struct HwDev {
     ull N;
+    ull Nrecip;            // floor((2^64 - 1) / N): exact 64/32 division by a multiply-high and <= 2 corrections
     ull a[HVB200_MAXD];
     int d;
 };
+// floor(t / N) for t < N * 2^32 with the reciprocal above (the quotient estimate is at most 2 too small)
+__device__ __forceinline__ ull div_by_n(ull t, ull N, ull Nrecip, ull &rem)
+{
+    ull q = __umul64hi(t, Nrecip);
+    ull r = t - q * N;
+    while (r >= N) { r -= N; q++; }
+    rem = r;
+    return q;
+}
 
 // RN64(x / N) as M * 2^e with M in [2^63, 2^64): bit-exact emulation of the x87 division
 // (i+1) / (long double)nsamples at c/hvapprox.c:295.  Requires 0 < x < N <= 2^32.
 struct X87Val { ull M; int e; };
-__device__ __forceinline__ X87Val x87_div(ull x, ull N)
+__device__ __forceinline__ X87Val x87_div(ull x, ull N, ull Nrecip)
 {
     const int lx = 63 - __clzll((long long)x), lN = 63 - __clzll((long long)N);
     int s = lN - lx;
@@ -949,9 +959,10 @@ __device__ __forceinline__ X87Val x87_div(ull x, ull N)
     if (X < N) { X <<= 1; s++; }            // N <= X < 2N  ->  X/N in [1,2)
     const ull r0 = X - N;
     const ull t1 = r0 << 32;
-    const ull q1 = t1 / N, r1 = t1 - q1 * N;
+    ull r1, r2;
+    const ull q1 = div_by_n(t1, N, Nrecip, r1);
     const ull t2 = r1 << 31;
-    const ull q2 = t2 / N, r2 = t2 - q2 * N;
+    const ull q2 = div_by_n(t2, N, Nrecip, r2);
     X87Val f;
     f.M = (1ull << 63) + (q1 << 31) + q2;
     f.e = -63 - s;
@@ -1087,7 +1098,7 @@ __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count
     const ull idx1 = i0 + j + 1;                    // i + 1
     const bool last = !(idx1 < P.N);                // last sample: all zeros (c/hvapprox.c:300-303)
     X87Val fac;
-    if (!last) fac = x87_div(idx1, P.N);
+    if (!last) fac = x87_div(idx1, P.N, P.Nrecip);
     double *out = dirs + j * (ull)(2 * d);
     unsigned capped = 0;
     double prod = 1.0;
@@ -2279,6 +2290,7 @@ extern "C" int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_para
     if (hw->nsamples > (1ull << 32)) { hvb200_set_error("DZ2019-HW on the device supports nsamples <= 2^32"); return -1; }
     HwDev P;
     P.N = hw->nsamples;
+    P.Nrecip = hw->nsamples ? ~0ull / hw->nsamples : 0;
     P.d = hw->d;
     for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
     const int b = span_begin(dp, 1);
@@ -2324,6 +2336,7 @@ extern "C" int hvb200cu_hw_prefetch(struct hvb200_plan *plan, const hvb200_hw_pa
     if (dp->used_recorded[buf]) CUDA_TRY(cudaStreamWaitEvent(dp->gen_stream, dp->ev_used[buf], 0));
     HwDev P;
     P.N = hw->nsamples;
+    P.Nrecip = hw->nsamples ? ~0ull / hw->nsamples : 0;
     P.d = hw->d;
     for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
     const int b = span_begin_on(dp, 1, dp->gen_stream);
