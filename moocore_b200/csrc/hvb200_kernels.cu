@@ -2120,6 +2120,20 @@ static int order_points(DevPlan *dp)
     return 0;
 }
 
+// The dynamic shared-memory limit is an attribute of the KERNEL FUNCTION, shared by all host threads: it is always
+// raised to the device maximum (never to the size one call needs — a concurrent call with a smaller point set
+// would lower it under a launch in flight: "invalid argument").  The limit does not affect occupancy.
+static int max_dyn_smem_limit()
+{
+    static int limit = 0;
+    if (limit == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0) limit = v;
+        else limit = 227 * 1024;
+    }
+    return limit;
+}
+
 extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batch, uint64_t *batch_out)
 {
     DevPlan *dp = (DevPlan *)plan->dev;
@@ -2176,21 +2190,21 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     int occ = 1;
     if (mode == MODE_BP) {
         bp_fn fn = pick_bp<HVB200_MAXD>(d);
-        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBpThreads, smem));
     } else if (mode == MODE_DPX) {
         dpx_fn fn = pick_dpx<32>(d);
-        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBlockThreads, smem));
     } else if (d <= 32) {
         maxmin_fn fn = pick_kernel(d, mode);
-        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBlockThreads, smem));
     } else {
-        CUDA_TRY(cudaFuncSetAttribute((const void *)k_maxmin_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute((const void *)k_maxmin_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
         CUDA_TRY(cudaFuncSetAttribute((const void *)k_maxmin_generic, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k_maxmin_generic, kBlockThreads, smem));
     }
@@ -2612,7 +2626,7 @@ extern "C" int hvb200cu_sets_begin(struct hvb200_plan *plan, const double *pts_h
     CUDA_TRY(cudaMemcpy(c->off, off_host, (size_t)(nsets + 1) * sizeof(unsigned), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemset(c->partial, 0, (size_t)nsets * c->grid_x * sizeof(double)));
     sets_fn fn = pick_sets<16>(dp->d);
-    CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
     return 0;
 }
 extern "C" int hvb200cu_sets_maxmin(struct hvb200_plan *plan, void *ctx, uint64_t count)
