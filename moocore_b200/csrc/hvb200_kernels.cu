@@ -2128,8 +2128,9 @@ static int max_dyn_smem_limit()
     static int limit = 0;
     if (limit == 0) {
         int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0) limit = v;
-        else limit = 227 * 1024;
+        // minus 1 KB: kernels with a few bytes of static shared memory must stay within the opt-in total
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 2048) limit = v - 1024;
+        else limit = 226 * 1024;
     }
     return limit;
 }
