@@ -18,6 +18,8 @@ from ._api import (  # noqa: F401
     library_path,
     device_count,
     directions,
+    epsilon_additive,
+    epsilon_mult,
     measure_fp64,
 )
 
@@ -33,6 +35,8 @@ __all__ = [
     "library_path",
     "device_count",
     "directions",
+    "epsilon_additive",
+    "epsilon_mult",
     "measure_fp64",
 ]
 __version__ = "0.1.0"

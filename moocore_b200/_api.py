@@ -84,6 +84,9 @@ def _load() -> ctypes.CDLL:
     L.hvb200_plan_set_kernel.argtypes = [vp, ctypes.c_int]
     L.hvb200_plan_run.restype = ctypes.c_int
     L.hvb200_plan_run.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, vp, _c_double_p]
+    for nm in ("epsilon_additive", "epsilon_mult"):
+        getattr(L, nm).restype = ctypes.c_double
+        getattr(L, nm).argtypes = [_c_double_p, ctypes.c_size_t, ctypes.c_uint8, _c_double_p, ctypes.c_size_t, _c_u8_p]
     L.hvb200_hv_approx_sets.restype = ctypes.c_int
     L.hvb200_hv_approx_sets.argtypes = [ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.c_uint8,
                                         _c_double_p, _c_u8_p, u64, u32, ctypes.c_int, _c_double_p]
@@ -268,6 +271,49 @@ def hv_approx_sets(
     if rc != 0:
         raise RuntimeError(f"moocore_b200: hv_approx_sets failed ({rc}): {_last_error()}")
     return out
+
+
+def _refset_common(points, ref, maximise, check_all_positive=False):
+    """Argument handling of python/src/moocore/_moocore.py:275-310 (_unary_refset_common)."""
+    points = np.ascontiguousarray(np.asarray(points, dtype=float))
+    ref = np.ascontiguousarray(np.atleast_2d(np.asarray(ref, dtype=float)))
+    if points.ndim != 2:
+        raise ValueError("input points must be a 2-D array")
+    if check_all_positive:
+        if not (points > 0).all():
+            raise ValueError("All values must be larger than 0 in the input points")
+        if not (ref > 0).all():
+            raise ValueError("All values must be larger than 0 in the reference set")
+    nobj = points.shape[1]
+    if nobj != ref.shape[1]:
+        raise ValueError(f"points and ref need to have the same number of columns ({nobj} != {ref.shape[1]})")
+    if nobj == 0:
+        raise ValueError("The number of columns cannot be 0")
+    maxi = np.ascontiguousarray(np.broadcast_to(np.asarray(maximise, dtype=bool), (nobj,))).view(np.uint8)
+    return points, ref, maxi, nobj
+
+
+def _epsilon(name, points, ref, maximise, check_all_positive):
+    points, ref, maxi, nobj = _refset_common(points, ref, maximise, check_all_positive)
+    if points.shape[0] == 0 or ref.shape[0] == 0:
+        raise ValueError("points and ref must not be empty")
+    if nobj > 64:
+        raise ValueError("This function supports at most 64 columns")
+    fn = getattr(_load(), name)
+    v = fn(_dp(points), points.shape[0], nobj, _dp(ref), ref.shape[0], maxi.ctypes.data_as(_c_u8_p))
+    if v != v:
+        raise RuntimeError(f"moocore_b200: CUDA {name} failed: {_last_error()}")
+    return float(v)
+
+
+def epsilon_additive(points, /, ref, *, maximise: bool | Sequence[bool] = False) -> float:
+    """Additive epsilon indicator (drop-in for ``moocore.epsilon_additive``, _moocore.py:462-511)."""
+    return _epsilon("epsilon_additive", points, ref, maximise, False)
+
+
+def epsilon_mult(points, /, ref, *, maximise: bool | Sequence[bool] = False) -> float:
+    """Multiplicative epsilon indicator (drop-in for ``moocore.epsilon_mult``); all values must be > 0."""
+    return _epsilon("epsilon_mult", points, ref, maximise, True)
 
 
 class Plan:

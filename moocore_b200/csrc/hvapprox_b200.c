@@ -720,6 +720,41 @@ int hvb200_hv_approx_sets(int method, const double *data, const size_t *cumsizes
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* epsilon indicator (c/epsilon.h:197-221; python/src/moocore/libmoocore.h:24-25)              */
+/* ------------------------------------------------------------------------------------------ */
+static double epsilon_common(int mult, const double *data, size_t n, dimension_t dim, const double *ref, size_t ref_size,
+                             const boolvec *maximise)
+{
+    tls_error[0] = 0;
+    const int d = (int)dim;
+    if (d < 1 || d > HVB200_MAXD || n == 0 || ref_size == 0) {
+        hvb200_set_error("epsilon: need 1..%d objectives and non-empty sets (d=%d, n=%zu, ref_size=%zu)", HVB200_MAXD, d, n, ref_size);
+        return fail_nan(mult ? "epsilon_mult" : "epsilon_additive");
+    }
+    const char *env = getenv("HVB200_DEVICE");
+    const int device = env ? atoi(env) : 0;
+    if (device < 0 || device >= hvb200cu_device_count()) {
+        hvb200_set_error("CUDA device %d not available (%d visible); this library has no CPU fallback", device, hvb200cu_device_count());
+        return fail_nan(mult ? "epsilon_mult" : "epsilon_additive");
+    }
+    signed char mm[HVB200_MAXD];
+    for (int k = 0; k < d; k++) mm[k] = maximise[k] ? 1 : -1;      /* minmax_from_boolvec, c/nondominated.h */
+    double out = NAN;
+    if (hvb200cu_epsilon(device, mult, data, n, ref, ref_size, d, mm, &out)) return fail_nan(mult ? "epsilon_mult" : "epsilon_additive");
+    return out;
+}
+double epsilon_additive(const double *restrict data, size_t n, dimension_t dim, const double *restrict ref, size_t ref_size,
+                        const boolvec *restrict maximise)
+{
+    return epsilon_common(0, data, n, dim, ref, ref_size, maximise);
+}
+double epsilon_mult(const double *restrict data, size_t n, dimension_t dim, const double *restrict ref, size_t ref_size,
+                    const boolvec *restrict maximise)
+{
+    return epsilon_common(1, data, n, dim, ref, ref_size, maximise);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* single-process multi-GPU                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {

@@ -6,6 +6,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include "../../include/hvapprox_b200.h"
+#include "../../include/epsilon_b200.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -65,6 +66,9 @@ int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double *values_hos
 /* copy the generated reciprocal directions of the current batch to the host (count x d) */
 int hvb200cu_read_dirs(struct hvb200_plan *plan, uint64_t count, double *r_host);
 int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2]);
+/* epsilon indicator */
+int hvb200cu_epsilon(int device, int mult, const double *A_host, size_t na, const double *B_host, size_t nb, int d,
+                     const signed char *mm, double *out);
 /* cached direction sets */
 int hvb200cu_dev_alloc(int device, size_t bytes, void **out);
 void hvb200cu_dev_free(int device, void *p);

@@ -2582,6 +2582,92 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     return 0;
 }
 
+static int max_dyn_smem_limit();
+// ---- epsilon indicator (the same max-min semiring, other operands) --------------------
+// I_eps(A, B) = max_{b in B} min_{a in A} max_k v_k(a, b),  v_k = a_k - b_k (additive) or a_k / b_k (multiplicative)
+// for a minimised objective and the operands swapped for a maximised one (c/epsilon.h:52-107).  Every v_k is one
+// IEEE operation and max/min are exact, so the result carries the reference's bits whatever the evaluation order;
+// the reference's early exits (:88-99) only prune.  One thread per point of B, A streamed through shared memory.
+struct EpsArgs { signed char mm[HVB200_MAXD]; int d; };
+static constexpr int kEpsThreads = 256, kEpsTile = 256;
+template <bool MULT>
+__global__ void __launch_bounds__(kEpsThreads) k_epsilon(const double *__restrict__ A, ull na, const double *__restrict__ B, ull nb,
+                                                         const EpsArgs e, double *__restrict__ block_max)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sa = reinterpret_cast<double *>(smem_raw);                 // [kEpsTile][d]
+    __shared__ double red[kEpsThreads / 32];
+    const int d = e.d;
+    const ull b = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = b < nb;
+    const double *pb = B + (valid ? b : 0) * (ull)d;
+    double eps_min = __longlong_as_double(0x7ff0000000000000LL);
+    for (ull t0 = 0; t0 < na; t0 += kEpsTile) {
+        const int tn = (int)min((ull)kEpsTile, na - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * d; i += kEpsThreads) sa[i] = A[t0 * (ull)d + i];
+        __syncthreads();
+        for (int i = 0; i < tn; i++) {
+            const double *pa = sa + (size_t)i * d;
+            double emax = -__longlong_as_double(0x7ff0000000000000LL);
+            for (int k = 0; k < d; k++) {
+                const double x = pa[k], y = __ldg(pb + k);
+                double v;
+                if (e.mm[k] < 0) v = MULT ? x / y : x - y;
+                else if (e.mm[k] > 0) v = MULT ? y / x : y - x;
+                else v = 0.0;
+                emax = (k == 0 || v > emax) ? v : emax;
+            }
+            eps_min = (emax < eps_min) ? emax : eps_min;
+        }
+    }
+    double v = valid ? eps_min : -__longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_down_sync(0xffffffffu, v, off);
+        v = (o > v) ? o : v;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = red[0];
+        for (int w = 1; w < kEpsThreads / 32; w++) m = (red[w] > m) ? red[w] : m;
+        block_max[blockIdx.x] = m;
+    }
+}
+extern "C" int hvb200cu_epsilon(int device, int mult, const double *A_host, size_t na, const double *B_host, size_t nb, int d,
+                                const signed char *mm, double *out)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    const unsigned blocks = (unsigned)((nb + kEpsThreads - 1) / kEpsThreads);
+    double *A = nullptr, *B = nullptr, *bm = nullptr;
+    int rc = -1;
+    std::vector<double> host(blocks);
+    do {
+        if (cudaMalloc(&A, na * (size_t)d * sizeof(double)) != cudaSuccess || cudaMalloc(&B, nb * (size_t)d * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&bm, blocks * sizeof(double)) != cudaSuccess) break;
+        if (cudaMemcpy(A, A_host, na * (size_t)d * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (cudaMemcpy(B, B_host, nb * (size_t)d * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        EpsArgs e;
+        e.d = d;
+        for (int k = 0; k < HVB200_MAXD; k++) e.mm[k] = k < d ? mm[k] : 0;
+        const size_t smem = (size_t)kEpsTile * d * sizeof(double);
+        if (cudaFuncSetAttribute((const void *)k_epsilon<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()) != cudaSuccess ||
+            cudaFuncSetAttribute((const void *)k_epsilon<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()) != cudaSuccess) break;
+        if (mult) k_epsilon<true><<<blocks, kEpsThreads, smem>>>(A, (ull)na, B, (ull)nb, e, bm);
+        else k_epsilon<false><<<blocks, kEpsThreads, smem>>>(A, (ull)na, B, (ull)nb, e, bm);
+        if (cudaMemcpy(host.data(), bm, blocks * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc) hvb200_set_error("epsilon indicator: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(A); cudaFree(B); cudaFree(bm);
+    if (rc) return -1;
+    double eps = mult ? 0.0 : -INFINITY;                  // c/epsilon.h:83
+    for (unsigned i = 0; i < blocks; i++) eps = (host[i] > eps) ? host[i] : eps;
+    *out = eps;
+    return 0;
+}
+
 // ---- batched point sets ------------------------------------------------------------------------
 struct SetsCtx {
     double *pts = nullptr;

@@ -581,3 +581,31 @@ ORC_API double orc_hv_approx_rphi_fang_wang_plus(const double *data, size_t n, u
     free(pts);
     return orc_finalize(sum, d, nsamples);
 }
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* epsilon indicator: restatement of c/epsilon.h:52-107 (epsilon_helper_) without its early exits, which only
+ * prune: I = max_b min_a max_k v_k, v_k = a_k - b_k | a_k / b_k for a minimised objective, operands swapped
+ * for a maximised one; start value 0 (multiplicative) or -inf (additive), c/epsilon.h:83.                    */
+/* ------------------------------------------------------------------------------------------ */
+__attribute__((visibility("default")))
+double orc_epsilon(int mult, const double *data, size_t n, int dim, const double *ref, size_t ref_size, const unsigned char *maximise)
+{
+    double eps = mult ? 0.0 : -INFINITY;
+    for (size_t b = 0; b < ref_size; b++) {
+        const double *pb = ref + b * (size_t)dim;
+        double eps_min = INFINITY;
+        for (size_t a = 0; a < n; a++) {
+            const double *pa = data + a * (size_t)dim;
+            double eps_max = 0.0;
+            for (int k = 0; k < dim; k++) {
+                const double x = maximise[k] ? pb[k] : pa[k], y = maximise[k] ? pa[k] : pb[k];
+                const double v = mult ? x / y : x - y;
+                eps_max = (k == 0 || v > eps_max) ? v : eps_max;
+            }
+            eps_min = (eps_max < eps_min) ? eps_max : eps_min;
+        }
+        eps = (eps_min > eps) ? eps_min : eps;
+    }
+    return eps;
+}
