@@ -2212,7 +2212,7 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     if (occ < 1) { hvb200_set_error("max-min kernel does not fit on an SM (d=%d)", d); return -1; }
     dp->grid = dp->sm_count * occ;
     if (mode == MODE_BP && dp->bp_hits_cap < (size_t)dp->grid * kBpHitCap) {
-        cudaFree(dp->bp_hits); cudaFree(dp->bp_chunk_sums); cudaFree(dp->bp_chunk_counter);
+        cudaFree(dp->bp_hits);
         dp->bp_hits = nullptr; dp->bp_hits_cap = 0;
         CUDA_TRY(cudaMalloc(&dp->bp_hits, (size_t)dp->grid * kBpHitCap * sizeof(uint2)));
         dp->bp_hits_cap = (size_t)dp->grid * kBpHitCap;
