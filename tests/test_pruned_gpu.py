@@ -167,3 +167,16 @@ def test_device_transform_and_filter_matches_host(mb, d, n, monkeypatch):
         assert mb.hv_approx(x, ref=np.where(maxi, 2.0, -1.0), maximise=maxi, nsamples=1000, method="DZ2019-MC", seed=1) == 0.0
     with mb.Plan(x, np.where(maxi, 2.0, -1.0), maxi, allow_extension=True) as plan:
         assert plan.empty and plan.npoints == 0
+
+
+def test_workspace_reuse_across_grid_sizes(mb):
+    # plans hand their device buffers to a per-device pool; a d=20 plan (2 CTAs/SM) followed by a d=5 plan
+    # (3 CTAs/SM, more hit lists) followed by d=20 again must not see stale per-chunk buffers
+    rng = np.random.default_rng(8)
+    for d, n in ((20, 3000), (5, 3000), (20, 2500), (6, 4000), (33, 1500)):
+        x = rng.random((n, d))
+        out = {}
+        for kern in ("exact", "pruned"):
+            with mb.Plan(x, 1.1, kernel=kern, allow_extension=True) as plan:
+                out[kern] = plan.run("DZ2019-MC", 600_000, 9, 0, 300_000)
+        assert abs(sum(out["exact"]) - sum(out["pruned"])) <= 1e-12 * sum(out["exact"])
