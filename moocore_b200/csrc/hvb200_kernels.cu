@@ -2590,17 +2590,25 @@ static int max_dyn_smem_limit();
 // the reference's early exits (:88-99) only prune.  One thread per point of B, A streamed through shared memory.
 struct EpsArgs { signed char mm[HVB200_MAXD]; int d; };
 static constexpr int kEpsThreads = 256, kEpsTile = 256;
-template <bool MULT>
+// MODE: -1 all objectives minimised, +1 all maximised, 0 mixed (per-objective sign from e.mm) — the three
+// specialisations of the reference (c/epsilon.h:166-176).  D > 0: compile-time dimension, the reference point of
+// the thread lives in registers; D = 0: run-time dimension.
+template <bool MULT, int MODE, int D>
 __global__ void __launch_bounds__(kEpsThreads) k_epsilon(const double *__restrict__ A, ull na, const double *__restrict__ B, ull nb,
                                                          const EpsArgs e, double *__restrict__ block_max)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sa = reinterpret_cast<double *>(smem_raw);                 // [kEpsTile][d]
     __shared__ double red[kEpsThreads / 32];
-    const int d = e.d;
+    const int d = D ? D : e.d;
     const ull b = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = b < nb;
     const double *pb = B + (valid ? b : 0) * (ull)d;
+    double pbr[D ? D : 1];
+    if constexpr (D > 0) {
+#pragma unroll
+        for (int k = 0; k < D; k++) pbr[k] = __ldg(pb + k);
+    }
     double eps_min = __longlong_as_double(0x7ff0000000000000LL);
     for (ull t0 = 0; t0 < na; t0 += kEpsTile) {
         const int tn = (int)min((ull)kEpsTile, na - t0);
@@ -2609,12 +2617,14 @@ __global__ void __launch_bounds__(kEpsThreads) k_epsilon(const double *__restric
         __syncthreads();
         for (int i = 0; i < tn; i++) {
             const double *pa = sa + (size_t)i * d;
-            double emax = -__longlong_as_double(0x7ff0000000000000LL);
-            for (int k = 0; k < d; k++) {
-                const double x = pa[k], y = __ldg(pb + k);
+            double emax = 0.0;
+#pragma unroll
+            for (int k = 0; k < (D ? D : d); k++) {
+                const double x = pa[k], y = D ? pbr[D ? k : 0] : __ldg(pb + k);
+                const int sgn = MODE ? MODE : (int)e.mm[k];
                 double v;
-                if (e.mm[k] < 0) v = MULT ? x / y : x - y;
-                else if (e.mm[k] > 0) v = MULT ? y / x : y - x;
+                if (sgn < 0) v = MULT ? x / y : x - y;
+                else if (sgn > 0) v = MULT ? y / x : y - x;
                 else v = 0.0;
                 emax = (k == 0 || v > emax) ? v : emax;
             }
@@ -2635,6 +2645,22 @@ __global__ void __launch_bounds__(kEpsThreads) k_epsilon(const double *__restric
         block_max[blockIdx.x] = m;
     }
 }
+typedef void (*eps_fn)(const double *, ull, const double *, ull, const EpsArgs, double *);
+template <bool MULT, int MODE, int D>
+static eps_fn pick_eps_d(int d)
+{
+    if constexpr (D < 2) {
+        return (eps_fn)k_epsilon<MULT, MODE, 0>;
+    } else {
+        if (d == D) return (eps_fn)k_epsilon<MULT, MODE, D>;
+        return pick_eps_d<MULT, MODE, D - 1>(d);
+    }
+}
+static eps_fn pick_eps(bool mult, int mode, int d)
+{
+    if (mult) return mode < 0 ? pick_eps_d<true, -1, 32>(d) : (mode > 0 ? pick_eps_d<true, 1, 32>(d) : pick_eps_d<true, 0, 32>(d));
+    return mode < 0 ? pick_eps_d<false, -1, 32>(d) : (mode > 0 ? pick_eps_d<false, 1, 32>(d) : pick_eps_d<false, 0, 32>(d));
+}
 extern "C" int hvb200cu_epsilon(int device, int mult, const double *A_host, size_t na, const double *B_host, size_t nb, int d,
                                 const signed char *mm, double *out)
 {
@@ -2652,10 +2678,11 @@ extern "C" int hvb200cu_epsilon(int device, int mult, const double *A_host, size
         e.d = d;
         for (int k = 0; k < HVB200_MAXD; k++) e.mm[k] = k < d ? mm[k] : 0;
         const size_t smem = (size_t)kEpsTile * d * sizeof(double);
-        if (cudaFuncSetAttribute((const void *)k_epsilon<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()) != cudaSuccess ||
-            cudaFuncSetAttribute((const void *)k_epsilon<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()) != cudaSuccess) break;
-        if (mult) k_epsilon<true><<<blocks, kEpsThreads, smem>>>(A, (ull)na, B, (ull)nb, e, bm);
-        else k_epsilon<false><<<blocks, kEpsThreads, smem>>>(A, (ull)na, B, (ull)nb, e, bm);
+        int mode = mm[0];
+        for (int k = 1; k < d; k++) if (mm[k] != mm[0]) mode = 0;
+        eps_fn fn = pick_eps(mult != 0, mode, d);
+        if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()) != cudaSuccess) break;
+        fn<<<blocks, kEpsThreads, smem>>>(A, (ull)na, B, (ull)nb, e, bm);
         if (cudaMemcpy(host.data(), bm, blocks * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) break;
         rc = 0;
     } while (0);
