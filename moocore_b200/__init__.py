@@ -20,6 +20,9 @@ from ._api import (  # noqa: F401
     directions,
     epsilon_additive,
     epsilon_mult,
+    igd,
+    igd_plus,
+    avg_hausdorff_dist,
     measure_fp64,
 )
 
@@ -37,6 +40,9 @@ __all__ = [
     "directions",
     "epsilon_additive",
     "epsilon_mult",
+    "igd",
+    "igd_plus",
+    "avg_hausdorff_dist",
     "measure_fp64",
 ]
 __version__ = "0.1.0"

@@ -87,6 +87,11 @@ def _load() -> ctypes.CDLL:
     for nm in ("epsilon_additive", "epsilon_mult"):
         getattr(L, nm).restype = ctypes.c_double
         getattr(L, nm).argtypes = [_c_double_p, ctypes.c_size_t, ctypes.c_uint8, _c_double_p, ctypes.c_size_t, _c_u8_p]
+    for nm in ("IGD", "IGD_plus"):
+        getattr(L, nm).restype = ctypes.c_double
+        getattr(L, nm).argtypes = [_c_double_p, ctypes.c_size_t, ctypes.c_uint8, _c_double_p, ctypes.c_size_t, _c_u8_p]
+    L.avg_Hausdorff_dist.restype = ctypes.c_double
+    L.avg_Hausdorff_dist.argtypes = [_c_double_p, ctypes.c_size_t, ctypes.c_uint8, _c_double_p, ctypes.c_size_t, _c_u8_p, ctypes.c_uint]
     L.hvb200_hv_approx_sets.restype = ctypes.c_int
     L.hvb200_hv_approx_sets.argtypes = [ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.c_uint8,
                                         _c_double_p, _c_u8_p, u64, u32, ctypes.c_int, _c_double_p]
@@ -314,6 +319,35 @@ def epsilon_additive(points, /, ref, *, maximise: bool | Sequence[bool] = False)
 def epsilon_mult(points, /, ref, *, maximise: bool | Sequence[bool] = False) -> float:
     """Multiplicative epsilon indicator (drop-in for ``moocore.epsilon_mult``); all values must be > 0."""
     return _epsilon("epsilon_mult", points, ref, maximise, True)
+
+
+def _gd_call(name, points, ref, maximise, *extra):
+    points, ref, maxi, nobj = _refset_common(points, ref, maximise)
+    if ref.shape[0] == 0:
+        raise ValueError("ref must not be empty")
+    if nobj > 64:
+        raise ValueError("This function supports at most 64 columns")
+    v = getattr(_load(), name)(_dp(points), points.shape[0], nobj, _dp(ref), ref.shape[0], maxi.ctypes.data_as(_c_u8_p), *extra)
+    if v != v:
+        raise RuntimeError(f"moocore_b200: CUDA {name} failed: {_last_error()}")
+    return float(v)
+
+
+def igd(points, /, ref, *, maximise: bool | Sequence[bool] = False) -> float:
+    """Inverted generational distance (drop-in for ``moocore.igd``, _moocore.py:310-390)."""
+    return _gd_call("IGD", points, ref, maximise)
+
+
+def igd_plus(points, /, ref, *, maximise: bool | Sequence[bool] = False) -> float:
+    """Modified inverted generational distance IGD+ (drop-in for ``moocore.igd_plus``)."""
+    return _gd_call("IGD_plus", points, ref, maximise)
+
+
+def avg_hausdorff_dist(points, /, ref, *, maximise: bool | Sequence[bool] = False, p: int = 1) -> float:
+    """Averaged Hausdorff distance (drop-in for ``moocore.avg_hausdorff_dist``, _moocore.py:416-460)."""
+    if p <= 0:
+        raise ValueError("'p' must be larger than zero")
+    return _gd_call("avg_Hausdorff_dist", points, ref, maximise, ctypes.c_uint(p))
 
 
 class Plan:

@@ -755,6 +755,60 @@ double epsilon_mult(const double *restrict data, size_t n, dimension_t dim, cons
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* IGD, IGD+, averaged Hausdorff distance (c/igd.h:196-287; libmoocore.h:20-22)                */
+/* ------------------------------------------------------------------------------------------ */
+static int gd_setup(const char *who, dimension_t dim, size_t n, size_t ref_size, const boolvec *maximise, signed char *mm, int *device)
+{
+    tls_error[0] = 0;
+    const int d = (int)dim;
+    if (d < 1 || d > HVB200_MAXD || ref_size == 0) {
+        hvb200_set_error("%s: need 1..%d objectives and a non-empty reference set (d=%d, n=%zu, ref_size=%zu)", who, HVB200_MAXD, d, n, ref_size);
+        return -1;
+    }
+    const char *env = getenv("HVB200_DEVICE");
+    *device = env ? atoi(env) : 0;
+    if (*device < 0 || *device >= hvb200cu_device_count()) {
+        hvb200_set_error("CUDA device %d not available (%d visible); this library has no CPU fallback", *device, hvb200cu_device_count());
+        return -1;
+    }
+    for (int k = 0; k < d; k++) mm[k] = maximise[k] ? 1 : -1;      /* minmax_from_boolvec */
+    return 0;
+}
+double IGD(const double *restrict data, size_t npoints, dimension_t nobj, const double *restrict ref, size_t ref_size,
+           const boolvec *restrict maximise)
+{   /* IGD_minmax, c/igd.h:186-194: gd_common(ref as a, data as r, plus=false, psize=false, p=1) */
+    signed char mm[HVB200_MAXD];
+    int device;
+    double v;
+    if (gd_setup("IGD", nobj, npoints, ref_size, maximise, mm, &device)) return fail_nan("IGD");
+    if (hvb200cu_gd_common(device, ref, ref_size, data, npoints, (int)nobj, mm, 0, 0, 1, &v)) return fail_nan("IGD");
+    return v;
+}
+double IGD_plus(const double *restrict data, size_t npoints, dimension_t nobj, const double *restrict ref, size_t ref_size,
+                const boolvec *restrict maximise)
+{   /* IGD_plus_minmax, c/igd.h:232-241: plus=true, psize=true, p=1 */
+    signed char mm[HVB200_MAXD];
+    int device;
+    double v;
+    if (gd_setup("IGD_plus", nobj, npoints, ref_size, maximise, mm, &device)) return fail_nan("IGD_plus");
+    if (hvb200cu_gd_common(device, ref, ref_size, data, npoints, (int)nobj, mm, 1, 1, 1, &v)) return fail_nan("IGD_plus");
+    return v;
+}
+double avg_Hausdorff_dist(const double *restrict data, size_t npoints, dimension_t nobj, const double *restrict ref, size_t ref_size,
+                          const boolvec *restrict maximise, unsigned int p)
+{   /* avg_Hausdorff_dist_minmax, c/igd.h:257-273: MAX(GD_p, IGD_p), psize=true, p cast to uint_fast8_t */
+    signed char mm[HVB200_MAXD];
+    int device;
+    double gd_p, igd_p;
+    if (gd_setup("avg_Hausdorff_dist", nobj, npoints, ref_size, maximise, mm, &device)) return fail_nan("avg_Hausdorff_dist");
+    const unsigned pp = (unsigned)(unsigned char)p;
+    if (pp == 0) { hvb200_set_error("avg_Hausdorff_dist: p must be positive"); return fail_nan("avg_Hausdorff_dist"); }
+    if (hvb200cu_gd_common(device, data, npoints, ref, ref_size, (int)nobj, mm, 0, 1, pp, &gd_p)) return fail_nan("avg_Hausdorff_dist");
+    if (hvb200cu_gd_common(device, ref, ref_size, data, npoints, (int)nobj, mm, 0, 1, pp, &igd_p)) return fail_nan("avg_Hausdorff_dist");
+    return (gd_p < igd_p) ? igd_p : gd_p;                          /* MAX(gd_p, igd_p) */
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* single-process multi-GPU                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {

@@ -69,6 +69,8 @@ int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2]);
 /* epsilon indicator */
 int hvb200cu_epsilon(int device, int mult, const double *A_host, size_t na, const double *B_host, size_t nb, int d,
                      const signed char *mm, double *out);
+int hvb200cu_gd_common(int device, const double *X_host, size_t nx, const double *Y_host, size_t ny, int d,
+                       const signed char *mm, int plus, int psize, unsigned p, double *result);
 /* cached direction sets */
 int hvb200cu_dev_alloc(int device, size_t bytes, void **out);
 void hvb200cu_dev_free(int device, void *p);

@@ -2695,6 +2695,131 @@ extern "C" int hvb200cu_epsilon(int device, int mult, const double *A_host, size
     return 0;
 }
 
+// ---- generational distances: GD / IGD / IGD+ / averaged Hausdorff (c/igd.h:60-289) -------------------------------
+// gd_common_helper_ (c/igd.h:61-127): for every point a of X the squared distance to the nearest point of Y,
+//     min_y sum_k diff_k^2,  diff_k = a_k - y_k   (plain)   or   max(oriented difference, 0)   ("plus"),
+// then a square root / power and a left-to-right sum over a.  The O(|X| |Y| d) part runs here, one thread per a with
+// Y streamed through shared memory; products and sums are separate roundings in the reference's order (-fmad=false),
+// min is exact, so each per-point value carries the reference's bits.  The tail (sqrt, pow_uint, ordered sum, powl)
+// is replayed on the host in the reference's order, which makes the result bit-identical, not just close.
+template <bool PLUS, int MODE, int D>
+__global__ void __launch_bounds__(kEpsThreads) k_gd(const double *__restrict__ X, ull nx, const double *__restrict__ Y, ull ny,
+                                                    const EpsArgs e, double *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sy = reinterpret_cast<double *>(smem_raw);                 // [kEpsTile][d]
+    const int d = D ? D : e.d;
+    const ull a = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = a < nx;
+    const double *pa = X + (valid ? a : 0) * (ull)d;
+    double par[D ? D : 1];
+    if constexpr (D > 0) {
+#pragma unroll
+        for (int k = 0; k < D; k++) par[k] = __ldg(pa + k);
+    }
+    double min_dist = __longlong_as_double(0x7ff0000000000000LL);
+    for (ull t0 = 0; t0 < ny; t0 += kEpsTile) {
+        const int tn = (int)min((ull)kEpsTile, ny - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * d; i += kEpsThreads) sy[i] = Y[t0 * (ull)d + i];
+        __syncthreads();
+        for (int i = 0; i < tn; i++) {
+            const double *pr = sy + (size_t)i * d;
+            double dist = 0.0;
+#pragma unroll
+            for (int k = 0; k < (D ? D : d); k++) {
+                const double a_d = D ? par[D ? k : 0] : __ldg(pa + k), r_d = pr[k];
+                const int sgn = MODE ? MODE : (int)e.mm[k];
+                double diff;
+                if (PLUS) {
+                    const double v = sgn < 0 ? r_d - a_d : (sgn > 0 ? a_d - r_d : 0.0);
+                    diff = (v < 0.0) ? 0.0 : v;                        // MAX(v, 0.), c/maxminclamp.h:58
+                } else {
+                    diff = sgn != 0 ? a_d - r_d : 0.0;
+                }
+                dist += diff * diff;
+            }
+            min_dist = (min_dist > dist) ? dist : min_dist;
+        }
+    }
+    if (valid) out[a] = min_dist;
+}
+typedef void (*gd_fn)(const double *, ull, const double *, ull, const EpsArgs, double *);
+template <bool PLUS, int MODE, int D>
+static gd_fn pick_gd_d(int d)
+{
+    if constexpr (D < 2) {
+        return (gd_fn)k_gd<PLUS, MODE, 0>;
+    } else {
+        if (d == D) return (gd_fn)k_gd<PLUS, MODE, D>;
+        return pick_gd_d<PLUS, MODE, D - 1>(d);
+    }
+}
+static gd_fn pick_gd(bool plus, int mode, int d)
+{
+    if (plus) return mode < 0 ? pick_gd_d<true, -1, 16>(d) : (mode > 0 ? pick_gd_d<true, 1, 16>(d) : pick_gd_d<true, 0, 16>(d));
+    // the plain difference is squared: the orientation does not matter, only ignored objectives (mm = 0) do
+    return mode != 0 ? pick_gd_d<false, -1, 16>(d) : pick_gd_d<false, 0, 16>(d);
+}
+// pow_uint (c/pow_int.h:59-74) on the host, same multiplication trees as the device pow_chain
+static double pow_uint_host(double x, unsigned e)
+{
+    if (e == 0) return 1.0;
+    if (e <= 31) {
+        const PowProg P = kPowProg[e];
+        double v[8];
+        v[0] = x;
+        for (int t = 0; t < P.n; t++) v[t + 1] = v[P.op[t][0]] * v[P.op[t][1]];
+        return v[P.n];
+    }
+    double acc = (e & 1) ? x : 1.0;
+    for (e >>= 1; e; e >>= 1) { x *= x; if (e & 1u) acc *= x; }
+    return acc;
+}
+// gd_common (c/igd.h:61-127, 159-174) for (X, Y) = (points_a, points_r)
+extern "C" int hvb200cu_gd_common(int device, const double *X_host, size_t nx, const double *Y_host, size_t ny, int d,
+                                  const signed char *mm, int plus, int psize, unsigned p, double *result)
+{
+    if (nx == 0) { *result = INFINITY; return 0; }
+    CUDA_TRY(cudaSetDevice(device));
+    const unsigned blocks = (unsigned)((nx + kEpsThreads - 1) / kEpsThreads);
+    double *X = nullptr, *Y = nullptr, *out = nullptr;
+    std::vector<double> host(nx);
+    int rc = -1;
+    do {
+        if (cudaMalloc(&X, nx * (size_t)d * sizeof(double)) != cudaSuccess || cudaMalloc(&Y, (ny ? ny : 1) * (size_t)d * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&out, nx * sizeof(double)) != cudaSuccess) break;
+        if (cudaMemcpy(X, X_host, nx * (size_t)d * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (ny && cudaMemcpy(Y, Y_host, ny * (size_t)d * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        EpsArgs e;
+        e.d = d;
+        for (int k = 0; k < HVB200_MAXD; k++) e.mm[k] = k < d ? mm[k] : 0;
+        int mode = mm[0];
+        for (int k = 1; k < d; k++) if (mm[k] != mm[0]) mode = 0;
+        gd_fn fn = pick_gd(plus != 0, mode, d);
+        if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()) != cudaSuccess) break;
+        fn<<<blocks, kEpsThreads, (size_t)kEpsTile * d * sizeof(double)>>>(X, (ull)nx, Y, (ull)ny, e, out);
+        if (cudaMemcpy(host.data(), out, nx * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc) hvb200_set_error("generational distance: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(X); cudaFree(Y); cudaFree(out);
+    if (rc) return -1;
+    double gd = 0.0;
+    for (size_t a = 0; a < nx; a++) {
+        double md = host[a];
+        if (md == 0.0) continue;                                        // zero_skip, c/igd.h:100-101,115
+        if (p == 1) md = sqrt(md);
+        else if (p % 2 == 0) md = pow_uint_host(md, p / 2);
+        else md = pow_uint_host(sqrt(md), p);
+        gd += md;
+    }
+    if (p == 1) *result = gd / (double)nx;
+    else if (psize) *result = (double)powl(gd / (double)nx, 1.0 / p);
+    else *result = (double)powl(gd, 1.0 / p) / (double)nx;
+    return 0;
+}
+
 // ---- batched point sets ------------------------------------------------------------------------
 struct SetsCtx {
     double *pts = nullptr;

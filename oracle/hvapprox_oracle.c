@@ -609,3 +609,46 @@ double orc_epsilon(int mult, const double *data, size_t n, int dim, const double
     }
     return eps;
 }
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* generational distances: restatement of gd_common_helper_ (c/igd.h:61-127).  (a, r) = (points_a, points_r);
+ * IGD = gd(ref, data, plus=0, psize=0, p=1), IGD+ = gd(ref, data, plus=1, psize=1, p=1),
+ * avg Hausdorff = max(gd(data, ref, 0, 1, p), gd(ref, data, 0, 1, p))  (c/igd.h:186-194, 232-241, 257-273).   */
+/* ------------------------------------------------------------------------------------------ */
+__attribute__((visibility("default")))
+double orc_gd_common(const double *pa_, size_t size_a, const double *pr_, size_t size_r, int dim, const unsigned char *maximise,
+                     int plus, int psize, unsigned p)
+{
+    if (size_a == 0) return INFINITY;
+    double gd = 0.0;
+    for (size_t a = 0; a < size_a; a++) {
+        const double *pa = pa_ + a * (size_t)dim;
+        double min_dist = INFINITY;
+        int zero = 0;
+        for (size_t r = 0; r < size_r && !zero; r++) {
+            const double *pr = pr_ + r * (size_t)dim;
+            double dist = 0.0;
+            for (int k = 0; k < dim; k++) {
+                double diff;
+                if (plus) {
+                    const double v = maximise[k] ? pa[k] - pr[k] : pr[k] - pa[k];
+                    diff = (v < 0.) ? 0. : v;
+                } else {
+                    diff = pa[k] - pr[k];
+                }
+                dist += diff * diff;
+            }
+            if (dist == 0) zero = 1;
+            min_dist = (min_dist > dist) ? dist : min_dist;
+        }
+        if (zero) continue;
+        if (p == 1) min_dist = sqrt(min_dist);
+        else if (p % 2 == 0) min_dist = orc_pow_uint(min_dist, p / 2);
+        else min_dist = orc_pow_uint(sqrt(min_dist), p);
+        gd += min_dist;
+    }
+    if (p == 1) return gd / (double)size_a;
+    if (psize) return (double)powl(gd / (double)size_a, 1.0 / p);
+    return (double)powl(gd, 1.0 / p) / (double)size_a;
+}
