@@ -471,10 +471,10 @@ def hv_approx_shard(points, ref, *, maximise=False, nsamples: int, seed: int = 0
                     device: int = 0, stream: int | None = None):
     """Shard `rank` of `world` of an estimate as a (hi, lo) partial sum: block-cyclic for DZ2019-HW (balanced),
     a contiguous range for the sequential MC and Rphi streams."""
-    from .sharding import shard_range
+    from .sharding import shard_block, shard_range
     with Plan(points, ref, maximise, device=device) as plan:
         if method == "DZ2019-HW" and world > 1:
-            return plan.run_blocks(method, nsamples, rank, world, seed=seed, stream=stream)
+            return plan.run_blocks(method, nsamples, rank, world, block=shard_block(nsamples, world), seed=seed, stream=stream)
         i0, i1 = shard_range(nsamples, rank, world)
         return plan.run(method, nsamples, seed, i0, i1, stream)
 

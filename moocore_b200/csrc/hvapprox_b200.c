@@ -545,6 +545,14 @@ int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint3
    directions.  The cost of a direction varies smoothly along a Hua-Wang lattice (its first angle grows with the
    index), so contiguous shards are unbalanced (8 GPUs: 85 % efficiency) while interleaved blocks are not.
    Only the lattice is index-addressable: the MC and Rphi streams are sequential and stay on contiguous ranges. */
+/* block size of the block-cyclic shards: 2^21 directions, halved (down to 2^16) until every rank gets >= 4 blocks */
+uint64_t hvb200_shard_block(uint_fast32_t nsamples, int world)
+{
+    uint64_t block = HVB200_SHARD_BLOCK;
+    if (world < 1) world = 1;
+    while (block > ((uint64_t)1 << 16) && block * (uint64_t)world * 4 > (uint64_t)nsamples) block >>= 1;
+    return block;
+}
 int hvb200_plan_run_blocks(hvb200_plan *plan, int method, uint_fast32_t nsamples_, uint32_t seed,
                            uint64_t block, uint64_t first, uint64_t stride, void *cuda_stream, double out_hilo[2])
 {
@@ -830,7 +838,7 @@ static void *shard_main(void *arg)
     j->rc = hvb200_plan_create(&plan, j->data, j->npoints, j->nobjs, j->ref, j->maximise, j->device);
     if (j->rc == 0 && !plan) { j->empty = 1; return NULL; }
     if (j->rc == 0 && j->stride > 1 && j->method == HVB200_METHOD_HW)
-        j->rc = hvb200_plan_run_blocks(plan, j->method, j->nsamples, j->seed, HVB200_SHARD_BLOCK, (uint64_t)j->device, (uint64_t)j->stride, NULL, j->hilo);
+        j->rc = hvb200_plan_run_blocks(plan, j->method, j->nsamples, j->seed, hvb200_shard_block(j->nsamples, j->stride), (uint64_t)j->device, (uint64_t)j->stride, NULL, j->hilo);
     else if (j->rc == 0) j->rc = hvb200_plan_run(plan, j->method, j->nsamples, j->seed, j->i0, j->i1, NULL, j->hilo);
     if (j->rc) snprintf(j->err, sizeof j->err, "%s", tls_error);
     j->plan = plan;

@@ -1408,6 +1408,8 @@ struct DevPlan {
     bool resources_ready = false;        // stream / events / small buffers exist (workspace reuse)
     bool ordered = false;                // points already sorted by probe arg-max frequency
     // block-pruned kernel (hvb200_bp.cuh)
+    std::vector<double> host_pts;        // host copy of the transformed points when the plan was built from one (saves a
+                                         // 0.6 ms pageable read-back in bp_prepare)
     bool bp_ready = false;
     double *bp_pts = nullptr; size_t bp_pts_cap = 0;
     float *bp_piv32 = nullptr; unsigned *bp_pividx = nullptr;
@@ -1748,8 +1750,11 @@ static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, co
         dp->pts_cap = padded;
     }
     // zero only the padding rows behind the real points
-    if (pts_dev) CUDA_TRY(cudaMemcpyAsync(dp->pts, pts_dev, plan->n * (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, us));
-    else CUDA_TRY(cudaMemcpyAsync(dp->pts, pts_host, plan->n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice, us));
+    if (pts_dev) { CUDA_TRY(cudaMemcpyAsync(dp->pts, pts_dev, plan->n * (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, us)); dp->host_pts.clear(); }
+    else {
+        CUDA_TRY(cudaMemcpyAsync(dp->pts, pts_host, plan->n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice, us));
+        dp->host_pts.assign(pts_host, pts_host + plan->n * (size_t)d);
+    }
     if (padded > plan->n * (size_t)d)
         CUDA_TRY(cudaMemsetAsync(dp->pts + plan->n * (size_t)d, 0, (padded - plan->n * (size_t)d) * sizeof(double), us));
     if (d <= 32) {
@@ -1906,7 +1911,7 @@ static void bp_kd_order(const std::vector<double> &norm, int d, std::vector<unsi
     std::nth_element(kv.begin(), kv.begin() + half, kv.end());
     for (size_t i = 0; i < cnt; i++) idx[lo + i] = kv[i].second;
     std::vector<std::pair<double, unsigned>>().swap(kv);
-    if (depth < 3 && cnt >= 8192) {
+    if (depth < 3 && cnt >= 2048) {
         // the two halves touch disjoint index ranges: 8 host threads at the third level
         std::thread left([&] { bp_kd_order(norm, d, idx, lo, lo + half, depth + 1); });
         bp_kd_order(norm, d, idx, lo + half, hi, depth + 1);
@@ -1938,15 +1943,20 @@ static int bp_prepare(DevPlan *dp)
         CUDA_TRY(cudaMalloc(&dp->wins, 2 * n * sizeof(unsigned)));
         dp->wins_cap = 2 * n;
     }
+    // the points come back first; the probe kernel (only the pivots need it) then runs under the host's kd build
+    std::vector<unsigned> wins(n);
+    std::vector<double> pts_rb;
+    if (dp->host_pts.size() != n * (size_t)d || dp->ordered) {
+        // built on the device, or reordered for the DPX screen since: read the points back
+        pts_rb.resize(n * (size_t)d);
+        CUDA_TRY(cudaMemcpyAsync(pts_rb.data(), dp->pts, n * (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, us));
+        CUDA_TRY(cudaStreamSynchronize(us));
+    }
+    const std::vector<double> &pts = pts_rb.empty() ? dp->host_pts : pts_rb;
     CUDA_TRY(cudaMemsetAsync(dp->wins, 0, n * sizeof(unsigned), us));
     k_probe_argmax<<<(nprobe * 32 + 127) / 128, 128, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, dp->wins);
     CUDA_TRY(cudaGetLastError());
-    std::vector<unsigned> wins(n);
-    std::vector<double> pts(n * (size_t)d);
-    CUDA_TRY(cudaMemcpyAsync(wins.data(), dp->wins, n * sizeof(unsigned), cudaMemcpyDeviceToHost, us));
-    CUDA_TRY(cudaMemcpyAsync(pts.data(), dp->pts, n * (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, us));
-    CUDA_TRY(cudaStreamSynchronize(us));
-    if (dbg) fprintf(stderr, "bp_prepare: probe+d2h %.2f ms\n", now() - t0);
+    if (dbg) fprintf(stderr, "bp_prepare: d2h %.2f ms\n", now() - t0);
     // key map of the point set (the same monotone map as the DPX screen, any d <= 64)
     std::vector<double> qlo(d, INFINITY), qhi(d, -INFINITY), qscale(d, 0.0);
     for (size_t i = 0; i < n; i++)
@@ -1973,6 +1983,10 @@ static int bp_prepare(DevPlan *dp)
     if (dbg) fprintf(stderr, "bp_prepare: kd %.2f ms\n", now() - t0);
     std::vector<unsigned> pos(n);
     for (size_t i = 0; i < n; i++) pos[idx[i]] = (unsigned)i;
+    // (a copy into pageable memory blocks until the probe kernel is done: issued only now, after the kd build)
+    CUDA_TRY(cudaMemcpyAsync(wins.data(), dp->wins, n * sizeof(unsigned), cudaMemcpyDeviceToHost, us));
+    CUDA_TRY(cudaStreamSynchronize(us));               // probe wins are on the host now
+    if (dbg) fprintf(stderr, "bp_prepare: probe wait %.2f ms\n", now() - t0);
     // pivots: the points that won most probes
     // pivots: up to 256, about an eighth of a small set (n=1000: 128 pivots 3.75 Tsp/s, 256 pivots 3.1)
     size_t npiv = std::min<size_t>(n, (size_t)bp_pivot_count());

@@ -23,6 +23,15 @@ def shard_range(nsamples: int, rank: int, world: int) -> Tuple[int, int]:
 SHARD_BLOCK = 1 << 21      # HVB200_SHARD_BLOCK of include/hvapprox_b200.h
 
 
+def shard_block(nsamples: int, world: int) -> int:
+    """Block size used for `world` ranks (hvb200_shard_block): 2^21 directions, halved down to 2^16 until every
+    rank gets at least 4 blocks."""
+    block = SHARD_BLOCK
+    while block > (1 << 16) and block * max(1, world) * 4 > nsamples:
+        block >>= 1
+    return block
+
+
 def shard_blocks(nsamples: int, rank: int, world: int, block: int = SHARD_BLOCK):
     """Block-cyclic shard of `rank`: the index ranges [b*block, min((b+1)*block, nsamples)) for b = rank,
     rank + world, ...  — what hvb200_plan_run_blocks evaluates for (first=rank, stride=world).  Used for

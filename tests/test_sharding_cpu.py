@@ -93,3 +93,14 @@ def test_two_rank_gloo_exchange(oracle, tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert "OK" in res.stdout
+
+
+def test_shard_block_matches_the_library():
+    import ctypes
+    from moocore_b200.sharding import shard_block
+    L = ctypes.CDLL(os.path.join(ROOT, "moocore_b200", "libmoocore_b200.so"))
+    L.hvb200_shard_block.restype = ctypes.c_uint64
+    for N in (1, 1000, 262144, 10**6, 10**8, 2**31):
+        for world in (1, 2, 8, 16):
+            assert shard_block(N, world) == L.hvb200_shard_block(ctypes.c_uint64(N), world)
+            assert (1 << 16) <= shard_block(N, world) <= (1 << 21)
