@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                 bv[r] = -1.0f;
                 bi[r] = 0;
             }
-#pragma unroll 2
+#pragma unroll 4
             for (int i = 0; i < a.n_piv; i++) {
                 const float *pp = piv + i * D;
                 float pk[D];
