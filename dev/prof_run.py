@@ -9,7 +9,7 @@ cfg = sys.argv[3] if len(sys.argv) > 3 else "cfg3"
 i0 = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 c = hvcases.CONFIGS[cfg]
 x, ref, maxi = hvcases.config_inputs(cfg)
-with mb.Plan(x, ref, maxi, kernel=kern) as plan:
+with mb.Plan(x, ref, maxi, kernel=kern, allow_extension=True) as plan:
     for _ in range(2):
         hilo = plan.run(c["method"], c["nsamples"], 0, i0, i0 + cnt)
     st = plan.stats()
