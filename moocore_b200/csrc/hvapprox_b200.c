@@ -358,10 +358,10 @@ int hvb200_rphi_sequence(dimension_t nobjs, uint64_t i0, uint64_t count, double 
    host recurrence costs 5 ns per step and objective and made the reference's DEFAULT method 10-16x slower than
    DZ2019-HW at the default 262144 samples (2.2 ms at d=3, 9.5 ms at d=20 against 0.14 / 0.58 ms).  The prefix
    [0, valid) of the direction set is therefore kept on the device per (device, d), extended on demand from
-   the saved recurrence state, and shared by all later calls.  Bounded (128 MB per entry, 8 entries); a run
+   the saved recurrence state, and shared by all later calls.  Bounded (1 GiB per entry, 8 entries, grown by doubling); a run
    that would not fit streams its directions as before.  HVB200_NO_DIRCACHE=1 disables it. */
 #define RPHI_CACHE_ENTRIES 8
-#define RPHI_CACHE_MAX_BYTES ((uint64_t)128 << 20)
+#define RPHI_CACHE_MAX_BYTES ((uint64_t)1 << 30)
 typedef struct {
     int used, device, d;
     double *dev;                        /* [cap][2][d] */
