@@ -49,3 +49,29 @@ def test_concurrent_calls_match_serial_results(mb):
     for k, (x, method, N, seed) in enumerate(jobs):
         want = mb.hv_approx(x, ref=1.1, nsamples=N, seed=seed, method=method)
         assert got[k] == want, (k, method, x.shape, N)
+
+
+def test_no_device_memory_growth_over_many_calls(mb):
+    # plans come and go through the workspace pool; repeated calls of every kind must not keep allocating
+    import torch
+
+    def burst():
+        rng = np.random.default_rng(3)
+        for i in range(60):
+            d = int(rng.choice([2, 4, 7]))
+            n = int(rng.choice([30, 400, 3000]))
+            x = hvcases.front("sphere", n, d, i)
+            mb.hv_approx(x, ref=1.1, nsamples=int(rng.choice([2000, 80_000, 700_000])), seed=i,
+                         method=["DZ2019-HW", "DZ2019-MC", "Rphi-FWE+"][i % 3])
+        mb.hv_approx_sets([hvcases.front("sphere", 50, 3, k) for k in range(10)], 1.1, nsamples=5000, method="DZ2019-HW")
+        mb.epsilon_additive(rng.random((500, 4)), rng.random((400, 4)))
+        mb.igd_plus(rng.random((500, 4)), rng.random((400, 4)))
+
+    burst()                                   # warm: pools, caches and tables reach their steady size
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(3):
+        burst()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, (free0, free1)
