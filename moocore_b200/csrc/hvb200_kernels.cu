@@ -2938,7 +2938,7 @@ extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
     plan->stats.newton_capped = counters[0];
     plan->stats.slow_path = counters[1];
     if (getenv("HVB200_DEBUG_COUNTERS"))
-        fprintf(stderr, "hvb200 counters: capped=%llu cand=%llu surv=%llu rounds=%llu live=%llu dirs_c=%llu\n", counters[0], counters[1], counters[2], counters[3], counters[4], counters[5]);
+        fprintf(stderr, "hvb200 counters: newton capped=%llu exact evaluations of candidates=%llu\n", counters[0], counters[1]);
     plan->stats.npoints = dp->n;
     plan->stats.kernel = dp->kernel_used == MODE_EXACT ? HVB200_KERNEL_EXACT : (dp->kernel_used == MODE_DPX ? HVB200_KERNEL_DPX : (dp->kernel_used == MODE_BP ? HVB200_KERNEL_BP : HVB200_KERNEL_SCREEN));
     for (const auto &s : dp->spans) {
