@@ -1043,6 +1043,13 @@ __device__ void hw_solve(double target, double u, int m, const double *__restric
         sincos(target, &s_out, &c_out);
         return;
     }
+    if (m == 1) {
+        // F_1(b) = 1 - cos b = t has the closed form cos b = 1 - t, sin b = sqrt(t (2 - t)): exact up to rounding
+        // (1 - t is exact for t >= 0.5, and below that its rounding error is under 1.2e-16 in F)
+        c_out = 1.0 - target;
+        s_out = sqrt(target * (2.0 - target));
+        return;
+    }
     const double HALF_PI = 1.57079632679489661923;
     double x = HALF_PI;
     double sb = 1.0, cb = 6.123233995736766e-17;     // sin, cos of (double)(pi/2)
@@ -1055,6 +1062,39 @@ __device__ void hw_solve(double target, double u, int m, const double *__restric
             const double a = __ldg(row + gi), b = __ldg(row + gi + 1);
             x = a + (b - a) * (g - gi);
             f = fm_eval(m, x, sb, cb) - target;
+            // One evaluation is enough when the start is close: with a = -f/F'(x) the Newton step, the root of
+            //   f + F' e + F'' e^2/2 + F''' e^3/6 + F'''' e^4/24 + ... = 0
+            // is the reverted series e = a - A a^2 + (2A^2 - B) a^3 - (5A^3 - 5AB + C) a^4 + ..., where (q = cot x)
+            //   A = F''/2F' = m q/2,  B = F'''/6F' = (m(m-1) q^2 - m)/6,  C = F''''/24F' = (m(m-1)(m-2) q^3 - m(3m-2) q)/24.
+            // Truncating after a^3 leaves a residual of F' |5A^3 - 5AB + C| a^4 (1 + O(m q a)) in F; when 1.5x that bound
+            // is below the stop rule's tolerance the verifying evaluation of the loop below is skipped, and sin/cos
+            // of x + e come from the rotation by e (Taylor series to e^6, |e| <= 1e-2: truncation < 1e-17).
+#ifndef HVB200_HW_ALWAYS_VERIFY                       // development switch: always run the verifying loop below
+            if (fabs(f) > 1e-15) {
+                const double gm2 = ipow(sb, m - 2);              // m >= 2 on this path
+                const double g = gm2 * sb * sb;
+                const double a = -f / g, aa = fabs(a);
+                const double q = cb / sb, mq = (double)m * q;
+                const double A = 0.5 * mq;
+                const double B = (mq * (double)(m - 1) * q - (double)m) * (1.0 / 6.0);
+                const double C = (mq * (double)((m - 1) * (m - 2)) * q * q - (double)(m * (3 * m - 2)) * q) * (1.0 / 24.0);
+                const double K = fabs(C) + 5.0 * fabs(A) * (A * A + fabs(B));
+                const double a2 = a * a;
+                const double e = a * (1.0 - a * (A - a * (2.0 * A * A - B)));
+                if (aa * (1.0 + fabs(mq)) <= 1e-2 && 1.5 * g * K * a2 * a2 <= 5e-16 && x + e <= HALF_PI) {
+                    const double e2 = e * e;
+                    const double sd = e * (1.0 - e2 * (1.0 / 6.0) * (1.0 - e2 * (1.0 / 20.0)));
+                    const double omc = 0.5 * e2 * (1.0 - e2 * (1.0 / 12.0) * (1.0 - e2 * (1.0 / 30.0)));
+                    s_out = sb + (cb * sd - sb * omc);
+                    c_out = cb - (sb * sd + cb * omc);
+#ifdef HVB200_HW_CHECK                                // development switch: count accepted solves that miss the stop rule
+                    double s2, c2;
+                    if (fabs(fm_eval(m, x + e, s2, c2) - target) > 1e-15 || fabs(s2 - s_out) > 4e-16 || fabs(c2 - c_out) > 4e-16) capped++;
+#endif
+                    return;
+                }
+            }
+#endif
         }
     }
     int it = 0;
