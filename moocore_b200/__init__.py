@@ -23,6 +23,7 @@ from ._api import (  # noqa: F401
     igd,
     igd_plus,
     avg_hausdorff_dist,
+    whv_hype,
     measure_fp64,
 )
 
@@ -43,6 +44,7 @@ __all__ = [
     "igd",
     "igd_plus",
     "avg_hausdorff_dist",
+    "whv_hype",
     "measure_fp64",
 ]
 __version__ = "0.1.0"

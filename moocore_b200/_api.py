@@ -92,6 +92,11 @@ def _load() -> ctypes.CDLL:
         getattr(L, nm).argtypes = [_c_double_p, ctypes.c_size_t, ctypes.c_uint8, _c_double_p, ctypes.c_size_t, _c_u8_p]
     L.avg_Hausdorff_dist.restype = ctypes.c_double
     L.avg_Hausdorff_dist.argtypes = [_c_double_p, ctypes.c_size_t, ctypes.c_uint8, _c_double_p, ctypes.c_size_t, _c_u8_p, ctypes.c_uint]
+    for nm, extra in (("whv_hype_unif", []), ("whv_hype_expo", [ctypes.c_double]), ("whv_hype_gaus", [_c_double_p])):
+        getattr(L, nm).restype = ctypes.c_double
+        getattr(L, nm).argtypes = [_c_double_p, ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, u32] + extra
+    L.hvb200_whv_ordered_sum.restype = ctypes.c_double
+    L.hvb200_whv_ordered_sum.argtypes = [ctypes.POINTER(ctypes.c_uint), ctypes.c_size_t, ctypes.c_int]
     L.hvb200_hv_approx_sets.restype = ctypes.c_int
     L.hvb200_hv_approx_sets.argtypes = [ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.c_uint8,
                                         _c_double_p, _c_u8_p, u64, u32, ctypes.c_int, _c_double_p]
@@ -348,6 +353,40 @@ def avg_hausdorff_dist(points, /, ref, *, maximise: bool | Sequence[bool] = Fals
     if p <= 0:
         raise ValueError("'p' must be larger than zero")
     return _gd_call("avg_Hausdorff_dist", points, ref, maximise, ctypes.c_uint(p))
+
+
+def whv_hype(points, /, *, ref, ideal, maximise: bool | Sequence[bool] = False, nsamples: int = 100000,
+             seed: int | np.random.Generator | None = None, dist: str = "uniform", mu=None) -> float:
+    """HypE Monte-Carlo estimate of the (weighted) hypervolume, 2 objectives (drop-in for ``moocore.whv_hype``,
+    _moocore.py:2767-2912): ``dist`` is ``"uniform"``, ``"exponential"`` (``mu`` a float) or ``"point"`` (``mu`` a
+    goal point).  Bit-identical to the reference for the same seed."""
+    points = np.array(np.asarray(points, dtype=float), order="C", copy=True)
+    if points.ndim != 2:
+        raise ValueError("input points must be a 2-D array")
+    nobj = points.shape[1]
+    if nobj != 2:
+        raise NotImplementedError("Only 2D points are currently supported")
+    ref = np.array(_array_1d_of_length_n(np.asarray(ref, dtype=float), nobj, name="ref"), dtype=float)
+    ideal = np.array(_array_1d_of_length_n(np.asarray(ideal, dtype=float), nobj, name="ideal"), dtype=float)
+    maxi = np.broadcast_to(np.asarray(maximise, dtype=bool), (nobj,))
+    if maxi.any():                                  # _moocore.py:2878-2886: negate the maximised objectives
+        points[:, maxi] = -points[:, maxi]
+        ref[maxi] = -ref[maxi]
+        ideal[maxi] = -ideal[maxi]
+    L = _load()
+    args = (_dp(points), points.shape[0], _dp(ideal), _dp(ref), int(nsamples), _get_seed_for_c(seed))
+    if dist == "uniform":
+        v = L.whv_hype_unif(*args)
+    elif dist == "exponential":
+        v = L.whv_hype_expo(*args, float(mu))
+    elif dist == "point":
+        mu = np.array(_array_1d_of_length_n(np.asarray(mu, dtype=float), nobj, name="mu"), dtype=float)
+        v = L.whv_hype_gaus(*args, _dp(mu))
+    else:
+        raise ValueError(f"Unknown value of dist = {dist}")
+    if v != v and _last_error():
+        raise RuntimeError(f"moocore_b200: CUDA whv_hype failed: {_last_error()}")
+    return float(v)
 
 
 class Plan:

@@ -817,6 +817,128 @@ double avg_Hausdorff_dist(const double *restrict data, size_t npoints, dimension
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* whv_hype: HypE weighted-hypervolume sampling, 2 objectives (c/whv_hype.c, c/whv_hype.h)      */
+/* ------------------------------------------------------------------------------------------ */
+/* estimate_whv's sum (c/whv_hype.c:183-189): for every sample, 1.0/count added count times to ONE running double.
+   Within a binade [2^(e-1), 2^e) every double is a multiple of u = 2^(e-53); if S + inc rounds to S + step and the
+   rounding is not a tie, then S' + inc rounds to S' + step for every S' of that binade, so j additions are the exact
+   sum S + j*step as long as it stays below 2^e.  Ties and binade crossings take literal additions. */
+double hvb200_whv_ordered_sum(const unsigned *counts, size_t nsamples, int naive)
+{
+    double S = 0.0;
+    for (size_t s = 0; s < nsamples; s++) {
+        unsigned left = counts[s];
+        if (!left) continue;
+        const double inc = 1.0 / counts[s];
+        while (!naive && left > 1 && S >= 1.0) {                 /* S >= 1 >= inc */
+            int ex;
+            (void)frexp(S, &ex);
+            const double top = ldexp(1.0, ex), u = ldexp(1.0, ex - 53);
+            const double t = S + inc;
+            const double step = t - S;                           /* exact */
+            unsigned j = 0;
+            if (t < top && fabs(inc - step) != 0.5 * u) {        /* inc - step: the exact rounding error (Fast2Sum) */
+                if (step == 0.0) { left = 0; break; }
+                const double room = (top - S) / step;            /* additions that stay below top, +-1 */
+                j = (room >= (double)left + 2.0) ? left : (room > 2.0 ? (unsigned)(room - 2.0) : 0u);
+            }
+            if (j == 0) { S = t; left--; continue; }
+            S += (double)j * step;                               /* exact: a multiple of u below top */
+            left -= j;
+        }
+        for (; left; left--) S += inc;
+    }
+    return S;
+}
+
+enum { WHV_UNIF, WHV_EXPO, WHV_GAUS };
+
+static double whv_hype_common(int dist, const char *who, const double *points, int npoints, const double *ideal, const double *ref,
+                              int nsamples, uint32_t seed, double mu_expo, const double *mu_gaus)
+{
+    tls_error[0] = 0;
+    if (npoints < 0 || nsamples <= 0 || !ideal || !ref || (npoints > 0 && !points) || (dist == WHV_GAUS && !mu_gaus)) {
+        hvb200_set_error("%s: need npoints >= 0, nsamples > 0 and non-null arguments (npoints=%d, nsamples=%d)", who, npoints, nsamples);
+        return fail_nan(who);
+    }
+    const char *env = getenv("HVB200_DEVICE");
+    const int device = env ? atoi(env) : 0;
+    if (device < 0 || device >= hvb200cu_device_count()) {
+        hvb200_set_error("CUDA device %d not available (%d visible); this library has no CPU fallback", device, hvb200cu_device_count());
+        return fail_nan(who);
+    }
+    /* normalise(): (x - ideal) / (ref - ideal) with a zero range replaced by 1 (c/nondominated.h:878-901, called with
+       the range [0, 1] and all-minimise by normalise01_inplace, c/whv_hype.c:205-212) */
+    double diff[2];
+    for (int k = 0; k < 2; k++) { diff[k] = ref[k] - ideal[k]; if (diff[k] == 0.0) diff[k] = 1.0; }
+    const size_t np = (size_t)npoints, ns = (size_t)nsamples;
+    double *samples = malloc(ns * 2 * sizeof(double));
+    double *pts = malloc((np ? np : 1) * 2 * sizeof(double));
+    unsigned *counts = calloc(ns, sizeof(unsigned));
+    if (!samples || !pts || !counts) {
+        free(samples); free(pts); free(counts);
+        hvb200_set_error("%s: out of memory", who);
+        return fail_nan(who);
+    }
+    mt_stream rng;
+    mt_seed(&rng, seed);
+    const double lower[2] = {0.0, 0.0}, range[2] = {1.0, 1.0};       /* hype_dist_new, c/whv_hype.c:94-107 */
+    if (dist == WHV_UNIF) {                                           /* uniform_dist_sample, :78-92 */
+        for (size_t i = 0; i < ns; i++)
+            for (int k = 0; k < 2; k++) samples[2 * i + k] = lower[k] + mt_unit(&rng) * range[k];
+    } else if (dist == WHV_EXPO) {                                    /* exp_dist_sample, :50-76 */
+        const size_t half = (size_t)(int)(0.5 * nsamples);
+        for (size_t i = 0; i < half; i++) {
+            double x = mt_unit(&rng);
+            samples[2 * i] = lower[0] - mu_expo * log(x);
+            x = mt_unit(&rng);
+            samples[2 * i + 1] = lower[1] + x * range[1];
+        }
+        for (size_t i = half; i < ns; i++) {
+            double x = mt_unit(&rng);
+            samples[2 * i] = lower[0] + x * range[0];
+            x = mt_unit(&rng);
+            samples[2 * i + 1] = lower[1] - mu_expo * log(x);
+        }
+    } else {                                                          /* gaussian_dist_sample, :30-48 */
+        double mu[2];
+        for (int k = 0; k < 2; k++) mu[k] = 0.0 + 1.0 * (mu_gaus[k] - ideal[k]) / diff[k];      /* :288 */
+        const double sigma1 = 0.25, sigma2 = 0.25, rho = 1.0;
+        const double sigma2rho = sigma2 * rho, nu = sigma2 * sqrt(1 - rho * rho);               /* c/rng.c:101-116 */
+        for (size_t i = 0; i < ns; i++) {
+            const double x1 = zig_normal(&rng);
+            samples[2 * i] = mu[0] + x1 * sigma1;
+            samples[2 * i + 1] = mu[1] + x1 * sigma2rho + nu * zig_normal(&rng);
+        }
+    }
+    for (size_t i = 0; i < np; i++)
+        for (int k = 0; k < 2; k++) pts[2 * i + k] = 0.0 + 1.0 * (points[2 * i + k] - ideal[k]) / diff[k];
+    double whv = NAN;
+    if (np == 0 || hvb200cu_whv_counts(device, pts, np, samples, ns, counts) == 0) {
+        whv = hvb200_whv_ordered_sum(counts, ns, 0);
+        double volume = 1.0;                                          /* calculate_volume_between_points, :197-203 */
+        for (int k = 0; k < 2; k++) volume *= (ref[k] - ideal[k]);
+        whv *= volume / nsamples;                                     /* Eq. 18, :236 */
+    }
+    free(samples); free(pts); free(counts);
+    if (whv != whv && tls_error[0]) return fail_nan(who);
+    return whv;
+}
+double whv_hype_unif(const double *points, int npoints, const double *ideal, const double *ref, int nsamples, uint32_t seed)
+{
+    return whv_hype_common(WHV_UNIF, "whv_hype_unif", points, npoints, ideal, ref, nsamples, seed, 0.0, NULL);
+}
+double whv_hype_expo(const double *points, int npoints, const double *ideal, const double *ref, int nsamples, uint32_t seed, double mu)
+{
+    return whv_hype_common(WHV_EXPO, "whv_hype_expo", points, npoints, ideal, ref, nsamples, seed, mu, NULL);
+}
+double whv_hype_gaus(const double *points, int npoints, const double *ideal, const double *ref, int nsamples, uint32_t seed,
+                     const double *mu)
+{
+    return whv_hype_common(WHV_GAUS, "whv_hype_gaus", points, npoints, ideal, ref, nsamples, seed, 0.0, mu);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* single-process multi-GPU                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {

@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include "../../include/hvapprox_b200.h"
 #include "../../include/epsilon_b200.h"
+#include "../../include/whv_hype_b200.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -71,6 +72,9 @@ int hvb200cu_epsilon(int device, int mult, const double *A_host, size_t na, cons
                      const signed char *mm, double *out);
 int hvb200cu_gd_common(int device, const double *X_host, size_t nx, const double *Y_host, size_t ny, int d,
                        const signed char *mm, int plus, int psize, unsigned p, double *result);
+/* whv_hype: per-sample dominator counts (2 objectives; pts and samples are n x 2) */
+int hvb200cu_whv_counts(int device, const double *pts_host, size_t npoints, const double *samples_host, size_t nsamples,
+                        unsigned *counts_host);
 /* cached direction sets */
 int hvb200cu_dev_alloc(int device, size_t bytes, void **out);
 void hvb200cu_dev_free(int device, void *p);

@@ -2749,6 +2749,52 @@ extern "C" int hvb200cu_epsilon(int device, int mult, const double *A_host, size
     return 0;
 }
 
+// ---- HypE weighted-hypervolume sampling, 2 objectives: the dominator counts of estimate_whv (c/whv_hype.c:152-195) ----
+// One thread per sample, the normalised points streamed through shared memory.  A point dominates a sample unless
+// sample[d] < p[d] for some d (the reference's test, :172-176, NaN included); the counts are integers, so any order works.
+constexpr int kWhvTile = 2048;
+__global__ void __launch_bounds__(256) k_whv_counts(const double2 *__restrict__ samples, ull nsamples,
+                                                    const double2 *__restrict__ pts, unsigned npoints, unsigned *__restrict__ counts)
+{
+    __shared__ double2 sp[kWhvTile];
+    const ull s = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s < nsamples;
+    const double2 smp = valid ? samples[s] : make_double2(0.0, 0.0);
+    unsigned cnt = 0;
+    for (unsigned t0 = 0; t0 < npoints; t0 += kWhvTile) {
+        const unsigned tn = min((unsigned)kWhvTile, npoints - t0);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < tn; i += blockDim.x) sp[i] = pts[t0 + i];
+        __syncthreads();
+#pragma unroll 4
+        for (unsigned i = 0; i < tn; i++) {
+            const double2 p = sp[i];
+            cnt += (!(smp.x < p.x) && !(smp.y < p.y)) ? 1u : 0u;
+        }
+    }
+    if (valid) counts[s] = cnt;
+}
+extern "C" int hvb200cu_whv_counts(int device, const double *pts_host, size_t npoints, const double *samples_host, size_t nsamples,
+                                   unsigned *counts_host)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    double2 *P = nullptr, *S = nullptr;
+    unsigned *C = nullptr;
+    int rc = -1;
+    do {
+        if (cudaMalloc(&P, npoints * sizeof(double2)) != cudaSuccess || cudaMalloc(&S, nsamples * sizeof(double2)) != cudaSuccess ||
+            cudaMalloc(&C, nsamples * sizeof(unsigned)) != cudaSuccess) break;
+        if (cudaMemcpy(P, pts_host, npoints * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (cudaMemcpy(S, samples_host, nsamples * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        k_whv_counts<<<(unsigned)((nsamples + 255) / 256), 256>>>(S, (ull)nsamples, P, (unsigned)npoints, C);
+        if (cudaMemcpy(counts_host, C, nsamples * sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc) hvb200_set_error("whv_hype dominator counts: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(P); cudaFree(S); cudaFree(C);
+    return rc;
+}
+
 // ---- generational distances: GD / IGD / IGD+ / averaged Hausdorff (c/igd.h:60-289) -------------------------------
 // gd_common_helper_ (c/igd.h:61-127): for every point a of X the squared distance to the nearest point of Y,
 //     min_y sum_k diff_k^2,  diff_k = a_k - y_k   (plain)   or   max(oriented difference, 0)   ("plus"),

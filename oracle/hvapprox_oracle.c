@@ -652,3 +652,57 @@ double orc_gd_common(const double *pa_, size_t size_a, const double *pr_, size_t
     if (psize) return (double)powl(gd / (double)size_a, 1.0 / p);
     return (double)powl(gd, 1.0 / p) / (double)size_a;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* whv_hype: restatement of c/whv_hype.c (2 objectives).  dist: 0 uniform (:78-92), 1 exponential (:50-76, mu = mu2[0]),
+ * 2 bivariate normal around mu2 (:30-48, c/rng.c:101-116 with sigma 0.25, rho 1).  Samples of the unit square from the
+ * MT19937 stream, points normalised to [ideal, ref] (c/nondominated.h:878-901), estimate_whv's ordered sum (:152-195)
+ * written literally, then Eq. 18 (:236).                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+__attribute__((visibility("default")))
+double orc_whv_hype(int dist, const double *points, int npoints, const double *ideal, const double *ref, int nsamples,
+                    uint32_t seed, const double *mu2)
+{
+    mt_state st;
+    mt_seed(&st, seed);
+    double diff[2];
+    for (int k = 0; k < 2; k++) { diff[k] = ref[k] - ideal[k]; if (diff[k] == 0.0) diff[k] = 1; }
+    double *smp = malloc(sizeof(double) * 2 * (size_t)nsamples);
+    if (dist == 0) {
+        for (int i = 0; i < nsamples; i++)
+            for (int k = 0; k < 2; k++) smp[2 * i + k] = 0.0 + mt_next_double(&st) * 1.0;
+    } else if (dist == 1) {
+        const int half = (int)(0.5 * nsamples);
+        const double mu = mu2[0];
+        for (int i = 0; i < nsamples; i++) {
+            const int expo_axis = i < half ? 0 : 1;
+            for (int k = 0; k < 2; k++) {
+                const double x = mt_next_double(&st);
+                smp[2 * i + k] = (k == expo_axis) ? 0.0 - mu * log(x) : 0.0 + x * 1.0;
+            }
+        }
+    } else {
+        double mu[2];
+        for (int k = 0; k < 2; k++) mu[k] = 0.0 + 1.0 * (mu2[k] - ideal[k]) / diff[k];
+        const double sigma = 0.25, rho = 1.0, nu = sigma * sqrt(1 - rho * rho);
+        for (int i = 0; i < nsamples; i++) {
+            const double x1 = zig_normal(&st);
+            smp[2 * i] = mu[0] + x1 * sigma;
+            smp[2 * i + 1] = mu[1] + x1 * (sigma * rho) + nu * zig_normal(&st);
+        }
+    }
+    double *p2 = malloc(sizeof(double) * 2 * (size_t)(npoints ? npoints : 1));
+    for (int j = 0; j < 2 * npoints; j++) p2[j] = 0.0 + 1.0 * (points[j] - ideal[j & 1]) / diff[j & 1];
+    double whv = 0.0;
+    for (int s = 0; s < nsamples; s++) {
+        unsigned dominated = 0;
+        for (int j = 0; j < npoints; j++)
+            if (!(smp[2 * s] < p2[2 * j]) && !(smp[2 * s + 1] < p2[2 * j + 1])) dominated++;
+        for (unsigned j = 0; j < dominated; j++) whv += 1.0 / dominated;
+    }
+    free(smp); free(p2);
+    double volume = 1.0;
+    for (int k = 0; k < 2; k++) volume *= (ref[k] - ideal[k]);
+    whv *= volume / nsamples;
+    return whv;
+}
