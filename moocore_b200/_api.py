@@ -80,6 +80,8 @@ def _load() -> ctypes.CDLL:
     L.hvb200_plan_destroy.argtypes = [vp]
     L.hvb200_plan_npoints.restype = size_t
     L.hvb200_plan_npoints.argtypes = [vp]
+    L.hvb200_plan_ndominated.restype = size_t
+    L.hvb200_plan_ndominated.argtypes = [vp]
     L.hvb200_plan_set_kernel.restype = ctypes.c_int
     L.hvb200_plan_set_kernel.argtypes = [vp, ctypes.c_int]
     L.hvb200_plan_run.restype = ctypes.c_int
@@ -416,6 +418,11 @@ class Plan:
     @property
     def npoints(self) -> int:
         return 0 if self._h is None else int(_load().hvb200_plan_npoints(self._h))
+
+    @property
+    def ndominated(self) -> int:
+        """Points the nondominated pre-filter removed at plan creation (they cannot change any sample value)."""
+        return 0 if self._h is None else int(_load().hvb200_plan_ndominated(self._h))
 
     def set_kernel(self, kernel: str) -> None:
         if _load().hvb200_plan_set_kernel(self._h, KERNEL_IDS[kernel]) != 0:

@@ -130,6 +130,7 @@ void hvb200_plan_destroy(hvb200_plan *plan)
     free(plan);
 }
 size_t hvb200_plan_npoints(const hvb200_plan *plan) { return plan ? plan->n : 0; }
+size_t hvb200_plan_ndominated(const hvb200_plan *plan) { return plan ? plan->n_dominated : 0; }
 int hvb200_plan_set_kernel(hvb200_plan *plan, int kernel)
 {
     if (kernel < HVB200_KERNEL_AUTO || kernel > HVB200_KERNEL_BP) { hvb200_set_error("bad kernel id %d", kernel); return -2; }

@@ -27,7 +27,8 @@ typedef struct hvb200_hw_params {
 struct hvb200_plan {
     int device;
     int d;                 /* number of objectives                                              */
-    size_t n;              /* n' surviving points                                               */
+    size_t n;              /* n' surviving points (after transform_and_filter and the nondominated filter) */
+    size_t n_dominated;    /* points the nondominated pre-filter removed                        */
     int kernel;            /* requested HVB200_KERNEL_*                                         */
     uint64_t run_samples;  /* size of the run being started (lets the device side amortise one-off work) */
     uint64_t run_total;    /* samples of the run being started, whatever its outputs (sizes per-chunk buffers) */

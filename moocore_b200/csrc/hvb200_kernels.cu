@@ -1322,6 +1322,51 @@ __global__ void __launch_bounds__(256) k_tf_scatter(const double *__restrict__ d
     if (flags[i]) out[(ull)pos[i] * (ull)a.d + k] = a.maxi[k] ? data[w] - a.ref[k] : a.ref[k] - data[w];
     if (w == 0) *kept = (ull)pos[n - 1] + flags[n - 1];
 }
+// ---- nondominated pre-filter: a transformed point q with p_k >= q_k for all k for some other
+// point p can never be the arg-max of max_p min_k p_k r_k (r > 0), so dropping it leaves every sample value — and
+// with the per-chunk sums every bit of the estimate — unchanged.  One thread per q, the set streamed through shared
+// memory; of identical points the first survives.  O(n^2 d) compares with an early exit on the first objective
+// that fails: 0.02 ms at n = 1e4, a few ms at n = 1e5.
+constexpr int kNdThreads = 256;
+constexpr int kNdTileBytes = 32 * 1024;
+__global__ void __launch_bounds__(kNdThreads) k_nd_flags(const double *__restrict__ pts, ull n, int d, int tile, unsigned *__restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sp = reinterpret_cast<double *>(smem_raw);                  // [tile][d]
+    const ull q = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = q < n;
+    double qv[HVB200_MAXD];
+    for (int k = 0; k < d; k++) qv[k] = valid ? pts[q * (ull)d + k] : 0.0;
+    bool dominated = !valid;
+    for (ull t0 = 0; t0 < n; t0 += (ull)tile) {
+        const int tn = (int)min((ull)tile, n - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * d; i += kNdThreads) sp[i] = pts[t0 * (ull)d + i];
+        __syncthreads();
+        if (dominated) continue;
+        for (int j = 0; j < tn; j++) {
+            const double *p = sp + j * d;
+            bool greater = false;
+            int k = 0;
+            for (; k < d; k++) {
+                const double pk = p[k];
+                if (pk < qv[k]) break;
+                greater |= pk > qv[k];
+            }
+            if (k == d && (greater || t0 + (ull)j < q)) { dominated = true; break; }
+        }
+    }
+    if (valid) flags[q] = dominated ? 0u : 1u;
+}
+__global__ void __launch_bounds__(256) k_gather_flagged(const double *__restrict__ src, ull n, int d, const unsigned *__restrict__ flags,
+                                                        const unsigned *__restrict__ pos, double *__restrict__ dst, ull *__restrict__ kept)
+{
+    const ull w = (ull)blockIdx.x * blockDim.x + threadIdx.x;       // element index = point * d + k
+    if (w >= n * (ull)d) return;
+    const ull i = w / (ull)d;
+    if (flags[i]) dst[(ull)pos[i] * (ull)d + (w - i * (ull)d)] = src[w];
+    if (w == 0) *kept = (ull)pos[n - 1] + flags[n - 1];
+}
 // per-objective minimum and maximum of a set of positive coordinates (bit patterns of positive doubles order
 // like unsigned integers): lo initialised to +inf bits, hi to 0
 __global__ void __launch_bounds__(256) k_colrange(const double *__restrict__ pts, ull n, int d, ull *__restrict__ lo, ull *__restrict__ hi)
@@ -1666,28 +1711,16 @@ static bool pool_give(DevPlan *dp)
 }
 
 static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, const double *pts_dev);
-extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host)
+// Scratch of the plan-creation kernels (transform_and_filter, nondominated filter): one cached allocation per device
+// (cudaMalloc/cudaFree cost more than the kernels: 1.3 of 2.1 ms at n = 5e4, d = 20); released again when it grew
+// beyond 256 MB.  Users hold tf_mutex.
+static std::mutex tf_mutex;
+static void *tf_scratch[16] = {nullptr};
+static size_t tf_cap[16] = {0};
+struct TfScratch { double *raw, *out; unsigned *flags, *pos; ull *kept_dev; void *tmp; size_t tmp_bytes; };
+static int tf_scratch_acquire(int device, size_t npoints, int d, TfScratch &sc)
 {
-    return plan_upload_impl(plan, pts_host, nullptr);
-}
-
-// transform_and_filter on the device: raw caller data -> compacted transformed set -> plan.  *kept_out = 0
-// means no point strictly dominates ref (no plan is built: the caller returns 0.0, c/hvapprox.c:228-229).
-extern "C" int hvb200cu_plan_upload_raw(struct hvb200_plan *plan, const double *data_host, size_t npoints,
-                                        const double *ref, const unsigned char *maximise, size_t *kept_out)
-{
-    *kept_out = 0;
-    CUDA_TRY(cudaSetDevice(plan->device));
-    const int d = plan->d;
-    if (npoints == 0) return 0;
-    if (npoints >= 0x7fffffffull) { hvb200_set_error("on-device transform_and_filter supports < 2^31 points"); return -1; }
-    // one cached scratch allocation per device (cudaMalloc/cudaFree cost more than the kernels: 1.3 of 2.1 ms at
-    // n = 5e4, d = 20); released again when it grew beyond 256 MB
-    static std::mutex tf_mutex;
-    static void *tf_scratch[16] = {nullptr};
-    static size_t tf_cap[16] = {0};
-    std::lock_guard<std::mutex> lock(tf_mutex);
-    const int dev = plan->device < 16 ? plan->device : 15;
+    const int dev = device < 16 ? device : 15;
     const size_t elems = npoints * (size_t)d;
     size_t tmp_bytes = 0;
     if (cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr, (int)npoints, (cudaStream_t)0) != cudaSuccess) {
@@ -1700,40 +1733,132 @@ extern "C" int hvb200cu_plan_upload_raw(struct hvb200_plan *plan, const double *
         tf_scratch[dev] = nullptr; tf_cap[dev] = 0;
         if (cudaMalloc(&tf_scratch[dev], need) != cudaSuccess) {
             cudaGetLastError();
-            hvb200_set_error("out of device memory (transform_and_filter, %zu points)", npoints);
+            hvb200_set_error("out of device memory (plan creation scratch, %zu points)", npoints);
             return -1;
         }
         tf_cap[dev] = need;
     }
     unsigned char *base = (unsigned char *)tf_scratch[dev];
-    double *raw = (double *)base;                          base += up(elems * sizeof(double));
-    double *out = (double *)base;                          base += up(elems * sizeof(double));
-    unsigned *flags = (unsigned *)base;                    base += up(npoints * sizeof(unsigned));
-    unsigned *pos = (unsigned *)base;                      base += up(npoints * sizeof(unsigned));
-    ull *kept_dev = (ull *)base;                           base += up(sizeof(ull));
-    void *tmp = (void *)base;
+    sc.raw = (double *)base;                          base += up(elems * sizeof(double));
+    sc.out = (double *)base;                          base += up(elems * sizeof(double));
+    sc.flags = (unsigned *)base;                      base += up(npoints * sizeof(unsigned));
+    sc.pos = (unsigned *)base;                        base += up(npoints * sizeof(unsigned));
+    sc.kept_dev = (ull *)base;                        base += up(sizeof(ull));
+    sc.tmp = (void *)base;
+    sc.tmp_bytes = tmp_bytes;
+    return 0;
+}
+static void tf_scratch_trim(int device)
+{
+    const int dev = device < 16 ? device : 15;
+    if (tf_cap[dev] > ((size_t)256 << 20)) { cudaFree(tf_scratch[dev]); tf_scratch[dev] = nullptr; tf_cap[dev] = 0; }
+}
+
+// HVB200_NDFILTER=0|1 forces the nondominated pre-filter off / on; by default it runs for 512 <= n' <= 2^20 (below,
+// the EXACT kernel reads every point anyway and a launch plus a scan cost more than they save; above, the O(n'^2)
+// pass itself takes seconds).
+static bool nd_filter_wanted(size_t n)
+{
+    const char *env = getenv("HVB200_NDFILTER");
+    if (env && env[0] == '0') return false;
+    if (env && env[0] == '1') return n >= 2 && n < 0x7fffffffull;
+    return n >= 512 && n <= ((size_t)1 << 20);
+}
+// src -> dst (device, n x d rows): the nondominated rows in their original order
+static int nd_filter_device(const TfScratch &sc, const double *src, double *dst, size_t n, int d, size_t *kept_out)
+{
+    int tile = kNdTileBytes / (8 * d);
+    if ((size_t)tile > n) tile = (int)n;
+    ull kept = 0;
+    k_nd_flags<<<(unsigned)((n + kNdThreads - 1) / kNdThreads), kNdThreads, (size_t)tile * d * sizeof(double)>>>(src, (ull)n, d, tile, sc.flags);
+    size_t tmp_bytes = sc.tmp_bytes;
+    bool ok = cub::DeviceScan::ExclusiveSum(sc.tmp, tmp_bytes, sc.flags, sc.pos, (int)n, (cudaStream_t)0) == cudaSuccess;
+    if (ok) {
+        k_gather_flagged<<<(unsigned)((n * (size_t)d + 255) / 256), 256>>>(src, (ull)n, d, sc.flags, sc.pos, dst, sc.kept_dev);
+        ok = cudaMemcpy(&kept, sc.kept_dev, sizeof kept, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (!ok) {
+        hvb200_set_error("nondominated filter failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    *kept_out = (size_t)kept;
+    return 0;
+}
+
+extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host)
+{
+    plan->n_dominated = 0;
+    if (nd_filter_wanted(plan->n)) {
+        CUDA_TRY(cudaSetDevice(plan->device));
+        std::lock_guard<std::mutex> lock(tf_mutex);
+        TfScratch sc;
+        if (tf_scratch_acquire(plan->device, plan->n, plan->d, sc)) return -1;
+        size_t kept = 0;
+        if (cudaMemcpy(sc.raw, pts_host, plan->n * (size_t)plan->d * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            hvb200_set_error("upload of the point set failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return -1;
+        }
+        if (nd_filter_device(sc, sc.raw, sc.out, plan->n, plan->d, &kept)) return -1;
+        int rc;
+        if (kept < plan->n) {
+            plan->n_dominated = plan->n - kept;
+            plan->n = kept;
+            rc = plan_upload_impl(plan, nullptr, sc.out);    // ends with a stream synchronisation: the scratch is free afterwards
+        } else {
+            rc = plan_upload_impl(plan, pts_host, nullptr);
+        }
+        tf_scratch_trim(plan->device);
+        return rc;
+    }
+    return plan_upload_impl(plan, pts_host, nullptr);
+}
+
+// transform_and_filter (c/hvapprox.c:30-66) on the device: flags -> exclusive scan -> scatter, then the
+// nondominated filter; the surviving rows keep the reference's order.
+extern "C" int hvb200cu_plan_upload_raw(struct hvb200_plan *plan, const double *data_host, size_t npoints,
+                                        const double *ref, const unsigned char *maximise, size_t *kept_out)
+{
+    *kept_out = 0;
+    plan->n_dominated = 0;
+    CUDA_TRY(cudaSetDevice(plan->device));
+    const int d = plan->d;
+    if (npoints == 0) return 0;
+    if (npoints >= 0x7fffffffull) { hvb200_set_error("on-device transform_and_filter supports < 2^31 points"); return -1; }
+    std::lock_guard<std::mutex> lock(tf_mutex);
+    TfScratch sc;
+    if (tf_scratch_acquire(plan->device, npoints, d, sc)) return -1;
+    const size_t elems = npoints * (size_t)d;
     int rc = -1;
     ull kept = 0;
     TfArgs a;
     a.d = d;
     for (int k = 0; k < HVB200_MAXD; k++) { a.ref[k] = k < d ? ref[k] : 0.0; a.maxi[k] = k < d ? (maximise[k] ? 1 : 0) : 0; }
     do {
-        if (cudaMemcpy(raw, data_host, elems * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) break;
-        k_tf_flags<<<(unsigned)((npoints + 255) / 256), 256>>>(raw, (ull)npoints, a, flags);
-        if (cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, pos, (int)npoints, (cudaStream_t)0) != cudaSuccess) break;
-        k_tf_scatter<<<(unsigned)((elems + 255) / 256), 256>>>(raw, (ull)npoints, a, flags, pos, out, kept_dev);
-        if (cudaMemcpy(&kept, kept_dev, sizeof kept, cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        if (cudaMemcpy(sc.raw, data_host, elems * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        k_tf_flags<<<(unsigned)((npoints + 255) / 256), 256>>>(sc.raw, (ull)npoints, a, sc.flags);
+        size_t tmp_bytes = sc.tmp_bytes;
+        if (cub::DeviceScan::ExclusiveSum(sc.tmp, tmp_bytes, sc.flags, sc.pos, (int)npoints, (cudaStream_t)0) != cudaSuccess) break;
+        k_tf_scatter<<<(unsigned)((elems + 255) / 256), 256>>>(sc.raw, (ull)npoints, a, sc.flags, sc.pos, sc.out, sc.kept_dev);
+        if (cudaMemcpy(&kept, sc.kept_dev, sizeof kept, cudaMemcpyDeviceToHost) != cudaSuccess) break;
         rc = 0;
     } while (0);
     if (rc) {
         const cudaError_t e = cudaGetLastError();
         hvb200_set_error("on-device transform_and_filter failed: %s", cudaGetErrorString(e));
     } else if (kept) {
-        plan->n = (size_t)kept;
-        rc = plan_upload_impl(plan, nullptr, out);      // ends with a stream synchronisation: `out` is free afterwards
-        *kept_out = (size_t)kept;
+        const double *final_pts = sc.out;
+        if (nd_filter_wanted((size_t)kept)) {
+            size_t kept2 = 0;
+            rc = nd_filter_device(sc, sc.out, sc.raw, (size_t)kept, d, &kept2);
+            if (rc == 0 && kept2 < kept) { plan->n_dominated = (size_t)kept - kept2; kept = kept2; final_pts = sc.raw; }
+        }
+        if (rc == 0) {
+            plan->n = (size_t)kept;
+            rc = plan_upload_impl(plan, nullptr, final_pts);      // ends with a stream synchronisation: the scratch is free afterwards
+            *kept_out = (size_t)kept;
+        }
     }
-    if (tf_cap[dev] > ((size_t)256 << 20)) { cudaFree(tf_scratch[dev]); tf_scratch[dev] = nullptr; tf_cap[dev] = 0; }
+    tf_scratch_trim(plan->device);
     return rc;
 }
 

@@ -16,6 +16,12 @@ from test_parity_gpu import oracle_dirs, oracle_values
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def no_nondominated_prefilter(monkeypatch):
+    # these sets are built from duplicates and dominated points on purpose: keep them in front of the kernel
+    monkeypatch.setenv("HVB200_NDFILTER", "0")
+
+
 def check(mb, oracle, tp, r, n_oracle=300):
     """tp: transformed points (all > 0), r: directions.  exact == pruned everywhere, == oracle on a subsample."""
     tp = np.ascontiguousarray(tp, dtype=float)
