@@ -77,7 +77,8 @@ MOOCORE_API void hvb200_plan_destroy(hvb200_plan *plan);
 MOOCORE_API size_t hvb200_plan_npoints(const hvb200_plan *plan);
 /* Points removed by the nondominated pre-filter at plan creation (a point weakly dominated by another one can never
  * attain max_p min_k p'_k r_k, so the estimate keeps every bit; hvb200_plan_npoints counts the points that remain).
- * Runs for 512 <= n' <= 2^20 by default; HVB200_NDFILTER=0|1 forces it off / on. */
+ * By default it runs for 512 <= n' <= 2^18 when a 256-point sample shows that at least 1/16 of the points are dominated;
+ * HVB200_NDFILTER=0|1 forces it off / on. */
 MOOCORE_API size_t hvb200_plan_ndominated(const hvb200_plan *plan);
 MOOCORE_API int hvb200_plan_set_kernel(hvb200_plan *plan, int kernel);
 

@@ -1326,37 +1326,43 @@ __global__ void __launch_bounds__(256) k_tf_scatter(const double *__restrict__ d
 // point p can never be the arg-max of max_p min_k p_k r_k (r > 0), so dropping it leaves every sample value — and
 // with the per-chunk sums every bit of the estimate — unchanged.  One thread per q, the set streamed through shared
 // memory; of identical points the first survives.  O(n^2 d) compares with an early exit on the first objective
-// that fails: 0.02 ms at n = 1e4, a few ms at n = 1e5.
-constexpr int kNdThreads = 256;
-constexpr int kNdTileBytes = 32 * 1024;
-__global__ void __launch_bounds__(kNdThreads) k_nd_flags(const double *__restrict__ pts, ull n, int d, int tile, unsigned *__restrict__ flags)
+// that fails.
+constexpr int kNdThreads = 128;                 // points q per CTA
+constexpr int kNdTileBytes = 32 * 1024;         // slice of candidate dominators p per CTA
+__global__ void __launch_bounds__(256) k_fill_u32(unsigned *__restrict__ a, ull n, unsigned v)
+{
+    const ull i = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+// grid (q blocks, p slices): CTA (x, y) tests its 128 points q against slice y of the set and clears flags[q] (preset
+// to 1) when a dominator turns up — a single thread walking the whole set is latency-bound (4 ms at n = 1e4).
+// Points q = qi * qstride for qi < qcount, flags indexed by qi (qstride = 1, qcount = n: the whole set; a strided
+// sample first tells whether the full pass is worth its time).
+__global__ void __launch_bounds__(kNdThreads) k_nd_flags(const double *__restrict__ pts, ull n, int d, int tile, unsigned *flags,
+                                                         ull qstride, ull qcount)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sp = reinterpret_cast<double *>(smem_raw);                  // [tile][d]
-    const ull q = (ull)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = q < n;
+    const ull qi = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    const ull q = qi * qstride;
+    const ull t0 = (ull)blockIdx.y * (ull)tile;
+    const int tn = (int)min((ull)tile, n - t0);
+    for (int i = threadIdx.x; i < tn * d; i += kNdThreads) sp[i] = pts[t0 * (ull)d + i];
+    __syncthreads();
+    if (qi >= qcount || flags[qi] == 0u) return;                        // already dominated (benign race: only ever cleared)
     double qv[HVB200_MAXD];
-    for (int k = 0; k < d; k++) qv[k] = valid ? pts[q * (ull)d + k] : 0.0;
-    bool dominated = !valid;
-    for (ull t0 = 0; t0 < n; t0 += (ull)tile) {
-        const int tn = (int)min((ull)tile, n - t0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < tn * d; i += kNdThreads) sp[i] = pts[t0 * (ull)d + i];
-        __syncthreads();
-        if (dominated) continue;
-        for (int j = 0; j < tn; j++) {
-            const double *p = sp + j * d;
-            bool greater = false;
-            int k = 0;
-            for (; k < d; k++) {
-                const double pk = p[k];
-                if (pk < qv[k]) break;
-                greater |= pk > qv[k];
-            }
-            if (k == d && (greater || t0 + (ull)j < q)) { dominated = true; break; }
+    for (int k = 0; k < d; k++) qv[k] = pts[q * (ull)d + k];
+    for (int j = 0; j < tn; j++) {
+        const double *p = sp + j * d;
+        bool greater = false;
+        int k = 0;
+        for (; k < d; k++) {
+            const double pk = p[k];
+            if (pk < qv[k]) break;
+            greater |= pk > qv[k];
         }
+        if (k == d && (greater || t0 + (ull)j < q)) { flags[qi] = 0u; return; }
     }
-    if (valid) flags[q] = dominated ? 0u : 1u;
 }
 __global__ void __launch_bounds__(256) k_gather_flagged(const double *__restrict__ src, ull n, int d, const unsigned *__restrict__ flags,
                                                         const unsigned *__restrict__ pos, double *__restrict__ dst, ull *__restrict__ kept)
@@ -1754,23 +1760,48 @@ static void tf_scratch_trim(int device)
     if (tf_cap[dev] > ((size_t)256 << 20)) { cudaFree(tf_scratch[dev]); tf_scratch[dev] = nullptr; tf_cap[dev] = 0; }
 }
 
-// HVB200_NDFILTER=0|1 forces the nondominated pre-filter off / on; by default it runs for 512 <= n' <= 2^20 (below,
-// the EXACT kernel reads every point anyway and a launch plus a scan cost more than they save; above, the O(n'^2)
-// pass itself takes seconds).
-static bool nd_filter_wanted(size_t n)
+// HVB200_NDFILTER=0|1 forces the nondominated pre-filter off / on.  By default it is considered for 512 <= n' <= 2^18
+// (below, the EXACT kernel reads every point anyway; above, the O(n'^2) pass takes longer than most runs) and runs
+// only if a strided sample of 256 points, tested against the whole set first (0.05 ms), has at least 1/16 of its
+// points dominated: a front gains nothing from the full pass (1.2 ms at n' = 1e4, 73 ms at 1e5, d = 10).
+static int nd_filter_mode(size_t n)        // 0 off, 1 on, 2 decide by sample
 {
     const char *env = getenv("HVB200_NDFILTER");
-    if (env && env[0] == '0') return false;
-    if (env && env[0] == '1') return n >= 2 && n < 0x7fffffffull;
-    return n >= 512 && n <= ((size_t)1 << 20);
+    if (env && env[0] == '0') return 0;
+    if (env && env[0] == '1') return (n >= 2 && n <= ((size_t)1 << 22)) ? 1 : 0;      /* grid.y = n / tile <= 65535 */
+    return (n >= 512 && n <= ((size_t)1 << 18)) ? 2 : 0;
+}
+constexpr int kNdSample = 256;
+static int nd_tile_rows(size_t n, int d)
+{
+    int tile = kNdTileBytes / (8 * d);
+    if (tile > 512) tile = 512;
+    if ((size_t)tile > n) tile = (int)n;
+    return tile;
+}
+// true when the full filter should run on src (device, n x d)
+static bool nd_filter_decide(const TfScratch &sc, const double *src, size_t n, int d)
+{
+    const int mode = nd_filter_mode(n);
+    if (mode != 2) return mode == 1;
+    const int tile = nd_tile_rows(n, d);
+    unsigned host[kNdSample];
+    k_fill_u32<<<1, 256>>>(sc.pos, (ull)kNdSample, 1u);
+    const dim3 grid((kNdSample + kNdThreads - 1) / kNdThreads, (unsigned)((n + tile - 1) / tile));
+    k_nd_flags<<<grid, kNdThreads, (size_t)tile * d * sizeof(double)>>>(src, (ull)n, d, tile, sc.pos, (ull)(n / kNdSample), (ull)kNdSample);
+    if (cudaMemcpy(host, sc.pos, sizeof host, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return false; }
+    int dominated = 0;
+    for (int i = 0; i < kNdSample; i++) dominated += host[i] ? 0 : 1;
+    return dominated * 16 >= kNdSample;
 }
 // src -> dst (device, n x d rows): the nondominated rows in their original order
 static int nd_filter_device(const TfScratch &sc, const double *src, double *dst, size_t n, int d, size_t *kept_out)
 {
-    int tile = kNdTileBytes / (8 * d);
-    if ((size_t)tile > n) tile = (int)n;
+    const int tile = nd_tile_rows(n, d);
     ull kept = 0;
-    k_nd_flags<<<(unsigned)((n + kNdThreads - 1) / kNdThreads), kNdThreads, (size_t)tile * d * sizeof(double)>>>(src, (ull)n, d, tile, sc.flags);
+    k_fill_u32<<<(unsigned)((n + 255) / 256), 256>>>(sc.flags, (ull)n, 1u);
+    const dim3 grid((unsigned)((n + kNdThreads - 1) / kNdThreads), (unsigned)((n + tile - 1) / tile));
+    k_nd_flags<<<grid, kNdThreads, (size_t)tile * d * sizeof(double)>>>(src, (ull)n, d, tile, sc.flags, 1ull, (ull)n);
     size_t tmp_bytes = sc.tmp_bytes;
     bool ok = cub::DeviceScan::ExclusiveSum(sc.tmp, tmp_bytes, sc.flags, sc.pos, (int)n, (cudaStream_t)0) == cudaSuccess;
     if (ok) {
@@ -1788,7 +1819,7 @@ static int nd_filter_device(const TfScratch &sc, const double *src, double *dst,
 extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host)
 {
     plan->n_dominated = 0;
-    if (nd_filter_wanted(plan->n)) {
+    if (nd_filter_mode(plan->n)) {
         CUDA_TRY(cudaSetDevice(plan->device));
         std::lock_guard<std::mutex> lock(tf_mutex);
         TfScratch sc;
@@ -1798,7 +1829,8 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
             hvb200_set_error("upload of the point set failed: %s", cudaGetErrorString(cudaGetLastError()));
             return -1;
         }
-        if (nd_filter_device(sc, sc.raw, sc.out, plan->n, plan->d, &kept)) return -1;
+        kept = plan->n;
+        if (nd_filter_decide(sc, sc.raw, plan->n, plan->d) && nd_filter_device(sc, sc.raw, sc.out, plan->n, plan->d, &kept)) return -1;
         int rc;
         if (kept < plan->n) {
             plan->n_dominated = plan->n - kept;
@@ -1847,7 +1879,7 @@ extern "C" int hvb200cu_plan_upload_raw(struct hvb200_plan *plan, const double *
         hvb200_set_error("on-device transform_and_filter failed: %s", cudaGetErrorString(e));
     } else if (kept) {
         const double *final_pts = sc.out;
-        if (nd_filter_wanted((size_t)kept)) {
+        if (nd_filter_decide(sc, sc.out, (size_t)kept, d)) {
             size_t kept2 = 0;
             rc = nd_filter_device(sc, sc.out, sc.raw, (size_t)kept, d, &kept2);
             if (rc == 0 && kept2 < kept) { plan->n_dominated = (size_t)kept - kept2; kept = kept2; final_pts = sc.raw; }
