@@ -1001,17 +1001,49 @@ __device__ __forceinline__ double x87_mul_frac(X87Val f, ull a)
 
 // F_m(b) = int_0^b sin^m via the reduction formula (same restatement as the oracle):
 //   even m: lead*b - cos*sin*H(sin^2);  odd m: lead*(1-cos) - cos*sin^2*H(sin^2)
+// sin and cos for the first quadrant, where every angle of the solve lives: reflect to [0, pi/4] about pi/4 and
+// evaluate the two minimax kernels of that interval (the classic fdlibm coefficients, < 1 ulp) with explicit FMAs.
+// No quadrant bookkeeping, no large-argument path: a third of the library call's instructions.
+#ifndef HVB200_HW_LIBM_SINCOS
+__device__ __forceinline__ void sincos_q1(double x, double *s, double *c)
+{
+    if (!(x >= 0.0 && x <= 1.5707963267948966192)) { sincos(x, s, c); return; }
+    const bool refl = x > 0.78539816339744830962;
+    const double y = refl ? (1.5707963267948966192 - x) + 6.123233995736766e-17 : x;
+    const double z = y * y;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double sy = fma(y * z, ps, y);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double hz = 0.5 * z;
+    const double w = 1.0 - hz;
+    const double cy = w + (((1.0 - w) - hz) + z * z * pc);
+    *s = refl ? cy : sy;
+    *c = refl ? sy : cy;
+}
+#else
+__device__ __forceinline__ void sincos_q1(double x, double *s, double *c) { sincos(x, s, c); }
+#endif
 __device__ __forceinline__ double fm_eval(int m, double b, double &sb, double &cb)
 {
-    sincos(b, &sb, &cb);
+    sincos_q1(b, &sb, &cb);
     if (m == 0) return b;
     if (m == 1) return 1.0 - cb;
     const double s2 = sb * sb;
     const int nh = c_fm_nh[m];
     double H = c_fm_h[m][nh - 1];
-    for (int t = nh - 2; t >= 0; t--) H = H * s2 + c_fm_h[m][t];
-    if (m & 1) return c_fm_lead[m] * (1.0 - cb) - cb * s2 * H;
-    return c_fm_lead[m] * b - cb * sb * H;
+    for (int t = nh - 2; t >= 0; t--) H = fma(H, s2, c_fm_h[m][t]);
+    if (m & 1) return fma(c_fm_lead[m], 1.0 - cb, -(cb * s2) * H);
+    return fma(c_fm_lead[m], b, -(cb * sb) * H);
 }
 __device__ __forceinline__ double ipow(double x, int e)
 {
@@ -1034,13 +1066,13 @@ __device__ void hw_solve(double target, double u, int m, const double *__restric
                          double &s_out, double &c_out, unsigned &capped)
 {
     if (target == 0.0 && m < 32 && c_theta0_bits[m] != ~0ull) {
-        sincos(__longlong_as_double((long long)c_theta0_bits[m]), &s_out, &c_out);
+        sincos_q1(__longlong_as_double((long long)c_theta0_bits[m]), &s_out, &c_out);
         return;
     }
     if (m == 0) {
         // F_0(b) = b: the reference's single Newton step x = pi/2 - (pi/2 - t) returns t up to a
         // long double rounding (1e-19); in FP64 the same step would lose t below 1e-16 absolute.
-        sincos(target, &s_out, &c_out);
+        sincos_q1(target, &s_out, &c_out);
         return;
     }
     if (m == 1) {
@@ -1071,22 +1103,24 @@ __device__ void hw_solve(double target, double u, int m, const double *__restric
             // of x + e come from the rotation by e (Taylor series to e^6, |e| <= 1e-2: truncation < 1e-17).
 #ifndef HVB200_HW_ALWAYS_VERIFY                       // development switch: always run the verifying loop below
             if (fabs(f) > 1e-15) {
+                // one division: t = a / sin x, so that A a = (m/2) v, B a^2 = (m(m-1) v^2 - m a^2)/6,
+                // C a^3 = (m(m-1)(m-2) v^3 - m(3m-2) v a^2)/24 with v = t cos x — no cot x needed
                 const double gm2 = ipow(sb, m - 2);              // m >= 2 on this path
                 const double g = gm2 * sb * sb;
-                const double a = -f / g, aa = fabs(a);
-                const double q = cb / sb, mq = (double)m * q;
-                const double A = 0.5 * mq;
-                const double B = (mq * (double)(m - 1) * q - (double)m) * (1.0 / 6.0);
-                const double C = (mq * (double)((m - 1) * (m - 2)) * q * q - (double)(m * (3 * m - 2)) * q) * (1.0 / 24.0);
-                const double K = fabs(C) + 5.0 * fabs(A) * (A * A + fabs(B));
-                const double a2 = a * a;
-                const double e = a * (1.0 - a * (A - a * (2.0 * A * A - B)));
-                if (aa * (1.0 + fabs(mq)) <= 1e-2 && 1.5 * g * K * a2 * a2 <= 5e-16 && x + e <= HALF_PI) {
+                const double t = -f / (g * sb);
+                const double a = t * sb, v = t * cb, md = (double)m;
+                const double u = 0.5 * md * v, v2 = v * v, a2 = a * a;
+                const double mm1 = md * (md - 1.0);
+                const double Ba2 = fma(mm1, v2, -md * a2) * (1.0 / 6.0);
+                const double Ca3 = v * fma(mm1 * (md - 2.0), v2, -md * fma(3.0, md, -2.0) * a2) * (1.0 / 24.0);
+                const double e = a * (fma(u, fma(2.0, u, -1.0), 1.0) - Ba2);
+                const double bound = 1.5 * g * fabs(a) * (fabs(Ca3) + 5.0 * fabs(u) * fma(u, u, fabs(Ba2)));
+                if (fabs(a) + md * fabs(v) <= 1e-2 && bound <= 5e-16 && x + e <= HALF_PI) {
                     const double e2 = e * e;
-                    const double sd = e * (1.0 - e2 * (1.0 / 6.0) * (1.0 - e2 * (1.0 / 20.0)));
-                    const double omc = 0.5 * e2 * (1.0 - e2 * (1.0 / 12.0) * (1.0 - e2 * (1.0 / 30.0)));
-                    s_out = sb + (cb * sd - sb * omc);
-                    c_out = cb - (sb * sd + cb * omc);
+                    const double sd = e * fma(e2 * fma(e2, -1.0 / 20.0, 1.0), -1.0 / 6.0, 1.0);
+                    const double omc = 0.5 * e2 * fma(e2 * fma(e2, -1.0 / 30.0, 1.0), -1.0 / 12.0, 1.0);
+                    s_out = sb + fma(cb, sd, -sb * omc);
+                    c_out = cb - fma(sb, sd, cb * omc);
 #ifdef HVB200_HW_CHECK                                // development switch: count accepted solves that miss the stop rule
                     double s2, c2;
                     if (fabs(fm_eval(m, x + e, s2, c2) - target) > 1e-15 || fabs(s2 - s_out) > 4e-16 || fabs(c2 - c_out) > 4e-16) capped++;
@@ -1129,41 +1163,67 @@ __global__ void __launch_bounds__(128) k_hw_table_init(double *__restrict__ tab,
     tab[idx] = theta;
 }
 
+// The rows of a warp's 32 samples are contiguous in `dirs` (32 x 2d doubles), but a thread writing its own row stores
+// with a stride of 2d doubles: 32 L1 tag cycles per store instruction, 20 of them per sample at d = 10 — the L1 tag stage,
+// not the arithmetic, bounded the kernel (18 % fewer instructions changed nothing).  Rows are staged in shared memory
+// (row stride 2d + 1 doubles: conflict-free) and the warp copies its block out with coalesced stores.
+// Measured (2e7 directions): staged 3.38 vs 3.6-3.8 ms at d = 10, but slower for d <= 6 (the copy loop outweighs
+// six stores) and for d >= 16 (the staging buffer costs occupancy), so STAGED is used for 7 <= d <= 12 only.
+template <bool STAGED>
 __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count, double *__restrict__ dirs,
                                                 ull *capped_counter, const double *__restrict__ tab, int ntab)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d = P.d, row_len = 2 * d, row_stride = 2 * d + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *wrows = reinterpret_cast<double *>(smem_raw) + (size_t)warp * 32 * row_stride;
     const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    const int d = P.d;
-    const ull idx1 = i0 + j + 1;                    // i + 1
-    const bool last = !(idx1 < P.N);                // last sample: all zeros (c/hvapprox.c:300-303)
-    X87Val fac;
-    if (!last) fac = x87_div(idx1, P.N, P.Nrecip);
-    double *out = dirs + j * (ull)(2 * d);
     unsigned capped = 0;
-    double prod = 1.0;
-    for (int q = 0; q < d - 1; q++) {
-        const int m = d - 2 - q;
-        const double u = last ? 0.0 : x87_mul_frac(fac, P.a[q]);
-        double s, c;
-        hw_solve(u * c_Im[m], u, m, tab, ntab, s, c, capped);
-        // w_{d-1} = c_0; w_{d-1-q} = (s_0..s_{q-1}) c_q; w_0 = s_0..s_{d-2}  (c/hvapprox.c:632-638)
-        const double w = (q == 0) ? c : prod * c;
-        prod = (q == 0) ? s : s * prod;
-        const double r = (fabs(w) <= 1e-20) ? 1e20 : 1.0 / w;
-        double wi = 1.0 / r;
-        out[d - 1 - q] = r;
-        out[d + d - 1 - q] = (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;
+    if (j < count) {
+        const ull idx1 = i0 + j + 1;                    // i + 1
+        const bool last = !(idx1 < P.N);                // last sample: all zeros (c/hvapprox.c:300-303)
+        X87Val fac;
+        if (!last) fac = x87_div(idx1, P.N, P.Nrecip);
+        double *out = STAGED ? wrows + lane * row_stride : dirs + j * (ull)row_len;
+        double prod = 1.0;
+        for (int q = 0; q < d - 1; q++) {
+            const int m = d - 2 - q;
+            const double u = last ? 0.0 : x87_mul_frac(fac, P.a[q]);
+            double s, c;
+            hw_solve(u * c_Im[m], u, m, tab, ntab, s, c, capped);
+            // w_{d-1} = c_0; w_{d-1-q} = (s_0..s_{q-1}) c_q; w_0 = s_0..s_{d-2}  (c/hvapprox.c:632-638)
+            const double w = (q == 0) ? c : prod * c;
+            prod = (q == 0) ? s : s * prod;
+            const double r = (fabs(w) <= 1e-20) ? 1e20 : 1.0 / w;
+            double wi = 1.0 / r;
+            out[d - 1 - q] = r;
+            out[d + d - 1 - q] = (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;
+        }
+        {
+            const double w = prod;
+            const double r = (fabs(w) <= 1e-20) ? 1e20 : 1.0 / w;
+            double wi = 1.0 / r;
+            out[0] = r;
+            out[d] = (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;
+        }
     }
-    {
-        const double w = prod;
-        const double r = (fabs(w) <= 1e-20) ? 1e20 : 1.0 / w;
-        double wi = 1.0 / r;
-        out[0] = r;
-        out[d] = (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;
+    __syncwarp();
+    const ull wfirst = (ull)blockIdx.x * blockDim.x + (ull)warp * 32;      // first sample of this warp
+    if (STAGED && wfirst < count) {
+        const int rows = (int)min((ull)32, count - wfirst);
+        double *dst = dirs + wfirst * (ull)row_len;
+        int row = 0, col = lane;
+        while (col >= row_len) { col -= row_len; row++; }
+        for (int idx = lane; idx < rows * row_len; idx += 32) {
+            dst[idx] = wrows[row * row_stride + col];
+            col += 32;
+            while (col >= row_len) { col -= row_len; row++; }
+        }
     }
     if (capped) atomicAdd(capped_counter, (ull)capped);
 }
+static bool gen_hw_staged(int d) { return d >= 7 && d <= 12; }
+static int gen_hw_smem_bytes(int d) { return gen_hw_staged(d) ? 128 * (2 * d + 1) * (int)sizeof(double) : 0; }
 
 __device__ __forceinline__ double safe_winv(double r)
 {
@@ -2520,7 +2580,8 @@ extern "C" int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_para
     P.d = hw->d;
     for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
     const int b = span_begin(dp, 1);
-    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(P, i0, count, dp->dirs + offset * (uint64_t)(2 * hw->d), dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
+    if (gen_hw_staged(hw->d)) k_gen_hw<true><<<(unsigned)((count + 127) / 128), 128, gen_hw_smem_bytes(hw->d), dp->stream>>>(P, i0, count, dp->dirs + offset * (uint64_t)(2 * hw->d), dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
+    else k_gen_hw<false><<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(P, i0, count, dp->dirs + offset * (uint64_t)(2 * hw->d), dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
     plan->stats.dirgen_launches++;
@@ -2566,7 +2627,8 @@ extern "C" int hvb200cu_hw_prefetch(struct hvb200_plan *plan, const hvb200_hw_pa
     P.d = hw->d;
     for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
     const int b = span_begin_on(dp, 1, dp->gen_stream);
-    k_gen_hw<<<(unsigned)((count + 127) / 128), 128, 0, dp->gen_stream>>>(P, i0, count, dp->dirs_buf[buf], dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
+    if (gen_hw_staged(hw->d)) k_gen_hw<true><<<(unsigned)((count + 127) / 128), 128, gen_hw_smem_bytes(hw->d), dp->gen_stream>>>(P, i0, count, dp->dirs_buf[buf], dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
+    else k_gen_hw<false><<<(unsigned)((count + 127) / 128), 128, 0, dp->gen_stream>>>(P, i0, count, dp->dirs_buf[buf], dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
     if (b >= 0) cudaEventRecord(dp->ev_pool[b], dp->gen_stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(dp->ev_gen[buf], dp->gen_stream));
