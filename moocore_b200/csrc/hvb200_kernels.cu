@@ -1779,8 +1779,9 @@ static bool pool_give(DevPlan *dp)
 static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, const double *pts_dev);
 // Scratch of the plan-creation kernels (transform_and_filter, nondominated filter): one cached allocation per device
 // (cudaMalloc/cudaFree cost more than the kernels: 1.3 of 2.1 ms at n = 5e4, d = 20); released again when it grew
-// beyond 256 MB.  Users hold tf_mutex.
-static std::mutex tf_mutex;
+// beyond 256 MB.  Users hold the device's tf_mutex (one per device: plans for different GPUs are built concurrently by
+// hvb200_hv_approx_multi).
+static std::mutex tf_mutex[16];
 static void *tf_scratch[16] = {nullptr};
 static size_t tf_cap[16] = {0};
 struct TfScratch { double *raw, *out; unsigned *flags, *pos; ull *kept_dev; void *tmp; size_t tmp_bytes; };
@@ -1881,7 +1882,7 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
     plan->n_dominated = 0;
     if (nd_filter_mode(plan->n)) {
         CUDA_TRY(cudaSetDevice(plan->device));
-        std::lock_guard<std::mutex> lock(tf_mutex);
+        std::lock_guard<std::mutex> lock(tf_mutex[plan->device < 16 ? plan->device : 15]);
         TfScratch sc;
         if (tf_scratch_acquire(plan->device, plan->n, plan->d, sc)) return -1;
         size_t kept = 0;
@@ -1916,7 +1917,7 @@ extern "C" int hvb200cu_plan_upload_raw(struct hvb200_plan *plan, const double *
     const int d = plan->d;
     if (npoints == 0) return 0;
     if (npoints >= 0x7fffffffull) { hvb200_set_error("on-device transform_and_filter supports < 2^31 points"); return -1; }
-    std::lock_guard<std::mutex> lock(tf_mutex);
+    std::lock_guard<std::mutex> lock(tf_mutex[plan->device < 16 ? plan->device : 15]);
     TfScratch sc;
     if (tf_scratch_acquire(plan->device, npoints, d, sc)) return -1;
     const size_t elems = npoints * (size_t)d;
