@@ -41,14 +41,27 @@ def env_int(name, default):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own code (oracle/_ref) or, failing that, the oracle port
 # ------------------------------------------------------------------------------------------------
-def load_cpu_impl():
-    """Returns (kind, window_fn(tp, d, N, i0, cnt) -> sum).  TEST/BASELINE use of oracle/ only."""
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown CPU"
+
+
+def load_cpu_impl(method, d):
+    """Returns (kind, flags, window_fn(tp, d, N, seed, i0, cnt) -> sum).  TEST/BASELINE use of oracle/ only.
+    The window entry point follows the config's method (HW / MC / Rphi windows of oracle/ref_shim.c); d > 31 is
+    outside the reference's domain and needs the patched d <= 64 build (oracle/patch_ref_d64.py)."""
     dp = ctypes.POINTER(ctypes.c_double)
-    for kind, path, sym in (
-        ("reference", os.path.join(ROOT, "oracle", "_ref", "libhvref_fast.so"), "ref_hw_window"),
-        ("reference", os.path.join(ROOT, "oracle", "_ref", "libhvref.so"), "ref_hw_window"),
-        ("port", os.path.join(ROOT, "oracle", "libhvoracle.so"), "orc_hw_window"),
-    ):
+    suffix = {"DZ2019-HW": "hw_window", "DZ2019-MC": "mc_window", "Rphi-FWE+": "rphi_window"}[method]
+    ref_libs = (("libhvref_d64_fast.so", "-O3 -march=x86-64-v3, patched to d <= 64"), ("libhvref_d64.so", "-O3 -march=x86-64-v2, patched to d <= 64")) if d > 31 else \
+               (("libhvref_fast.so", "-O3 -march=x86-64-v3"), ("libhvref.so", "-O3 -march=x86-64-v2"))
+    cands = [("reference", os.path.join(ROOT, "oracle", "_ref", nm), "ref_" + suffix, fl) for nm, fl in ref_libs]
+    cands.append(("port", os.path.join(ROOT, "oracle", "libhvoracle.so"), "orc_" + suffix, "-O2 -march=x86-64-v2"))
+    for kind, path, sym, flags in cands:
         if not os.path.exists(path):
             continue
         try:
@@ -58,21 +71,25 @@ def load_cpu_impl():
         fn = getattr(L, sym)
         fn.restype = ctypes.c_double
 
-        def window(tp, d, N, i0, cnt, fn=fn):
-            return fn(tp.ctypes.data_as(dp), ctypes.c_size_t(tp.shape[0]), ctypes.c_int(d), ctypes.c_uint64(N),
-                      ctypes.c_uint64(i0), ctypes.c_uint64(cnt), None)
+        def window(tp, d, N, seed, i0, cnt, fn=fn):
+            a = (tp.ctypes.data_as(dp), ctypes.c_size_t(tp.shape[0]), ctypes.c_int(d))
+            if method == "DZ2019-HW":
+                return fn(*a, ctypes.c_uint64(N), ctypes.c_uint64(i0), ctypes.c_uint64(cnt), None)
+            if method == "DZ2019-MC":       # the stream is sequential: every thread evaluates the window [0, cnt)
+                return fn(*a, ctypes.c_uint32(seed), ctypes.c_uint64(0), ctypes.c_uint64(cnt), None, None)
+            return fn(*a, ctypes.c_uint64(0), ctypes.c_uint64(cnt), None, None, None)
 
-        return kind, window
+        return kind, flags, window
     raise RuntimeError("no CPU baseline library: run `make -C oracle` first")
 
 
-def cpu_throughput(tp, d, N, threads, samples_per_thread, i_base=0):
+def cpu_throughput(tp, c, threads, samples_per_thread, i_base=0):
     """sample*points/s of the CPU implementation with `threads` host threads (ctypes drops the GIL)."""
-    kind, window = load_cpu_impl()
+    kind, flags, window = load_cpu_impl(c["method"], c["d"])
     sums = [0.0] * threads
 
     def work(t):
-        sums[t] = window(tp, d, N, i_base + t * samples_per_thread, samples_per_thread)
+        sums[t] = window(tp, c["d"], c["nsamples"], c["seed"], i_base + t * samples_per_thread, samples_per_thread)
 
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
     t0 = time.perf_counter()
@@ -81,7 +98,13 @@ def cpu_throughput(tp, d, N, threads, samples_per_thread, i_base=0):
     for t in ths:
         t.join()
     dt = time.perf_counter() - t0
-    return kind, threads * samples_per_thread * tp.shape[0] / dt, dt
+    return kind, flags, threads * samples_per_thread * tp.shape[0] / dt, dt
+
+
+def sample_desc(c, count, threads):
+    if c["method"] == "DZ2019-HW":
+        return f"DZ2019-HW window of {count} directions of the N={c['nsamples']} lattice per step, split over {threads} thread(s)"
+    return f"the first {count // threads} {c['method']} directions of the stream (seed {c['seed']}) on each of {threads} thread(s)"
 
 
 def run_reference_arm(args, rank, world):
@@ -92,14 +115,14 @@ def run_reference_arm(args, rank, world):
     tp = hvcases.transformed(x, ref, maxi)
     d, N = c["d"], c["nsamples"]
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # bounded sample: ~2 s of work per thread per step
-    spt = max(64, int(2.0 * 0.4e9 / tp.shape[0]))
+    # bounded sample: ~2 s of work per thread per step (0.4e9 point*dim*10 evaluations per second and core at d = 10)
+    spt = max(16, int(2.0 * 0.4e9 * 10 / (tp.shape[0] * d)))
     for _ in range(args.warmup):
-        cpu_throughput(tp, d, N, cores, max(16, spt // 8))
+        cpu_throughput(tp, c, cores, max(8, spt // 8))
     t_total, units = 0.0, 0.0
-    kind = "port"
+    kind, flags = "port", ""
     for s in range(args.steps):
-        kind, thr, dt = cpu_throughput(tp, d, N, cores, spt, i_base=s * cores * spt)
+        kind, flags, thr, dt = cpu_throughput(tp, c, cores, spt, i_base=s * cores * spt)
         t_total += dt
         units += cores * spt * tp.shape[0]
     value = units / t_total / 1e9
@@ -109,8 +132,8 @@ def run_reference_arm(args, rank, world):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config), "sample": f"{cores * spt} of {N} directions per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"DZ2019-HW window of {cores * spt} directions of the N={N} lattice per step, "
-                                   f"split over {cores} threads (reference code is single-threaded; -O3 -march=x86-64-v3)"},
+                         "sample": f"{sample_desc(c, cores * spt, cores)}; {cpu_model()}, {cores} host threads "
+                                   f"(the reference code is single-threaded; built {flags})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -129,8 +152,9 @@ def reference_rel_error(cfg, estimate):
 
 def workload_name(cfg):
     c = hvcases.CONFIGS[cfg]
-    return (f"{cfg}: hv_approx {c['method']} d={c['d']} n={c['n']} {c['kind']} front nsamples={c['nsamples']:.0e} "
-            f"ref=1.1 minimise")
+    objs = "ref=1.1 minimise" if cfg != "cfg5" else "every third objective maximised (ref -0.1), the others minimised (ref 1.1)"
+    seed = f" seed={c['seed']}" if c["method"] == "DZ2019-MC" else ""
+    return f"{cfg}: hv_approx {c['method']}{seed} d={c['d']} n={c['n']} {c['kind']} front nsamples={c['nsamples']:.0e} {objs}"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -211,7 +235,7 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg: `value` ----------------
-    plan = mb.Plan(x, ref, maxi, device=local_rank, kernel=args.kernel)
+    plan = mb.Plan(x, ref, maxi, device=local_rank, kernel=args.kernel, allow_extension=d > 31)
     npts = plan.npoints
     stream = torch.cuda.current_stream().cuda_stream
     result = {}
@@ -259,7 +283,7 @@ def run_ours(args, rank, local_rank, world):
     # ---------------- end-to-end leg: host buffers through the C-ABI each step ----------------
     def step_e2e():
         hilo = mb.hv_approx_shard(x, ref, maximise=maxi, nsamples=N, seed=seed, method=method, rank=rank, world=world,
-                                  device=local_rank, stream=stream)
+                                  device=local_rank, stream=stream, allow_extension=d > 31)
         flat = gather_partials(hilo, device=dev)
         return mb.hv_approx_finalize(d, N, flat)
 
@@ -327,14 +351,14 @@ def run_ours(args, rank, local_rank, world):
             pass
         # CPU baseline: bounded sample of the same workload on 1 host core (N=1 runs only)
         tp = hvcases.transformed(x, ref, maxi)
-        spt = max(64, int(12.0 * 0.4e9 / tp.shape[0]))
+        spt = max(16, int(12.0 * 0.4e9 * 10 / (tp.shape[0] * d)))
         try:
             if world > 1:
                 raise RuntimeError("cpu_baseline is timed at N=1 only")
-            kind, thr, dt = cpu_throughput(tp, d, N, 1, spt)
+            kind, flags, thr, dt = cpu_throughput(tp, c, 1, spt)
             cpu = {"value": thr / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
-                   "sample": f"first {spt} of the N={N} DZ2019-HW directions, {dt:.1f} s on 1 host core "
-                             f"(the reference is single-threaded)"}
+                   "sample": f"{sample_desc(c, spt, 1)}, {dt:.1f} s on 1 core of {cpu_model()} "
+                             f"(the reference is single-threaded; built {flags})"}
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         line = {

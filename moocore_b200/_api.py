@@ -263,6 +263,8 @@ def hv_approx_sets(
     if isinstance(sets, tuple) and len(sets) == 2 and np.ndim(sets[1]) == 1 and np.ndim(sets[0]) == 2:
         data = np.ascontiguousarray(sets[0], dtype=float)
         cum = np.ascontiguousarray(sets[1], dtype=np.uint64)
+        if cum.size and (np.any(np.diff(cum.astype(np.int64)) < 0) or int(cum[-1]) > data.shape[0]):
+            raise ValueError("cumsizes must be non-decreasing and its last entry at most the number of rows of data")
     else:
         arrs = [np.ascontiguousarray(a, dtype=float) for a in sets]
         if not arrs:
@@ -425,6 +427,10 @@ class Plan:
         return 0 if self._h is None else int(_load().hvb200_plan_ndominated(self._h))
 
     def set_kernel(self, kernel: str) -> None:
+        if kernel not in KERNEL_IDS:
+            raise ValueError(f"Unknown kernel = {kernel}")
+        if self._h is None:
+            return
         if _load().hvb200_plan_set_kernel(self._h, KERNEL_IDS[kernel]) != 0:
             raise RuntimeError(_last_error())
 
@@ -472,6 +478,8 @@ class Plan:
         r = np.ascontiguousarray(r, dtype=np.float64)
         assert r.ndim == 2 and r.shape[1] == self.nobj
         vals = np.zeros(r.shape[0], dtype=np.float64) if want_values else None
+        if self._h is None:
+            return vals, (0.0, 0.0)
         out = (ctypes.c_double * 2)()
         rc = _load().hvb200_plan_run_directions(self._h, _dp(r), r.shape[0], _dp(vals) if want_values else None, out)
         if rc != 0:
@@ -514,11 +522,11 @@ def hv_approx_range(points, ref, *, maximise=False, nsamples: int, seed: int = 0
 
 
 def hv_approx_shard(points, ref, *, maximise=False, nsamples: int, seed: int = 0, method: str, rank: int, world: int,
-                    device: int = 0, stream: int | None = None):
+                    device: int = 0, stream: int | None = None, allow_extension: bool = False):
     """Shard `rank` of `world` of an estimate as a (hi, lo) partial sum: block-cyclic for DZ2019-HW (balanced),
     a contiguous range for the sequential MC and Rphi streams."""
     from .sharding import shard_block, shard_range
-    with Plan(points, ref, maximise, device=device) as plan:
+    with Plan(points, ref, maximise, device=device, allow_extension=allow_extension) as plan:
         if method == "DZ2019-HW" and world > 1:
             return plan.run_blocks(method, nsamples, rank, world, block=shard_block(nsamples, world), seed=seed, stream=stream)
         i0, i1 = shard_range(nsamples, rank, world)

@@ -133,12 +133,14 @@ size_t hvb200_plan_npoints(const hvb200_plan *plan) { return plan ? plan->n : 0;
 size_t hvb200_plan_ndominated(const hvb200_plan *plan) { return plan ? plan->n_dominated : 0; }
 int hvb200_plan_set_kernel(hvb200_plan *plan, int kernel)
 {
+    if (!plan) { hvb200_set_error("NULL plan (no point strictly dominates ref)"); return -2; }
     if (kernel < HVB200_KERNEL_AUTO || kernel > HVB200_KERNEL_BP) { hvb200_set_error("bad kernel id %d", kernel); return -2; }
     plan->kernel = kernel;
     return 0;
 }
 int hvb200_plan_last_stats(const hvb200_plan *plan, hvb200_stats *out)
 {
+    if (!plan) { memset(out, 0, sizeof *out); hvb200_set_error("NULL plan (no point strictly dominates ref)"); return -2; }
     *out = plan->stats;
     return 0;
 }
@@ -363,9 +365,12 @@ int hvb200_rphi_sequence(dimension_t nobjs, uint64_t i0, uint64_t count, double 
    that would not fit streams its directions as before.  HVB200_NO_DIRCACHE=1 disables it. */
 #define RPHI_CACHE_ENTRIES 8
 #define RPHI_CACHE_MAX_BYTES ((uint64_t)1 << 30)
+/* a cached direction buffer is shared by the cache entry and by the runs that read it: whoever drops the last
+   reference frees it (all under g_rphi_mutex; a run drops its reference after hvb200cu_run_end, which is synchronous) */
+typedef struct rphi_buf { double *dev; int device; int refs; } rphi_buf;
 typedef struct {
     int used, device, d;
-    double *dev;                        /* [cap][2][d] */
+    rphi_buf *buf;                      /* dev: [cap][2][d] */
     uint64_t cap, valid;
     unsigned __int128 u[HVB200_MAXD];   /* recurrence state after `valid` steps */
     uint64_t stamp;
@@ -373,6 +378,10 @@ typedef struct {
 static rphi_cache_t g_rphi_cache[RPHI_CACHE_ENTRIES];
 static uint64_t g_rphi_stamp;
 static pthread_mutex_t g_rphi_mutex = PTHREAD_MUTEX_INITIALIZER;
+static void rphi_buf_unref_locked(rphi_buf *b)
+{
+    if (b && --b->refs == 0) { hvb200cu_dev_free(b->device, b->dev); free(b); }
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* run                                                                                         */
@@ -388,6 +397,7 @@ static int run_range(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t 
 static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32_t seed, uint64_t i0, uint64_t i1,
                         void *stream, double out_hilo[2], double *values_out, double *dirs_out, void *sets_ctx)
 {
+    if (!plan) { hvb200_set_error("NULL plan (no point strictly dominates ref)"); return -2; }
     const int d = plan->d;
     tls_error[0] = 0;
     if (i1 < i0 || i1 > nsamples) { hvb200_set_error("bad sample range [%llu, %llu) of %llu",
@@ -399,7 +409,7 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
     /* DZ2019-MC stream: generated on the device unless HVB200_MC=host asks for the host generator
        (kept as an independent cross-check of the device generator) */
     const char *mc_env = getenv("HVB200_MC");
-    const int mc_on_device = !(mc_env && !strcmp(mc_env, "host"));
+    int mc_on_device = !(mc_env && !strcmp(mc_env, "host"));
     uint64_t batch = 0;
     uint64_t want = i1 - i0 ? i1 - i0 : 1;
     if ((values_out || dirs_out) && want > (1u << 22)) want = 1u << 22;
@@ -420,10 +430,16 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
         hw_params_init(&hw, d, nsamples);
     } else if (method == HVB200_METHOD_MC && mc_on_device) {
         /* the stream is sequential: skip the normals of samples [0, i0) */
-        if (hvb200cu_mc_begin(plan, seed) || hvb200cu_mc_skip(plan, i0 * (uint64_t)d)) return -1;
-    } else if (method == HVB200_METHOD_MC) {
+        int rc = hvb200cu_mc_begin(plan, seed);
+        if (rc == 0) rc = hvb200cu_mc_skip(plan, i0 * (uint64_t)d);
+        if (rc == 2) mc_on_device = 0;      /* a ziggurat tail loop beyond the device's skip tables: host generator */
+        else if (rc) return -1;
+    }
+    if (method == HVB200_METHOD_MC && !mc_on_device) {
         mt_seed(&mt, seed);
         for (uint64_t j = 0; j < i0; j++) for (int k = 0; k < d; k++) (void)zig_normal(&mt);
+    } else if (method == HVB200_METHOD_MC) {
+        ;
     } else if (method == HVB200_METHOD_RPHI) {
         rphi_mantissas(rphi_M, d - 1);
         for (int k = 0; k < d - 1; k++) u[k] = (unsigned __int128)1 << 63;       /* seed 0.5 */
@@ -453,9 +469,9 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
             else if (victim->used && c->stamp < victim->stamp) victim = c;
         }
         if (!e) {
-            /* a replaced entry's buffer is not freed: another thread's kernels may still read it (bounded leak:
-               it only happens after more than 8 distinct (device, d) pairs) */
+            /* the victim's buffer goes when its last reader is done */
             e = victim;
+            if (e->used) rphi_buf_unref_locked(e->buf);
             memset(e, 0, sizeof *e);
             e->used = 1; e->device = plan->device; e->d = d;
             for (int k = 0; k < d - 1; k++) e->u[k] = (unsigned __int128)1 << 63;        /* seed 0.5 */
@@ -466,24 +482,36 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
             while (cap < i1) cap <<= 1;
             if (cap * (uint64_t)(16 * d) > RPHI_CACHE_MAX_BYTES) cap = RPHI_CACHE_MAX_BYTES / (uint64_t)(16 * d);
             void *nb = NULL;
-            if (hvb200cu_dev_alloc(plan->device, cap * (size_t)(16 * d), &nb)) rc = -1;
+            rphi_buf *nbuf = malloc(sizeof *nbuf);
+            if (!nbuf) { hvb200_set_error("out of host memory"); rc = -1; }
+            else if (hvb200cu_dev_alloc(plan->device, cap * (size_t)(16 * d), &nb)) { free(nbuf); rc = -1; }
             else {
-                if (e->valid && hvb200cu_copy_dev(plan, nb, e->dev, e->valid * (size_t)(2 * d))) rc = -1;
-                /* the old buffer stays allocated for readers in flight (sizes double: bounded by the cap) */
-                e->dev = nb;
-                e->cap = cap;
+                nbuf->dev = nb; nbuf->device = plan->device; nbuf->refs = 1;
+                if (e->valid && hvb200cu_copy_dev(plan, nb, e->buf->dev, e->valid * (size_t)(2 * d))) {
+                    hvb200cu_dev_free(plan->device, nb); free(nbuf); rc = -1;
+                } else {
+                    rphi_buf_unref_locked(e->buf);       /* freed now, or by the last run still reading it */
+                    e->buf = nbuf;
+                    e->cap = cap;
+                }
             }
         }
         for (uint64_t b0 = e->valid; rc == 0 && b0 < i1; ) {
             const uint64_t cnt = (i1 - b0 < batch) ? i1 - b0 : batch;
             double *uu = hvb200cu_staging(plan, cnt * (size_t)(d - 1));
             if (!uu) { rc = -1; break; }
-            rphi_advance(e->u, rphi_M, d - 1, cnt, uu);
-            if (hvb200cu_gen_rphi(plan, uu, cnt) || hvb200cu_copy_dirs_out(plan, e->dev + b0 * (size_t)(2 * d), cnt, 1)) { rc = -1; break; }
+            /* advance a copy of the recurrence state: it is committed together with `valid` only when the GPU
+               steps succeeded, so a failed batch leaves the entry consistent */
+            unsigned __int128 unext[HVB200_MAXD];
+            memcpy(unext, e->u, sizeof unext);
+            rphi_advance(unext, rphi_M, d - 1, cnt, uu);
+            if (hvb200cu_gen_rphi(plan, uu, cnt) || hvb200cu_copy_dirs_out(plan, e->buf->dev + b0 * (size_t)(2 * d), cnt, 1)) { rc = -1; break; }
+            memcpy(e->u, unext, sizeof unext);
             b0 += cnt;
             e->valid = b0;                   /* the state e->u matches e->valid after every batch */
         }
-        if (rc == 0) view = e->dev;
+        rphi_buf *held = NULL;
+        if (rc == 0) { held = e->buf; held->refs++; view = held->dev; }
         pthread_mutex_unlock(&g_rphi_mutex);
         if (rc) return -1;
         for (uint64_t b0 = i0; b0 < i1; b0 += batch) {
@@ -498,8 +526,12 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
             if (rc) break;
         }
         hvb200cu_set_dirs_view(plan, NULL);
+        if (rc == 0 && hvb200cu_run_end(plan, out_hilo)) rc = -1;       /* synchronous: no kernel reads `view` after it */
+        else if (rc) hvb200cu_plan_sync(plan);
+        pthread_mutex_lock(&g_rphi_mutex);
+        rphi_buf_unref_locked(held);
+        pthread_mutex_unlock(&g_rphi_mutex);
         if (rc) return -1;
-        if (hvb200cu_run_end(plan, out_hilo)) return -1;
         plan->stats.samples = i1 - i0;
         return 0;
     }
@@ -513,7 +545,16 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
         } else if (method == HVB200_METHOD_HW) {
             if (hvb200cu_gen_hw(plan, &hw, b0, cnt)) return -1;
         } else if (method == HVB200_METHOD_MC && mc_on_device) {
-            if (hvb200cu_gen_mc_device(plan, cnt)) return -1;
+            const int rc = hvb200cu_gen_mc_device(plan, cnt);
+            if (rc == 2) {
+                /* 1.5e-12 per pair: a tail loop the device's 16-entry skip tables cannot express.  The rest of the run
+                   comes from the host generator (same stream), restarted at this batch */
+                mc_on_device = 0;
+                mt_seed(&mt, seed);
+                for (uint64_t j = 0; j < b0; j++) for (int k = 0; k < d; k++) (void)zig_normal(&mt);
+                b0 -= batch;
+                continue;
+            } else if (rc) return -1;
         } else if (method == HVB200_METHOD_MC) {
             double *z = hvb200cu_staging(plan, cnt * (size_t)d);
             if (!z) return -1;
@@ -546,18 +587,19 @@ int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint3
    directions.  The cost of a direction varies smoothly along a Hua-Wang lattice (its first angle grows with the
    index), so contiguous shards are unbalanced (8 GPUs: 85 % efficiency) while interleaved blocks are not.
    Only the lattice is index-addressable: the MC and Rphi streams are sequential and stay on contiguous ranges. */
-/* block size of the block-cyclic shards: 2^21 directions, halved (down to 2^16) until every rank gets >= 4 blocks */
+/* block size of the block-cyclic shards: 2^21 directions, halved (down to 2^10) until every rank gets >= 4 blocks */
 uint64_t hvb200_shard_block(uint_fast32_t nsamples, int world)
 {
     uint64_t block = HVB200_SHARD_BLOCK;
     if (world < 1) world = 1;
-    while (block > ((uint64_t)1 << 16) && block * (uint64_t)world * 4 > (uint64_t)nsamples) block >>= 1;
+    while (block > ((uint64_t)1 << 10) && block * (uint64_t)world * 4 > (uint64_t)nsamples) block >>= 1;
     return block;
 }
 int hvb200_plan_run_blocks(hvb200_plan *plan, int method, uint_fast32_t nsamples_, uint32_t seed,
                            uint64_t block, uint64_t first, uint64_t stride, void *cuda_stream, double out_hilo[2])
 {
     (void)seed;
+    if (!plan) { hvb200_set_error("NULL plan (no point strictly dominates ref)"); return -2; }
     const uint64_t nsamples = (uint64_t)nsamples_;
     const int d = plan->d;
     tls_error[0] = 0;
@@ -621,6 +663,7 @@ int hvb200_directions(int method, dimension_t nobjs, uint_fast32_t nsamples, uin
 int hvb200_plan_run_directions(hvb200_plan *plan, const double *r_host, uint64_t count,
                                double *values_out, double out_hilo[2])
 {
+    if (!plan) { hvb200_set_error("NULL plan (no point strictly dominates ref)"); return -2; }
     tls_error[0] = 0;
     uint64_t batch = 0;
     uint64_t want = count ? count : 1;
@@ -994,8 +1037,12 @@ double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, di
     if (ndevices == 1) {
         shard_main(&jobs[0]);
     } else {
-        for (int g = 0; g < ndevices; g++) pthread_create(&th[g], NULL, shard_main, &jobs[g]);
-        for (int g = 0; g < ndevices; g++) pthread_join(th[g], NULL);
+        int started[16] = {0};
+        for (int g = 0; g < ndevices; g++) started[g] = pthread_create(&th[g], NULL, shard_main, &jobs[g]) == 0;
+        for (int g = 0; g < ndevices; g++) {
+            if (started[g]) pthread_join(th[g], NULL);
+            else shard_main(&jobs[g]);               /* no thread: this shard runs inline, it is never dropped */
+        }
     }
     double pairs[32];
     int failed = -1, empty = 0;

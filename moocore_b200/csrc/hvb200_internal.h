@@ -82,6 +82,8 @@ void hvb200cu_dev_free(int device, void *p);
 int hvb200cu_copy_dirs_out(struct hvb200_plan *plan, double *dst, uint64_t count, int wait);
 int hvb200cu_copy_dev(struct hvb200_plan *plan, double *dst, const double *src, size_t doubles);
 void hvb200cu_set_dirs_view(struct hvb200_plan *plan, const double *view);
+/* wait for everything queued on the plan's stream (error paths that must not leave readers of a shared buffer behind) */
+void hvb200cu_plan_sync(struct hvb200_plan *plan);
 /* batched point sets against one direction set */
 size_t hvb200cu_sets_max_points(int d);
 int hvb200cu_sets_begin(struct hvb200_plan *plan, const double *pts_host, const unsigned *off_host, int nsets, void **ctx_out);

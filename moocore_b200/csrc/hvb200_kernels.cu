@@ -2672,7 +2672,8 @@ extern "C" int hvb200cu_mc_skip(struct hvb200_plan *plan, uint64_t nnormals)
     DevPlan *dp = (DevPlan *)plan->dev;
     while (nnormals) {
         const uint64_t step = nnormals < (1ull << 24) ? nnormals : (1ull << 24);
-        if (mcgen_normals(plan, dp, dp->mc, step, nullptr)) return -1;
+        const int rc = mcgen_normals(plan, dp, dp->mc, step, nullptr);
+        if (rc) return rc;
         nnormals -= step;
     }
     return 0;
@@ -2687,7 +2688,7 @@ extern "C" int hvb200cu_gen_mc_device(struct hvb200_plan *plan, uint64_t count)
         CUDA_TRY(cudaMalloc(&dp->staging_dev, ndoubles * sizeof(double)));
         dp->staging_dev_cap = ndoubles;
     }
-    if (mcgen_normals(plan, dp, dp->mc, ndoubles, dp->staging_dev)) return -1;
+    if (const int rc = mcgen_normals(plan, dp, dp->mc, ndoubles, dp->staging_dev)) return rc;
     const int b = span_begin(dp, 1);
     k_gen_mc<<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(dp->staging_dev, count, dp->d, dp->dirs);
     span_end(dp, b);
@@ -2732,6 +2733,14 @@ extern "C" int hvb200cu_copy_dev(struct hvb200_plan *plan, double *dst, const do
     CUDA_TRY(cudaMemcpyAsync(dst, src, doubles * sizeof(double), cudaMemcpyDeviceToDevice, dp->stream));
     CUDA_TRY(cudaStreamSynchronize(dp->stream));
     return 0;
+}
+extern "C" void hvb200cu_plan_sync(struct hvb200_plan *plan)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    if (!dp) return;
+    cudaSetDevice(dp->device);
+    if (dp->stream) cudaStreamSynchronize(dp->stream);
+    cudaGetLastError();
 }
 extern "C" void hvb200cu_set_dirs_view(struct hvb200_plan *plan, const double *view)
 {

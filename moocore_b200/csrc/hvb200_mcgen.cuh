@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) k_zig_classify(const unsigned *__restrict
                     L = 1 + 2 * (t + 1);
                     break;
                 }
-                if (1 + 2 * (t + 2) > kZigMaxL) { atomicOr(&scalars[2], 1ull); L = kZigMaxL; em = 0; break; }
+                if (1 + 2 * (t + 2) > kZigMaxL) { L = kZigMaxL; em = 2; break; }      // beyond the skip tables: reported if this attempt is real
             }
         } else {                        // wedge: pair j+1
             if (j + 1 >= npairs) { L = 0; em = 0; }
@@ -231,12 +231,14 @@ struct SkipCompose {
     }
 };
 __global__ void __launch_bounds__(256) k_zig_flags(const ull *__restrict__ fscan, const unsigned char *__restrict__ emit,
-                                                   ull npairs, unsigned *__restrict__ eflag)
+                                                   ull npairs, unsigned *__restrict__ eflag, ull *scalars)
 {
     const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= npairs) return;
     const bool start = (j == 0) || ((fscan[j - 1] & 15ull) == 0);      // skip counter before pair j, from s = 0
-    eflag[j] = (start && emit[j]) ? 1u : 0u;
+    // a tail loop longer than the skip tables express (1.5e-12 per pair) only matters when an attempt really starts here
+    if (start && emit[j] == 2) atomicOr(&scalars[2], 1ull);
+    eflag[j] = (start && emit[j] == 1) ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256) k_zig_scatter(const unsigned *__restrict__ eflag, const unsigned *__restrict__ epos,
                                                      const double *__restrict__ val, const unsigned char *__restrict__ L,
@@ -444,7 +446,7 @@ static int mcgen_normals(struct hvb200_plan *plan, DevPlan *dp, McGen *g, ull ne
         CUDA_TRY(cudaMemsetAsync(g->scalars, 0, 4 * sizeof(ull), dp->stream));
         k_zig_classify<<<grid, 256, 0, dp->stream>>>(g->words, P, g->L, g->emit, g->val, g->ftab, g->scalars);
         CUDA_TRY(cub::DeviceScan::InclusiveScan(g->cub_tmp, g->cub_tmp_bytes, g->ftab, g->fscan, SkipCompose(), (int)P, dp->stream));
-        k_zig_flags<<<grid, 256, 0, dp->stream>>>(g->fscan, g->emit, P, g->eflag);
+        k_zig_flags<<<grid, 256, 0, dp->stream>>>(g->fscan, g->emit, P, g->eflag, g->scalars);
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(g->cub_tmp, g->cub_tmp_bytes, g->eflag, g->epos, (int)P, dp->stream));
         k_zig_scatter<<<grid, 256, 0, dp->stream>>>(g->eflag, g->epos, g->val, g->L, P, need, normals_dev, g->scalars);
         span_end(dp, b);
@@ -452,7 +454,10 @@ static int mcgen_normals(struct hvb200_plan *plan, DevPlan *dp, McGen *g, ull ne
         plan->stats.dirgen_launches += 3;
         CUDA_TRY(cudaMemcpyAsync(g->scalars_host, g->scalars, 4 * sizeof(ull), cudaMemcpyDeviceToHost, dp->stream));
         CUDA_TRY(cudaStreamSynchronize(dp->stream));
-        if (g->scalars_host[2]) { hvb200_set_error("ziggurat tail loop longer than %d pairs (device limit)", kZigMaxL); return -1; }
+        if (g->scalars_host[2] || getenv("HVB200_MC_FORCE_TAIL_OVERFLOW")) {
+            hvb200_set_error("ziggurat tail loop longer than %d pairs (device limit)", kZigMaxL);
+            return 2;                       // the caller continues this run with the host generator
+        }
         // the last kZigMaxL pairs may hold attempts whose look-ahead leaves the batch: never end there
         if (g->scalars_host[1] >= need && g->scalars_host[0] + 2 * kZigMaxL <= P) {
             // keep the pairs behind the last used attempt for the next batch

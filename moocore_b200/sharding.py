@@ -24,10 +24,10 @@ SHARD_BLOCK = 1 << 21      # HVB200_SHARD_BLOCK of include/hvapprox_b200.h
 
 
 def shard_block(nsamples: int, world: int) -> int:
-    """Block size used for `world` ranks (hvb200_shard_block): 2^21 directions, halved down to 2^16 until every
+    """Block size used for `world` ranks (hvb200_shard_block): 2^21 directions, halved down to 2^10 until every
     rank gets at least 4 blocks."""
     block = SHARD_BLOCK
-    while block > (1 << 16) and block * max(1, world) * 4 > nsamples:
+    while block > (1 << 10) and block * max(1, world) * 4 > nsamples:
         block >>= 1
     return block
 
@@ -43,21 +43,37 @@ def shard_blocks(nsamples: int, rank: int, world: int, block: int = SHARD_BLOCK)
     return [(lo, min(lo + block, nsamples)) for lo in range(rank * block, nsamples, world * block)]
 
 
+_gather_cache = {}
+
+
 def gather_partials(hilo: Sequence[float], group=None, device=None):
     """All-gather one (hi, lo) pair per rank; returns a flat list [hi0, lo0, hi1, lo1, ...].
 
     Works with any initialised torch.distributed backend; without an initialised process
-    group it returns the local pair (world size 1)."""
+    group it returns the local pair (world size 1).  The send/receive tensors (and, on a GPU, a pinned
+    host landing buffer) are allocated once per (device, world) and reused: one collective and one
+    device->host copy per call."""
     import torch
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()):
         return [float(hilo[0]), float(hilo[1])]
     world = dist.get_world_size(group)
-    t = torch.tensor([hilo[0], hilo[1]], dtype=torch.float64, device=device)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t, group=group)
-    flat = []
-    for o in out:
-        flat.extend(o.cpu().tolist())
-    return flat
+    key = (str(device), world, id(group))
+    bufs = _gather_cache.get(key)
+    if bufs is None:
+        send = torch.empty(2, dtype=torch.float64, device=device)
+        recv = torch.empty(2 * world, dtype=torch.float64, device=device)
+        on_gpu = send.is_cuda
+        stage = torch.empty(2, dtype=torch.float64, pin_memory=on_gpu)
+        land = torch.empty(2 * world, dtype=torch.float64, pin_memory=on_gpu)
+        bufs = _gather_cache[key] = (send, recv, stage, land)
+    send, recv, stage, land = bufs
+    stage[0] = float(hilo[0])
+    stage[1] = float(hilo[1])
+    send.copy_(stage, non_blocking=True)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    land.copy_(recv, non_blocking=True)
+    if recv.is_cuda:
+        torch.cuda.current_stream(recv.device).synchronize()
+    return land.tolist()

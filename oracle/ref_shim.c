@@ -13,6 +13,8 @@
  */
 #define DEBUG 0
 #include <stdint.h>
+#include "config.h"     /* first on purpose: the d <= 64 build (oracle/Makefile, libhvref_d64.so) puts a patched copy
+                           ahead of the reference's on the include path; its include guard then keeps the limit */
 #include "ziggurat_constants.h" /* reference c/ziggurat_constants.h (static tables) */
 #include "hvapprox.c"   /* reference c/hvapprox.c — brings the three public entry points + statics */
 /* mt19937.h leaks the macros N and M (c/mt19937/mt19937.h:12-13). */
@@ -218,6 +220,7 @@ SHIM_API double ref_pow_uint(double x, unsigned e) { return pow_uint(x, e); }
 SHIM_API int ref_sizeof_dimension_t(void) { return (int)sizeof(dimension_t); }
 SHIM_API int ref_sizeof_uint_fast32_t(void) { return (int)sizeof(uint_fast32_t); }
 SHIM_API int ref_sizeof_boolvec(void) { return (int)sizeof(boolvec); }
+SHIM_API int ref_dimension_max(void) { return MOOCORE_HVAPPROX_DIMENSION_MAX; }
 
 /* Ziggurat tables (c/ziggurat_constants.h:66,154,284,1264-1266) — accessors so that
  * oracle/gen_ziggurat_tables.py can verify its own regenerated tables bit-for-bit. */

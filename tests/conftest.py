@@ -67,6 +67,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_r2():
+    """Round-2 goldens (tests/golden/make_golden_r2.py): config 5 from the patched d <= 64 reference, DZ2019-HW at d = 21, 22."""
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "golden_r2.json")))
+
+
+@pytest.fixture(scope="session")
 def mb():
     import moocore_b200
 

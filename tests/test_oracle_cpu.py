@@ -149,3 +149,97 @@ def test_mc_rphi_windows_vs_reference_bit_exact(oracle, reflib, d):
     a = oracle.orc_rphi_window(P(tp), ctypes.c_size_t(100), d, ctypes.c_uint64(1000), ctypes.c_uint64(300), P(v1), None, None)
     b = reflib.ref_rphi_window(P(tp), ctypes.c_size_t(100), d, ctypes.c_uint64(1000), ctypes.c_uint64(300), P(v2), None, None)
     assert a == b and np.array_equal(v1, v2)
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: config 5 (d = 50, patched reference), extension dimensions, DZ2019-HW at d = 21, 22
+# ---------------------------------------------------------------------------------------------
+def test_cfg5_inputs_unchanged(golden_r2):
+    x, _, _ = hvcases.config_inputs("cfg5")
+    assert hvcases.digest(x) == golden_r2["cfg5_digest"]
+
+
+@pytest.mark.parametrize("w", [0, 1])
+def test_cfg5_mc_windows(oracle, golden_r2, w):
+    """Config 5 against the patched reference (oracle/patch_ref_d64.py): n = 1e5, d = 50, mixed maximise mask.
+    The third window (1e7 samples = 5e8 normals deep) is left to the GPU test: 9 s of host RNG."""
+    c = hvcases.CONFIGS["cfg5"]
+    x, ref, maxi = hvcases.config_inputs("cfg5")
+    tp = hvcases.transformed(x, ref, maxi)
+    g = golden_r2["cfg5_windows"][w]
+    assert tp.shape[0] == g["npoints"]
+    cnt = 64
+    vals, r = np.zeros(cnt), np.zeros((cnt, c["d"]))
+    oracle.orc_mc_window(P(tp), ctypes.c_size_t(tp.shape[0]), c["d"], ctypes.c_uint32(c["seed"]),
+                         ctypes.c_uint64(g["i0"]), ctypes.c_uint64(cnt), P(vals), P(r))
+    assert [float(v).hex() for v in vals] == g["values"][:cnt]
+    assert [[float(v).hex() for v in row] for row in r[:4]] == g["dirs"]
+
+
+def test_cfg5_small_full_estimates(oracle, golden_r2):
+    g = golden_r2["cfg5_small"]
+    x, ref, maxi = hvcases.config_inputs("cfg5")
+    xs = np.ascontiguousarray(x[:g["n"]])
+    for method in ("DZ2019-MC", "Rphi-FWE+"):
+        assert estimate(oracle, "orc_", method, xs, ref, maxi, g["nsamples"], 42) == fh(g[method])
+
+
+def test_extension_dims_windows(oracle, golden_r2):
+    for g in golden_r2["ext_dims"]:
+        d = g["d"]
+        tp = np.ascontiguousarray(1.1 - hvcases.front("random", g["n"], d, g["pseed"]))
+        v = np.zeros(g["count"])
+        s = oracle.orc_mc_window(P(tp), ctypes.c_size_t(g["n"]), d, ctypes.c_uint32(g["mc_seed"]), ctypes.c_uint64(g["i0"]),
+                                 ctypes.c_uint64(g["count"]), P(v), None)
+        assert s == fh(g["mc_sum"]) and [float(t).hex() for t in v[:32]] == g["mc_values"]
+        s = oracle.orc_rphi_window(P(tp), ctypes.c_size_t(g["n"]), d, ctypes.c_uint64(g["i0"]), ctypes.c_uint64(g["count"]), P(v), None, None)
+        assert s == fh(g["rphi_sum"]) and [float(t).hex() for t in v[:32]] == g["rphi_values"]
+
+
+def test_hw_d21_d22_windows(oracle, golden_r2):
+    """The last two dimensions where the reference's DZ2019-HW terminates."""
+    for g in golden_r2["hw_d21_d22"]:
+        d, N = g["d"], g["N"]
+        tp = np.ascontiguousarray(1.1 - hvcases.front("sphere", g["n"], d, g["pseed"]))
+        vals = np.zeros(g["count"])
+        s = oracle.orc_hw_window(P(tp), ctypes.c_size_t(g["n"]), d, ctypes.c_uint64(N), ctypes.c_uint64(g["i0"]),
+                                 ctypes.c_uint64(g["count"]), P(vals))
+        assert rel(s, fh(g["sum"])) <= TOL
+        want = np.array([fh(v) for v in g["values"]])
+        assert np.max(np.abs(vals[:64] - want) / want) < (1e-6 if g["i0"] == 0 else 1e-9)
+
+
+def test_int_sin_pow_vs_reference_m19_m20(oracle, reflib):
+    """F_m at the two exponents only d = 21, 22 reach: the reduction formula and the reference's closed forms differ
+    most here (both carry the cancellation noise that stops the reference from terminating at d >= 23)."""
+    rng = np.random.default_rng(2)
+    for m in (19, 20):
+        for b in rng.random(2000) * np.pi / 2:
+            assert abs(oracle.orc_int_sin_pow(m, b) - reflib.ref_int_sin_pow(m, b)) < 1e-14
+        assert oracle.orc_solve_inverse_u(0.0, m) == reflib.ref_solve_inverse_u(0.0, m)
+
+
+@pytest.mark.parametrize("d,N", [(21, 1_000_000), (22, 262144), (21, 100_000_000), (22, 1_000_000_000)])
+def test_random_hw_windows_vs_reference_d21_d22(oracle, reflib, d, N):
+    rng = np.random.default_rng(d)
+    tp = np.ascontiguousarray(1.1 - hvcases.front("sphere", 200, d, d))
+    for i0 in [0, int(rng.integers(0, N - 500)), N - 500]:
+        a = oracle.orc_hw_window(P(tp), ctypes.c_size_t(200), d, ctypes.c_uint64(N), ctypes.c_uint64(i0), ctypes.c_uint64(500), None)
+        b = reflib.ref_hw_window(P(tp), ctypes.c_size_t(200), d, ctypes.c_uint64(N), ctypes.c_uint64(i0), ctypes.c_uint64(500), None)
+        assert rel(a, b) <= TOL
+
+
+def test_patched_reference_is_the_reference_below_32(reflib):
+    """The d <= 64 build differs from the reference only past its domain: same bits inside it."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libhvref_d64.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libhvref_d64.so not built")
+    R64 = ctypes.CDLL(path)
+    for nm in ("hv_approx_normal", "hv_approx_hua_wang", "hv_approx_rphi_fang_wang_plus"):
+        getattr(R64, nm).restype = ctypes.c_double
+    assert R64.ref_dimension_max() == 64 and reflib.ref_dimension_max() == 31
+    for d in (2, 7, 20, 31):
+        x = hvcases.front("sphere", 50, d, d)
+        for method in ("DZ2019-MC", "Rphi-FWE+") + (("DZ2019-HW",) if d <= 20 else ()):
+            assert estimate(R64, "", method, x, 1.1, False, 3000, 9) == estimate(reflib, "", method, x, 1.1, False, 3000, 9)
