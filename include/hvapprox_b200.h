@@ -146,6 +146,10 @@ MOOCORE_API double hvb200_hv_approx_multi(int method, const double *data, size_t
                                           const double *ref, const boolvec *maximise,
                                           uint_fast32_t nsamples, uint32_t seed, int ndevices);
 
+/* How the calling thread's last multi-GPU call (hvb200_hv_approx_multi, or a drop-in entry point under
+ * HVB200_NGPUS=k) combined the per-GPU partial sums: 0 = single device, 1 = NCCL all-gather, 2 = host copies. */
+MOOCORE_API int hvb200_multi_last_exchange(void);
+
 /* FP64 pipe micro-benchmark used for the roofline denominator: returns measured DFMA
  * FLOP/s (2 flops per DFMA) of `device`, or a negative number on failure. */
 MOOCORE_API double hvb200_measure_fp64_flops(int device, double *dmul_per_s, double *dsetp_per_s);

@@ -438,7 +438,7 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
     if (method == HVB200_METHOD_MC && !mc_on_device) {
         mt_seed(&mt, seed);
         for (uint64_t j = 0; j < i0; j++) for (int k = 0; k < d; k++) (void)zig_normal(&mt);
-    } else if (method == HVB200_METHOD_MC) {
+    } else if (method == HVB200_METHOD_MC || method == HVB200_METHOD_HW) {
         ;
     } else if (method == HVB200_METHOD_RPHI) {
         rphi_mantissas(rphi_M, d - 1);
@@ -996,6 +996,11 @@ typedef struct {
     char err[512];
 } shard_job;
 
+/* how the last multi-GPU call of this thread combined its partial sums: 0 = one device (nothing to exchange),
+   1 = NCCL all-gather over NVLink, 2 = host copies (NCCL unavailable or disabled) */
+static __thread int tls_last_exchange;
+int hvb200_multi_last_exchange(void) { return tls_last_exchange; }
+
 static void *shard_main(void *arg)
 {
     shard_job *j = arg;
@@ -1064,10 +1069,11 @@ double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, di
         /* exchange step: one NCCL all-gather of the 16-byte partials over NVLink; every GPU ends up
            with all pairs, device 0's copy is finalised (fixed order, long double).  Without NCCL the
            host copies of the same pairs are used. */
+        tls_last_exchange = ndevices > 1 ? 2 : 0;
         if (ndevices > 1 && !getenv("HVB200_NO_NCCL")) {
             double gathered[32];
             const int rc = hvb200cu_nccl_allgather(plans, ndevices, gathered);
-            if (rc == 0) memcpy(pairs, gathered, 2 * (size_t)ndevices * sizeof(double));
+            if (rc == 0) { memcpy(pairs, gathered, 2 * (size_t)ndevices * sizeof(double)); tls_last_exchange = 1; }
             else if (rc < 0) fprintf(stderr, "moocore_b200: NCCL exchange failed (%s); using host copies\n", tls_error);
         }
         result = hvb200_finalize(nobjs, nsamples, pairs, ndevices);

@@ -285,9 +285,13 @@ def test_multi_gpu_single_process_matches_single(mb):
     os.environ["HVB200_NGPUS"] = "2"
     try:
         b = mb.hv_approx(x, ref=ref, nsamples=300_000, method="DZ2019-HW")
+        from moocore_b200 import _api
+        assert _api._load().hvb200_multi_last_exchange() == 1       # the partial sums went through ncclAllGather
+        c = mb.hv_approx(x, ref=ref, nsamples=300_000, seed=42, method="DZ2019-MC")
     finally:
         del os.environ["HVB200_NGPUS"]
     assert rel(a, b) < 1e-14
+    assert rel(c, mb.hv_approx(x, ref=ref, nsamples=300_000, seed=42, method="DZ2019-MC")) < 1e-14
 
 
 # ---------------------------------------------------------------------------------------------
