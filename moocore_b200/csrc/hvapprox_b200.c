@@ -71,8 +71,15 @@ static size_t transform_and_filter(const double *data, size_t n, int d, const do
 /* ------------------------------------------------------------------------------------------ */
 /* plans                                                                                      */
 /* ------------------------------------------------------------------------------------------ */
+static int plan_create_shared(hvb200_plan **plan_out, const double *data, size_t npoints, dimension_t nobjs,
+                              const double *ref, const boolvec *maximise, int device, void *share);
 int hvb200_plan_create(hvb200_plan **plan_out, const double *data, size_t npoints, dimension_t nobjs,
                        const double *ref, const boolvec *maximise, int device)
+{
+    return plan_create_shared(plan_out, data, npoints, nobjs, ref, maximise, device, NULL);
+}
+static int plan_create_shared(hvb200_plan **plan_out, const double *data, size_t npoints, dimension_t nobjs,
+                              const double *ref, const boolvec *maximise, int device, void *share)
 {
     *plan_out = NULL;
     tls_error[0] = 0;
@@ -90,6 +97,7 @@ int hvb200_plan_create(hvb200_plan **plan_out, const double *data, size_t npoint
     if (!plan) { hvb200_set_error("out of host memory"); return -4; }
     plan->device = device;
     plan->d = d;
+    plan->share = share;
     plan->kernel = HVB200_KERNEL_AUTO;
     const char *env = getenv("HVB200_KERNEL");
     if (env && !strcmp(env, "exact")) plan->kernel = HVB200_KERNEL_EXACT;
@@ -418,7 +426,18 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
     if ((method == HVB200_METHOD_RPHI || (method == HVB200_METHOD_MC && !mc_on_device)) && want > (1u << 18)) want = 1u << 18;
     plan->run_samples = (values_out || dirs_out) ? 0 : i1 - i0;
     plan->run_total = i1 - i0;
+    /* a DZ2019-HW sum needs no direction buffer: the pruned max-min kernel can generate the lattice itself */
+    plan->want_fused_hw = method == HVB200_METHOD_HW && !values_out && !dirs_out && !sets_ctx && plan->n > 0 &&
+                          d <= MOOCORE_HVAPPROX_DIMENSION_MAX + 1;
     if (hvb200cu_run_begin(plan, stream, want, &batch)) return -1;
+    if (hvb200cu_run_is_fused(plan)) {
+        hvb200_hw_params hwf;
+        hw_params_init(&hwf, d, nsamples);
+        if (hvb200cu_maxmin_hw_fused(plan, &hwf, i0, 62, 1, i1 - i0)) return -1;
+        if (hvb200cu_run_end(plan, out_hilo)) return -1;
+        plan->stats.samples = i1 - i0;
+        return 0;
+    }
 
     const int rphi_cached = method == HVB200_METHOD_RPHI && i1 > 0 && !getenv("HVB200_NO_DIRCACHE") &&
                             i1 * (uint64_t)(16 * d) <= RPHI_CACHE_MAX_BYTES;
@@ -448,12 +467,6 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
         hvb200_set_error("unknown method %d", method);
         return -2;
     }
-
-    /* DZ2019-HW sums: the generator of the next batch overlaps the max-min kernel of this one */
-    /* (opt-in, HVB200_PIPELINE=1: measured neutral on B200 — the generator and the max-min kernel compete
-       for the same issue slots, 669 vs 671 ms per cfg3 step) */
-    const int hw_pipelined = method == HVB200_METHOD_HW && !dirs_out && !values_out && plan->n && getenv("HVB200_PIPELINE") != NULL;
-    if (hw_pipelined && i0 < i1 && hvb200cu_hw_prefetch(plan, &hw, i0, (i1 - i0 < batch) ? i1 - i0 : batch)) return -1;
 
     /* Rphi-FWE+ with a cacheable prefix: make [0, i1) resident (extending the cached prefix from its saved
        recurrence state), then evaluate straight from the cache */
@@ -538,11 +551,7 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
 
     for (uint64_t b0 = i0; b0 < i1; b0 += batch) {
         const uint64_t cnt = (i1 - b0 < batch) ? i1 - b0 : batch;
-        if (hw_pipelined) {
-            if (hvb200cu_hw_swap(plan)) return -1;
-            const uint64_t nb = b0 + batch;
-            if (nb < i1 && hvb200cu_hw_prefetch(plan, &hw, nb, (i1 - nb < batch) ? i1 - nb : batch)) return -1;
-        } else if (method == HVB200_METHOD_HW) {
+        if (method == HVB200_METHOD_HW) {
             if (hvb200cu_gen_hw(plan, &hw, b0, cnt)) return -1;
         } else if (method == HVB200_METHOD_MC && mc_on_device) {
             const int rc = hvb200cu_gen_mc_device(plan, cnt);
@@ -613,9 +622,17 @@ int hvb200_plan_run_blocks(hvb200_plan *plan, int method, uint_fast32_t nsamples
     uint64_t batch = 0;
     plan->run_samples = total;
     plan->run_total = total;
+    plan->want_fused_hw = plan->n > 0 && (block & (block - 1)) == 0;      /* the fused kernel maps positions by shifts */
     if (hvb200cu_run_begin(plan, cuda_stream, total ? total : 1, &batch)) return -1;
     hvb200_hw_params hw;
     hw_params_init(&hw, d, nsamples);
+    if (hvb200cu_run_is_fused(plan)) {
+        /* one launch over the whole shard: position p of the shard is direction (first + (p / block) stride) block + p % block */
+        if (hvb200cu_maxmin_hw_fused(plan, &hw, first * block, __builtin_ctzll(block), stride, total)) return -1;
+        if (hvb200cu_run_end(plan, out_hilo)) return -1;
+        plan->stats.samples = total;
+        return 0;
+    }
     /* the blocks of this shard are generated side by side into the direction buffer and evaluated by ONE
        max-min launch per full buffer: small launches lose ~15 % to start-up and tail */
     uint64_t filled = 0;
@@ -670,6 +687,7 @@ int hvb200_plan_run_directions(hvb200_plan *plan, const double *r_host, uint64_t
     if (want > (1u << 20)) want = 1u << 20;
     plan->run_samples = 0;
     plan->run_total = count;
+    plan->want_fused_hw = 0;
     if (hvb200cu_run_begin(plan, NULL, want, &batch)) return -1;
     for (uint64_t b0 = 0; b0 < count; b0 += batch) {
         const uint64_t cnt = (count - b0 < batch) ? count - b0 : batch;
@@ -993,6 +1011,7 @@ typedef struct {
     double hilo[2];
     int empty;
     hvb200_plan *plan;      /* kept alive until the exchange step */
+    void *share;            /* host-side preparation shared by the shards (same point set on every GPU) */
     char err[512];
 } shard_job;
 
@@ -1006,7 +1025,7 @@ static void *shard_main(void *arg)
     shard_job *j = arg;
     hvb200_plan *plan = NULL;
     j->hilo[0] = j->hilo[1] = 0.0;
-    j->rc = hvb200_plan_create(&plan, j->data, j->npoints, j->nobjs, j->ref, j->maximise, j->device);
+    j->rc = plan_create_shared(&plan, j->data, j->npoints, j->nobjs, j->ref, j->maximise, j->device, j->share);
     if (j->rc == 0 && !plan) { j->empty = 1; return NULL; }
     if (j->rc == 0 && j->stride > 1 && j->method == HVB200_METHOD_HW)
         j->rc = hvb200_plan_run_blocks(plan, j->method, j->nsamples, j->seed, hvb200_shard_block(j->nsamples, j->stride), (uint64_t)j->device, (uint64_t)j->stride, NULL, j->hilo);
@@ -1030,9 +1049,10 @@ double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, di
     shard_job jobs[16];
     pthread_t th[16];
     memset(jobs, 0, sizeof jobs);
+    void *share = ndevices > 1 ? hvb200cu_share_new() : NULL;
     for (int g = 0; g < ndevices; g++) {
         shard_job *j = &jobs[g];
-        j->method = method; j->device = g;
+        j->method = method; j->device = g; j->share = share;
         j->data = data; j->npoints = npoints; j->nobjs = nobjs; j->ref = ref; j->maximise = maximise;
         j->nsamples = (uint64_t)nsamples; j->seed = seed;
         j->i0 = (uint64_t)nsamples * (uint64_t)g / (uint64_t)ndevices;
@@ -1079,6 +1099,7 @@ double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, di
         result = hvb200_finalize(nobjs, nsamples, pairs, ndevices);
     }
     for (int g = 0; g < ndevices; g++) hvb200_plan_destroy(jobs[g].plan);
+    if (share) hvb200cu_share_free(share);
     return result;
 }
 

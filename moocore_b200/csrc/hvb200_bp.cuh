@@ -64,6 +64,18 @@ struct BpArgs {
     ull *slow_counter;
     uint2 *hits;              // [grid][kBpHitCap] hit lists
     double qscale[HVB200_MAXD], qlos[HVB200_MAXD];
+    // GEN = true (DZ2019-HW sums): the CTA generates the directions of its chunk itself (hw_direction) into a private
+    // scratch block [2D][CH] (objective-major: coalesced for the lane = direction phases), which stays in L2 — there is
+    // no direction buffer in HBM and no separate generator launch.  Position p of the launch is lattice index
+    // gen_i0 + ((p >> gen_shift) * gen_stride << gen_shift) + (p & (2^gen_shift - 1)): a contiguous range
+    // (gen_shift = 62) or the block-cyclic shard of one rank (blocks of 2^gen_shift directions, every gen_stride-th).
+    HwDev hw;
+    ull gen_i0, gen_stride;
+    int gen_shift;
+    const double *gen_tab;
+    int gen_ntab;
+    double *gen_scratch;      // [grid][2D][CH]
+    ull *capped_counter;
 };
 
 // shared-memory carve-up, used by the kernel and by the host to size the launch.
@@ -122,33 +134,48 @@ __device__ __forceinline__ unsigned bp_transpose32(unsigned x, int lane)
     return x;
 }
 
-// exact value of one point for one direction, the reference's arithmetic (c/hvapprox.c:81-102)
-template <int D>
-__device__ __forceinline__ double bp_exact(const double *__restrict__ pp, const double *__restrict__ rr)
+// 3-input FP32 min (FMNMX3, sm_100+): NaN operands are ignored like fminf
+__device__ __forceinline__ float bp_fmin3(float a, float b, float c)
 {
-    double m = __ldg(pp) * __ldg(rr);
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+static_assert(kBpMaxPivots <= 512, "the packed arg-max key of phase A holds a 9-bit pivot index");
+
+// exact value of one point for one direction, the reference's arithmetic (c/hvapprox.c:81-102)
+// (rr points at r_0 of the direction; RS = stride between its components: 1 in the row-major direction buffer, CH in a
+// CTA's generated scratch block, which is read with L2-coherent loads because the same kernel wrote it)
+template <int D, int RS>
+__device__ __forceinline__ double bp_exact(const double *__restrict__ pp, const double *rr)
+{
+    auto ldr = [&](int k) { return RS == 1 ? __ldg(rr + k) : __ldcg(rr + (size_t)k * RS); };
+    double m = __ldg(pp) * ldr(0);
 #pragma unroll
     for (int k = 1; k < D; k++) {
-        const double t = __ldg(pp + k) * __ldg(rr + k);
+        const double t = __ldg(pp + k) * ldr(k);
         m = (t < m) ? t : m;
     }
     return m;
 }
 
-template <int D, int R>
-__device__ __forceinline__ void bp_candidate(const BpArgs &a, ull chunk_base, unsigned dl, unsigned pt, long long *bestbits)
+// cdirs: the chunk's directions — row-major rows of the direction buffer, or the CTA's objective-major scratch block
+template <int D, int R, bool GEN>
+__device__ __forceinline__ void bp_candidate(const BpArgs &a, const double *cdirs, unsigned dl, unsigned pt, long long *bestbits)
 {
-    const double m = bp_exact<D>(a.pts + (size_t)pt * D, a.dirs + (chunk_base + dl) * (2 * D));
+    constexpr int CH = kBpThreads * R;
+    const double m = GEN ? bp_exact<D, CH>(a.pts + (size_t)pt * D, cdirs + dl)
+                         : bp_exact<D, 1>(a.pts + (size_t)pt * D, cdirs + (size_t)dl * (2 * D));
     if (m > 0.0) atomicMax(bestbits + dl, __double_as_longlong(m));
 }
 
-template <int D, int R>
-__device__ __noinline__ void bp_candidate_cold(const BpArgs &a, ull chunk_base, unsigned dl, unsigned pt, long long *bestbits)
+template <int D, int R, bool GEN>
+__device__ __noinline__ void bp_candidate_cold(const BpArgs &a, const double *cdirs, unsigned dl, unsigned pt, long long *bestbits)
 {
-    bp_candidate<D, R>(a, chunk_base, dl, pt, bestbits);
+    bp_candidate<D, R, GEN>(a, cdirs, dl, pt, bestbits);
 }
 
-template <int D, int R>
+template <int D, int R, bool GEN>
 __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_maxmin_bp(const __grid_constant__ BpArgs a)
 {
     constexpr int G = kBpG, W = (D + 1) / 2, CH = kBpThreads * R, DW = CH / 32;
@@ -196,6 +223,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
 
     const ull n_chunks = (a.count + CH - 1) / CH;
     ull slow = 0;
+    unsigned capped = 0;           // GEN: Newton solves stopped by the iteration cap
 
     // chunks are handed out dynamically (their cost varies with the directions); the first one is static
     ull chunk = blockIdx.x;
@@ -209,41 +237,71 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
             tma_load_1d(bnd, a.bpair, bytes, bar);
         }
         bool valid[R];
+        const double *cdirs = GEN ? a.gen_scratch + (size_t)blockIdx.x * (2 * D * CH) : a.dirs + chunk_base * (2 * D);
+        // component k of direction dl of this chunk: reciprocal weight r (k < D) and winv (D <= k < 2D)
+        auto dirv = [&](int dl, int k) { return GEN ? __ldcg(cdirs + (size_t)k * CH + dl) : __ldg(cdirs + (size_t)dl * (2 * D) + k); };
+        if constexpr (GEN) {
+            // ---- generator: every thread produces its R directions of the chunk (the previous chunk's readers are
+            //      behind the barrier that ended it; the other threads read these rows only in phase D, behind barriers)
+#pragma unroll 1
+            for (int r = 0; r < R; r++) {
+                const ull p = chunk_base + (ull)r * kBpThreads + tid;
+                if (p < a.count) {
+                    const ull i = a.gen_i0 + (((p >> a.gen_shift) * a.gen_stride) << a.gen_shift) + (p & ((1ull << a.gen_shift) - 1ull));
+                    double *o = a.gen_scratch + (size_t)blockIdx.x * (2 * D * CH) + r * kBpThreads + tid;
+                    hw_direction(a.hw, i, a.gen_tab, a.gen_ntab, capped,
+                                 [&](int k, double rk, double wk) { __stcg(o + (size_t)k * CH, rk); __stcg(o + (size_t)(D + k) * CH, wk); });
+                }
+            }
+        }
         // ---- phase A: FP32 ranking of the pivots, exact value of the best one
         {
             float rf[R][D];
-            float bv[R];
-            int bi[R];
+            unsigned bkey[R];          // best pivot so far: {FP32 bits of its min with the low 9 bits dropped | pivot index}
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const ull smp = chunk_base + (ull)r * kBpThreads + tid;
                 valid[r] = smp < a.count;
-                const double *dir = a.dirs + (valid[r] ? smp : 0) * (2 * D);
+                const int dl = valid[r] ? r * kBpThreads + tid : 0;      // (an invalid slot ranks direction 0 and is never summed)
 #pragma unroll
-                for (int k = 0; k < D; k++) rf[r][k] = (float)__ldg(dir + k);
-                bv[r] = -1.0f;
-                bi[r] = 0;
+                for (int k = 0; k < D; k++) rf[r][k] = (float)dirv(dl, k);
+                bkey[r] = 0u;
             }
-#pragma unroll 4
-            for (int i = 0; i < a.n_piv; i++) {
-                const float *pp = piv + i * D;
-                float pk[D];
+            // Two pivots per iteration.  The min over the objectives runs on 3-input FMNMX3 and the running arg-max is
+            // one VIMNMX3.U32 on packed keys (positive floats order like their bit patterns; 9 index bits replace
+            // the low mantissa bits, i.e. near-ties within 6e-5 are broken by the index — any pivot gives a valid b0).
+            // 33 instructions per pivot pair and direction instead of 44: the ALU pipe is this kernel's busiest.
+#pragma unroll 2
+            for (int i = 0; i < a.n_piv; i += 2) {
+                const int i1 = min(i + 1, a.n_piv - 1);
+                const float *pa = piv + i * D, *pb = piv + i1 * D;
+                float ka[D], kb[D];
 #pragma unroll
-                for (int k = 0; k < D; k++) pk[k] = pp[k];
+                for (int k = 0; k < D; k++) { ka[k] = pa[k]; kb[k] = pb[k]; }
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    float m = pk[0] * rf[r][0];
+                    float ta[D], tb[D];
 #pragma unroll
-                    for (int k = 1; k < D; k++) m = fminf(m, pk[k] * rf[r][k]);
-                    if (m > bv[r]) { bv[r] = m; bi[r] = i; }
+                    for (int k = 0; k < D; k++) { ta[k] = ka[k] * rf[r][k]; tb[k] = kb[k] * rf[r][k]; }
+                    float ma = ta[0], mb = tb[0];
+#pragma unroll
+                    for (int k = 1; k + 1 < D; k += 2) { ma = bp_fmin3(ma, ta[k], ta[k + 1]); mb = bp_fmin3(mb, tb[k], tb[k + 1]); }
+                    if constexpr (D % 2 == 0) { ma = fminf(ma, ta[D - 1]); mb = fminf(mb, tb[D - 1]); }
+                    const unsigned keya = (__float_as_uint(ma) & 0xfffffe00u) | (unsigned)i;
+                    const unsigned keyb = (__float_as_uint(mb) & 0xfffffe00u) | (unsigned)i1;
+                    bkey[r] = max(bkey[r], max(keya, keyb));
                 }
             }
+            int bi[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) bi[r] = (int)(bkey[r] & 0x1ffu);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 double b = 0.0;
                 if (valid[r] && a.n_piv > 0) {
-                    const ull smp = chunk_base + (ull)r * kBpThreads + tid;
-                    const double m = bp_exact<D>(a.pts + (size_t)__ldg(a.piv_idx + bi[r]) * D, a.dirs + smp * (2 * D));
+                    const int dl = r * kBpThreads + tid;
+                    const double *pp = a.pts + (size_t)__ldg(a.piv_idx + bi[r]) * D;
+                    const double m = GEN ? bp_exact<D, CH>(pp, cdirs + dl) : bp_exact<D, 1>(pp, cdirs + (size_t)dl * (2 * D));
                     b = (m > 0.0) ? m : 0.0;
                 }
                 bestbits[r * kBpThreads + tid] = __double_as_longlong(b);
@@ -260,10 +318,9 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
             for (int r = 0; r < R; r++) {
                 const int dl = r * kBpThreads + tid;
                 if (valid[r]) {
-                    const double *winv = a.dirs + (chunk_base + dl) * (2 * D) + D;
                     const double best_m = __longlong_as_double(bestbits[dl]) * (1.0 - 0x1p-20);
 #pragma unroll
-                    for (int k = 0; k < D; k++) negT[r][k] = bp_neg_key16(best_m, __ldg(winv + k), a.qscale[k], a.qlos[k]);
+                    for (int k = 0; k < D; k++) negT[r][k] = bp_neg_key16(best_m, dirv(dl, D + k), a.qscale[k], a.qlos[k]);
                     unsigned tw[4 * Q + 4];
 #pragma unroll
                     for (int j = 0; j < 4 * Q + 4; j++) {
@@ -443,7 +500,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
 #pragma unroll
                             for (int u = 0; u < 4; u++)
                                 if (((sp >> u) & 1u) && (m16[u] & 0x80008000u) == 0u) {
-                                    bp_candidate_cold<D, R>(a, chunk_base, off[u] >> 4, blk * kBpBlock + lane, bestbits);
+                                    bp_candidate_cold<D, R, GEN>(a, cdirs, off[u] >> 4, blk * kBpBlock + lane, bestbits);
                                     slow++;
                                 }
                         }
@@ -463,7 +520,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                     while (cm) {
                         const int q = __ffs((int)cm) - 1;
                         cm &= cm - 1;
-                        bp_candidate<D, R>(a, chunk_base, dl, blk * kBpBlock + q, bestbits);
+                        bp_candidate<D, R, GEN>(a, cdirs, dl, blk * kBpBlock + q, bestbits);
                         slow++;
                     }
                 }
@@ -496,4 +553,5 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) slow += __shfl_down_sync(0xffffffffu, slow, off);
     if (a.slow_counter && lane == 0 && slow) atomicAdd(a.slow_counter, slow);
+    if (GEN && capped) atomicAdd(a.capped_counter, (ull)capped);
 }

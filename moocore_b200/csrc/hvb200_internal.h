@@ -34,6 +34,8 @@ struct hvb200_plan {
     uint64_t run_total;    /* samples of the run being started, whatever its outputs (sizes per-chunk buffers) */
     /* device side (owned by the CUDA TU) */
     void *dev;             /* struct dev_plan*                                                  */
+    int want_fused_hw;     /* the run being started is a DZ2019-HW sum: the max-min kernel may generate its directions itself */
+    void *share;           /* preparation shared by the plans of one multi-GPU call (hvb200cu_share_new), or NULL */
     hvb200_stats stats;
 };
 
@@ -53,9 +55,6 @@ int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batc
 /* direction producers: fill the plan's direction buffer with `count` samples */
 int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
 int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count, uint64_t offset);
-/* pipelined DZ2019-HW: generate a batch on a second stream into the spare direction buffer, then swap */
-int hvb200cu_hw_prefetch(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
-int hvb200cu_hw_swap(struct hvb200_plan *plan);
 int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count);     /* count*d normals */
 /* DZ2019-MC stream generated on the device: begin(seed), skip n normals, then per batch */
 int hvb200cu_mc_begin(struct hvb200_plan *plan, uint32_t seed);
@@ -63,6 +62,11 @@ int hvb200cu_mc_skip(struct hvb200_plan *plan, uint64_t nnormals);
 int hvb200cu_gen_mc_device(struct hvb200_plan *plan, uint64_t count);
 int hvb200cu_gen_rphi(struct hvb200_plan *plan, const double *u_host, uint64_t count);         /* count*(d-1) u   */
 int hvb200cu_gen_uploaded(struct hvb200_plan *plan, const double *r_host, uint64_t count);     /* count*d r       */
+/* DZ2019-HW sums with the generator fused into the pruned max-min kernel (no direction buffer, one launch):
+   run_is_fused tells whether run_begin chose that path for the run in progress */
+int hvb200cu_run_is_fused(struct hvb200_plan *plan);
+int hvb200cu_maxmin_hw_fused(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t first, int shift,
+                             uint64_t stride, uint64_t count);
 /* consume the direction buffer; values_host (optional) receives per-sample s^d */
 int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double *values_host);
 /* copy the generated reciprocal directions of the current batch to the host (count x d) */
@@ -89,6 +93,11 @@ size_t hvb200cu_sets_max_points(int d);
 int hvb200cu_sets_begin(struct hvb200_plan *plan, const double *pts_host, const unsigned *off_host, int nsets, void **ctx_out);
 int hvb200cu_sets_maxmin(struct hvb200_plan *plan, void *ctx, uint64_t count);
 int hvb200cu_sets_end(struct hvb200_plan *plan, void *ctx, double *hilo_host);
+
+/* host-side preparation of the pruned kernel shared by the plans that one multi-GPU call creates for the same
+   point set on several devices (built once, by whichever plan needs it first) */
+void *hvb200cu_share_new(void);
+void hvb200cu_share_free(void *share);
 
 /* pinned staging buffer for host-produced streams (MC normals, Rphi u); grows on demand */
 double *hvb200cu_staging(struct hvb200_plan *plan, size_t ndoubles);

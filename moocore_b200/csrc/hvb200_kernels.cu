@@ -46,10 +46,20 @@
 #include <mutex>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>     // header-only: ranges are no-ops unless a profiler injects its library
+
 #include "hvb200_tables.h"
 #include "hvb200_internal.h"
 
 typedef unsigned long long ull;
+
+// NVTX range of the enclosing scope (plan creation, preparation, direction generators, max-min, reduction): the
+// phases of one estimate show up by name on an Nsight Systems / Nsight Compute timeline.
+struct NvtxScope {
+    explicit NvtxScope(const char *name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+};
+#define HVB200_NVTX(name) NvtxScope nvtx_scope_(name)
 
 #define CUDA_TRY(expr)                                                                       \
     do {                                                                                     \
@@ -357,26 +367,53 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_maxmin(const MaxminArgs
             for (int g0 = 0; g0 < a.tile_points; g0 += G) {
                 const double2 *gp = tile2 + (g0 * D) / 2;
                 if (MODE == MODE_EXACT) {
-                    double m[R][G];
+                    // The textbook loop, every product formed and compared: per element one DMUL and one DSETP.  The
+                    // running min of c/hvapprox.c:84-100 is a select (DSETP + 2 FSEL per element, which made the loop
+                    // issue-bound at 53 % FP64-pipe utilisation); max_p min_k (p_k r_k) only needs to know whether
+                    // EVERY product of a point exceeds the running max, so the comparisons chain through one
+                    // predicate per (direction, point) — DSETP.GT.AND — and the min itself is formed for the few
+                    // points that raise the max (~ln n per direction).  Same products, same comparisons, same bits.
+                    bool c[R][G];
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+#pragma unroll
+                        for (int g = 0; g < G; g++) c[r][g] = true;
 #pragma unroll
                     for (int j = 0; j < (G * D) / 2; j++) {
+                        // large D: keep the scheduler from hoisting every load and product of the group ahead of the
+                        // comparisons (r[D] already fills the register file): shared-memory loads do not cross the fence
+                        if (D > 16 && j > 0 && j % 8 == 0) asm volatile("" ::: "memory");
                         const double2 v = gp[j];
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
                             const int e = 2 * j + h, g = e / D, k = e % D;
                             const double pv = h ? v.y : v.x;
 #pragma unroll
-                            for (int r = 0; r < R; r++) {
-                                const double prod = pv * T[r][k];
-                                if (k == 0) m[r][g] = prod;
-                                else m[r][g] = (prod < m[r][g]) ? prod : m[r][g];
-                            }
+                            for (int r = 0; r < R; r++) c[r][g] = c[r][g] & (pv * T[r][k] > best[r]);
                         }
                     }
+                    bool any = false;
 #pragma unroll
                     for (int r = 0; r < R; r++)
 #pragma unroll
-                        for (int g = 0; g < G; g++) best[r] = (m[r][g] > best[r]) ? m[r][g] : best[r];
+                        for (int g = 0; g < G; g++) any = any | c[r][g];
+                    if (any) {
+#pragma unroll
+                        for (int g = 0; g < G; g++)
+#pragma unroll
+                            for (int r = 0; r < R; r++)
+                                if (c[r][g]) {
+                                    const double *p = tile + (size_t)(g0 + g) * D;
+                                    double m = p[0] * T[r][0];
+#pragma unroll
+                                    for (int k = 1; k < D; k++) {
+                                        const double t = p[k] * T[r][k];
+                                        m = (t < m) ? t : m;
+                                    }
+                                    best[r] = (m > best[r]) ? m : best[r];
+                                    slow++;
+                                }
+                    }
                 } else {
                     bool c[R][G];
 #pragma unroll
@@ -757,7 +794,6 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_maxmin_dpx(const __grid
     }
 }
 
-#include "hvb200_bp.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Point ordering for the screens.  max over points is order-free (exact), so the processing order
@@ -815,87 +851,6 @@ __global__ void __launch_bounds__(256) k_gather_rows(const double *__restrict__ 
     const ull i = w / d;
     const int k = (int)(w - i * d);
     dst[w] = src[(ull)order[i] * d + k];
-}
-
-// Generic fall-back for d > 32 (extension beyond the reference's domain): runtime d, EXACT only,
-// directions read from L1/L2, one direction per thread.
-__global__ void __launch_bounds__(kBlockThreads) k_maxmin_generic(const MaxminArgs a, int d)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tile_doubles = a.tile_points * d;
-    const unsigned tile_bytes = (unsigned)tile_doubles * 8u;
-    double *tiles = reinterpret_cast<double *>(smem_raw);
-    const int stage_doubles = a.stage_bytes / 8;
-    ull *full_bar = reinterpret_cast<ull *>(smem_raw + (size_t)kStages * a.stage_bytes);
-    ull *empty_bar = full_bar + kStages;
-    double *red = reinterpret_cast<double *>(empty_bar + kStages + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumerThreads / 32); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const ull CH = kConsumerThreads;
-    const ull n_chunks = (a.count + CH - 1) / CH;
-    const ull my_chunks = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const bool resident = a.n_tiles <= kStages;
-    const ull total_loads = resident ? (my_chunks ? (ull)a.n_tiles : 0) : my_chunks * (ull)a.n_tiles;
-    if (warp == kConsumerThreads / 32) {
-        if (lane == 0) {
-            for (ull q = 0; q < total_loads; q++) {
-                const int stage = (int)(q % kStages);
-                if (q >= (ull)kStages) mbar_wait(&empty_bar[stage], (unsigned)(((q / kStages) - 1) & 1));
-                mbar_arrive_expect_tx(&full_bar[stage], tile_bytes);
-                tma_load_1d(tiles + (size_t)stage * stage_doubles,
-                            a.pts + (size_t)(q % (ull)a.n_tiles) * tile_doubles, tile_bytes, &full_bar[stage]);
-            }
-        }
-        return;
-    }
-    double acc = 0.0;
-    ull q = 0;
-    for (ull chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        const ull sample = chunk * CH + tid;
-        const bool valid = sample < a.count;
-        const double *rr = a.dirs + (valid ? sample : 0) * (ull)(2 * d);
-        double best = 0.0;
-        for (int t = 0; t < a.n_tiles; t++, q++) {
-            const int stage = resident ? t : (int)(q % kStages);
-            const unsigned parity = resident ? 0u : (unsigned)((q / kStages) & 1);
-            mbar_wait(&full_bar[stage], parity);
-            const double *tile = tiles + (size_t)stage * stage_doubles;
-            for (int g = 0; g < a.tile_points; g++) {
-                const double *p = tile + (size_t)g * d;
-                double m = p[0] * __ldg(rr);
-                for (int k = 1; k < d; k++) {
-                    const double pr = p[k] * __ldg(rr + k);
-                    m = (pr < m) ? pr : m;
-                }
-                best = (m > best) ? m : best;
-            }
-            if (!resident) { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[stage]); }
-        }
-        // generic square-and-multiply / chain by runtime exponent
-        double v;
-        {
-            unsigned e = (unsigned)d;
-            double x = best;
-            double accp = (e & 1u) ? x : 1.0;
-            for (e >>= 1; e; e >>= 1) { x *= x; if (e & 1u) accp *= x; }
-            v = accp;
-        }
-        if (valid) { acc += v; if (a.values) a.values[sample] = v; }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-    if (lane == 0) red[warp] = acc;
-    consumer_bar_sync();
-    if (tid == 0) {
-        double v[8];
-#pragma unroll
-        for (int w = 0; w < 8; w++) v[w] = (w < kConsumerWarps) ? red[w] : 0.0;
-        a.cta_sums[blockIdx.x] += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1163,6 +1118,35 @@ __global__ void __launch_bounds__(128) k_hw_table_init(double *__restrict__ tab,
     tab[idx] = theta;
 }
 
+// One DZ2019-HW direction (c/hvapprox.c:676-680 for sample index i): x87-exact lattice point, d-1 solves, polar ->
+// cartesian in the reference's product order.  emit(k, r_k, winv_k) is called for k = d-1 ... 0 with the reciprocal
+// weight r_k = |w_k| <= 1e-20 ? 1e20 : 1/w_k (:640-646) and winv_k = w_k (the clamp's 1e-20 when clamped): the
+// screens only need a winv with winv <= (1/r)(1 + 2^-53) for their conservative thresholds, and r = RN(1/w) gives
+// w = (1/r)/(1 + e), |e| <= 2^-53 — one FP64 division per component instead of two.
+template <typename Emit>
+__device__ __forceinline__ void hw_direction(const HwDev &P, ull i, const double *__restrict__ tab, int ntab, unsigned &capped, Emit emit)
+{
+    const int d = P.d;
+    const ull idx1 = i + 1;
+    const bool last = !(idx1 < P.N);                // last sample: all zeros (c/hvapprox.c:300-303)
+    X87Val fac;
+    if (!last) fac = x87_div(idx1, P.N, P.Nrecip);
+    double prod = 1.0;
+    for (int q = 0; q < d - 1; q++) {
+        const int m = d - 2 - q;
+        const double u = last ? 0.0 : x87_mul_frac(fac, P.a[q]);
+        double s, c;
+        hw_solve(u * c_Im[m], u, m, tab, ntab, s, c, capped);
+        // w_{d-1} = c_0; w_{d-1-q} = (s_0..s_{q-1}) c_q; w_0 = s_0..s_{d-2}  (c/hvapprox.c:632-638)
+        const double w = (q == 0) ? c : prod * c;
+        prod = (q == 0) ? s : s * prod;
+        const bool tiny = fabs(w) <= 1e-20;
+        emit(d - 1 - q, tiny ? 1e20 : 1.0 / w, tiny ? 1e-20 : w);
+    }
+    const bool tiny = fabs(prod) <= 1e-20;
+    emit(0, tiny ? 1e20 : 1.0 / prod, tiny ? 1e-20 : prod);
+}
+
 // The rows of a warp's 32 samples are contiguous in `dirs` (32 x 2d doubles), but a thread writing its own row stores
 // with a stride of 2d doubles: 32 L1 tag cycles per store instruction, 20 of them per sample at d = 10 — the L1 tag stage,
 // not the arithmetic, bounded the kernel (18 % fewer instructions changed nothing).  Rows are staged in shared memory
@@ -1180,32 +1164,8 @@ __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count
     const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned capped = 0;
     if (j < count) {
-        const ull idx1 = i0 + j + 1;                    // i + 1
-        const bool last = !(idx1 < P.N);                // last sample: all zeros (c/hvapprox.c:300-303)
-        X87Val fac;
-        if (!last) fac = x87_div(idx1, P.N, P.Nrecip);
         double *out = STAGED ? wrows + lane * row_stride : dirs + j * (ull)row_len;
-        double prod = 1.0;
-        for (int q = 0; q < d - 1; q++) {
-            const int m = d - 2 - q;
-            const double u = last ? 0.0 : x87_mul_frac(fac, P.a[q]);
-            double s, c;
-            hw_solve(u * c_Im[m], u, m, tab, ntab, s, c, capped);
-            // w_{d-1} = c_0; w_{d-1-q} = (s_0..s_{q-1}) c_q; w_0 = s_0..s_{d-2}  (c/hvapprox.c:632-638)
-            const double w = (q == 0) ? c : prod * c;
-            prod = (q == 0) ? s : s * prod;
-            const double r = (fabs(w) <= 1e-20) ? 1e20 : 1.0 / w;
-            double wi = 1.0 / r;
-            out[d - 1 - q] = r;
-            out[d + d - 1 - q] = (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;
-        }
-        {
-            const double w = prod;
-            const double r = (fabs(w) <= 1e-20) ? 1e20 : 1.0 / w;
-            double wi = 1.0 / r;
-            out[0] = r;
-            out[d] = (wi < __longlong_as_double(0x7ff0000000000000LL)) ? wi : 0.0;
-        }
+        hw_direction(P, i0 + j, tab, ntab, capped, [&](int k, double r, double winv) { out[k] = r; out[d + k] = winv; });
     }
     __syncwarp();
     const ull wfirst = (ull)blockIdx.x * blockDim.x + (ull)warp * 32;      // first sample of this warp
@@ -1222,6 +1182,8 @@ __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count
     }
     if (capped) atomicAdd(capped_counter, (ull)capped);
 }
+#include "hvb200_bp.cuh"
+
 static bool gen_hw_staged(int d) { return d >= 7 && d <= 12; }
 static int gen_hw_smem_bytes(int d) { return gen_hw_staged(d) ? 128 * (2 * d + 1) * (int)sizeof(double) : 0; }
 
@@ -1561,7 +1523,10 @@ struct DevPlan {
     // block-pruned kernel (hvb200_bp.cuh)
     std::vector<double> host_pts;        // host copy of the transformed points when the plan was built from one (saves a
                                          // 0.6 ms pageable read-back in bp_prepare)
-    bool bp_ready = false;
+    bool bp_ready = false, bp_begun = false, bp_probe_queued = false;
+    void *share = nullptr;               // BpShare of a single-process multi-GPU call (not owned)
+    bool fused = false;                  // this run: k_maxmin_bp generates its DZ2019-HW directions itself
+    double *gen_scratch = nullptr; size_t gen_scratch_cap = 0;   // [grid][2d][CH] per-CTA direction blocks (L2 resident)
     double *bp_pts = nullptr; size_t bp_pts_cap = 0;
     float *bp_piv32 = nullptr; unsigned *bp_pividx = nullptr;
     uint2 *bp_hits = nullptr; size_t bp_hits_cap = 0;    // per-CTA hit lists of phase C
@@ -1579,14 +1544,6 @@ struct DevPlan {
     double qlo[32] = {0}, qhi[32] = {0}, qscale[32] = {0};
     double *dirs = nullptr;      size_t dirs_cap = 0;      // doubles (the workspace may serve plans of different d)
     const double *dirs_view = nullptr;   // when set, the consumers read this (cached direction sets) instead of `dirs`
-    // DZ2019-HW pipelining: the generator of batch b+1 runs on gen_stream into the other buffer while
-    // the max-min kernel of batch b runs on the main stream (different pipes: FP64 vs ALU for the DPX screen)
-    double *dirs_buf[2] = {nullptr, nullptr}; size_t dirs_buf_cap[2] = {0, 0};
-    cudaStream_t gen_stream = nullptr;
-    cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr}, ev_begin = nullptr;
-    bool used_recorded[2] = {false, false};
-    int cur_buf = 0, pending_buf = -1;
-    bool pipelined = false;
     double *cta_sums = nullptr;  int cta_cap = 0;
     double *values = nullptr;    size_t values_cap = 0;
     double *out_hilo = nullptr;
@@ -1680,7 +1637,8 @@ static constexpr KernelCfg cfg_for(int D)
     if (D <= 5)  return {2, 4, 2, true};
     if (D <= 12) return {3, 2, 2, false};
     if (D <= 24) return {1, 2, 2, true};
-    return {1, 2, 2, false};
+    if (D <= 32) return {1, 2, 2, false};
+    return {1, 2, 1, false};      // 33..64 (extension, EXACT only): r[D] alone is up to 128 registers -> one CTA per SM
 }
 static constexpr size_t kSmemPerSm = 227 * 1024;
 static constexpr size_t kBarrierBytes = (2 * kStages + 2) * sizeof(ull) + 8 * sizeof(double);
@@ -1701,8 +1659,12 @@ static maxmin_fn pick_mode(int mode)
     constexpr KernelCfg c = cfg_for(D);
     constexpr KernelCfg e = cfg_exact_for(D);
     static_assert(c.staged == e.staged && c.minb == e.minb, "EXACT and SCREEN share the shared-memory geometry");
-    return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<D, e.R, e.G, MODE_EXACT, e.minb>
-                              : (maxmin_fn)k_maxmin<D, c.R, c.G, MODE_SCREEN, c.minb>;
+    if constexpr (D > 32) {
+        return (maxmin_fn)k_maxmin<D, e.R, e.G, MODE_EXACT, e.minb>;       // the screens stop at 32 objectives
+    } else {
+        return mode == MODE_EXACT ? (maxmin_fn)k_maxmin<D, e.R, e.G, MODE_EXACT, e.minb>
+                                  : (maxmin_fn)k_maxmin<D, c.R, c.G, MODE_SCREEN, c.minb>;
+    }
 }
 template <int D>
 static maxmin_fn pick_d(int d, int mode)
@@ -1714,7 +1676,7 @@ static maxmin_fn pick_d(int d, int mode)
         return pick_d<D - 1>(d, mode);
     }
 }
-static maxmin_fn pick_kernel(int d, int mode) { return pick_d<32>(d, mode); }
+static maxmin_fn pick_kernel(int d, int mode) { return pick_d<HVB200_MAXD>(d, mode); }
 // DPX screen geometry: R directions per thread, G point pairs per group ((G*D) % 4 == 0).
 struct DpxCfg { int R, G, minb; };
 static constexpr DpxCfg dpx_cfg_for(int D)
@@ -1739,11 +1701,7 @@ static dpx_fn pick_dpx(int d)
         return pick_dpx<D - 1>(d);
     }
 }
-static KernelCfg cfg_runtime(int d)
-{
-    if (d > 32) return {1, 1, 1, false};
-    return cfg_for(d);
-}
+static KernelCfg cfg_runtime(int d) { return cfg_for(d); }
 
 // Workspace cache: a DevPlan keeps its device buffers, stream and events when its plan is destroyed
 // and is handed to the next plan created on the same device, so that repeated hv_approx calls (the
@@ -1957,6 +1915,7 @@ extern "C" int hvb200cu_plan_upload_raw(struct hvb200_plan *plan, const double *
 
 static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, const double *pts_dev)
 {
+    HVB200_NVTX("hvb200:plan_create");
     CUDA_TRY(cudaSetDevice(plan->device));
     if (upload_constants(plan->device)) return -1;
     DevPlan *dp = pool_take(plan->device);
@@ -1966,7 +1925,8 @@ static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, co
     dp->d = plan->d;
     dp->n = plan->n;
     dp->ordered = false;
-    dp->bp_ready = false;
+    dp->bp_ready = dp->bp_begun = dp->bp_probe_queued = false;
+    dp->share = plan->share;
     const int d = plan->d;
     const KernelCfg kc = cfg_runtime(d);
     dp->R = kc.R;
@@ -2088,11 +2048,8 @@ static void devplan_release(DevPlan *dp)
 {
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
-    cudaFree(dp->dirs_buf[1]); cudaFree(dp->pts_tmp); cudaFree(dp->wins);
+    cudaFree(dp->pts_tmp); cudaFree(dp->wins); cudaFree(dp->gen_scratch);
     cudaFree(dp->bp_hits); cudaFree(dp->bp_chunk_sums); cudaFree(dp->bp_chunk_counter); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
-    for (int i = 0; i < 2; i++) { if (dp->ev_gen[i]) cudaEventDestroy(dp->ev_gen[i]); if (dp->ev_used[i]) cudaEventDestroy(dp->ev_used[i]); }
-    if (dp->ev_begin) cudaEventDestroy(dp->ev_begin);
-    if (dp->gen_stream) cudaStreamDestroy(dp->gen_stream);
     for (int i = 0; i < 2; i++) {
         if (dp->staging_host[i]) cudaFreeHost(dp->staging_host[i]);
         if (dp->staging_free[i]) cudaEventDestroy(dp->staging_free[i]);
@@ -2105,19 +2062,6 @@ static void devplan_release(DevPlan *dp)
     delete dp;
 }
 
-static int span_begin_on(DevPlan *dp, int kind, cudaStream_t st)
-{
-    while (dp->ev_pool.size() < dp->ev_next + 2) {
-        cudaEvent_t e;
-        if (cudaEventCreate(&e) != cudaSuccess) return -1;
-        dp->ev_pool.push_back(e);
-    }
-    const int a = (int)dp->ev_next, b = a + 1;
-    dp->ev_next += 2;
-    dp->spans.push_back({a, b, kind});
-    cudaEventRecord(dp->ev_pool[a], st);
-    return b;
-}
 static int span_begin(DevPlan *dp, int kind)
 {
     while (dp->ev_pool.size() < dp->ev_next + 2) {
@@ -2144,11 +2088,34 @@ static bp_fn pick_bp(int d)
     if constexpr (D < 2) {
         return nullptr;
     } else {
-        if (d == D) return (bp_fn)k_maxmin_bp<D, bp_R_of(D)>;
+        if (d == D) return (bp_fn)k_maxmin_bp<D, bp_R_of(D), false>;
         return pick_bp<D - 1>(d);
     }
 }
-static void bp_kd_order(const std::vector<double> &norm, int d, std::vector<unsigned> &idx, size_t lo, size_t hi, int depth = 0)
+// the variant that generates its DZ2019-HW directions itself (d <= 32: the reference's method stops there)
+template <int D>
+static bp_fn pick_bp_gen(int d)
+{
+    if constexpr (D < 2) {
+        return nullptr;
+    } else {
+        if (d == D) return (bp_fn)k_maxmin_bp<D, bp_R_of(D), true>;
+        return pick_bp_gen<D - 1>(d);
+    }
+}
+// Host threads of one kd build: 2^g_kd_depth.  Several plans may be prepared at the same time — one process per GPU
+// under torchrun (LOCAL_WORLD_SIZE), or the shard threads of a single-process multi-GPU call — so the build takes
+// its share of the host's cores instead of 8 threads each (64 threads on a 32-core box at 8 GPUs).
+static int bp_kd_depth()
+{
+    unsigned cores = std::thread::hardware_concurrency();
+    if (cores == 0) cores = 8;
+    int sharers = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) sharers = std::max(1, atoi(e));
+    const unsigned mine = std::max(1u, cores / (unsigned)sharers);
+    return mine >= 8 ? 3 : (mine >= 4 ? 2 : (mine >= 2 ? 1 : 0));
+}
+static void bp_kd_order(const std::vector<double> &norm, int d, std::vector<unsigned> &idx, size_t lo, size_t hi, int max_depth, int depth = 0)
 {
     const size_t cnt = hi - lo;
     if (cnt <= (size_t)kBpBlock) return;
@@ -2169,14 +2136,14 @@ static void bp_kd_order(const std::vector<double> &norm, int d, std::vector<unsi
     std::nth_element(kv.begin(), kv.begin() + half, kv.end());
     for (size_t i = 0; i < cnt; i++) idx[lo + i] = kv[i].second;
     std::vector<std::pair<double, unsigned>>().swap(kv);
-    if (depth < 3 && cnt >= 2048) {
-        // the two halves touch disjoint index ranges: 8 host threads at the third level
-        std::thread left([&] { bp_kd_order(norm, d, idx, lo, lo + half, depth + 1); });
-        bp_kd_order(norm, d, idx, lo + half, hi, depth + 1);
+    if (depth < max_depth && cnt >= 2048) {
+        // the two halves touch disjoint index ranges
+        std::thread left([&] { bp_kd_order(norm, d, idx, lo, lo + half, max_depth, depth + 1); });
+        bp_kd_order(norm, d, idx, lo + half, hi, max_depth, depth + 1);
         left.join();
     } else {
-        bp_kd_order(norm, d, idx, lo, lo + half, depth + 1);
-        bp_kd_order(norm, d, idx, lo + half, hi, depth + 1);
+        bp_kd_order(norm, d, idx, lo, lo + half, max_depth, depth + 1);
+        bp_kd_order(norm, d, idx, lo + half, hi, max_depth, depth + 1);
     }
 }
 static int bp_pivot_count()
@@ -2185,14 +2152,37 @@ static int bp_pivot_count()
     const int v = e ? atoi(e) : 320;
     return v < 1 ? 1 : (v > kBpMaxPivots ? kBpMaxPivots : v);
 }
-static int bp_prepare(DevPlan *dp)
+static size_t bp_npiv_for(size_t n)
+{
+    // pivots: up to 320, about an eighth of a small set (n=1000: 128 pivots 3.75 Tsp/s, 256 pivots 3.1)
+    size_t npiv = std::min<size_t>(n, (size_t)bp_pivot_count());
+    if (!getenv("HVB200_BP_PIVOTS")) npiv = std::min<size_t>(npiv, std::max<size_t>(16, n / 8));
+    return npiv;
+}
+
+// What the pruned kernel's preparation builds on the host.  It depends on the transformed point set only, so the
+// plans that hvb200_hv_approx_multi creates for the same set on several GPUs build it once and share it (BpShare).
+struct BpHostPrep {
+    std::vector<double> sorted;          // [n_pad][d] points in kd order, zero padded
+    std::vector<float> piv32;            // [npiv][d]
+    std::vector<unsigned> pividx;        // [npiv] row of each pivot in `sorted`
+    std::vector<unsigned> pkeys;         // [nb_pad][W][32]
+    std::vector<unsigned> bpair;         // [nb_pad/2][d]
+    double qscale[HVB200_MAXD], qlos[HVB200_MAXD];
+    int rc = 0;
+};
+struct BpShare { std::once_flag once; BpHostPrep prep; };
+extern "C" void *hvb200cu_share_new(void) { return new (std::nothrow) BpShare(); }
+extern "C" void hvb200cu_share_free(void *p) { delete (BpShare *)p; }
+
+// Stage 1, at the start of a run: geometry (it depends on n and d only) and the probe kernel, asynchronously.  The
+// host part (stage 2) runs when the first max-min launch is due — by then the direction generator of the first
+// batch has been queued, so the 1.6 ms of host work at cfg3 hide behind it instead of idling the GPU.
+static int bp_prepare_begin(DevPlan *dp)
 {
     const size_t n = dp->n;
-    const int d = dp->d, W = (d + 1) / 2;
+    const int d = dp->d;
     cudaStream_t us = dp->own_stream;
-    const bool dbg = getenv("HVB200_DEBUG_TIMING") != nullptr;
-    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t0 = now();
     unsigned nprobe = 4096;
     while (nprobe > 256 && (double)nprobe * (double)n > 6e8) nprobe /= 2;
     if (dp->wins_cap < 2 * n) {
@@ -2201,7 +2191,48 @@ static int bp_prepare(DevPlan *dp)
         CUDA_TRY(cudaMalloc(&dp->wins, 2 * n * sizeof(unsigned)));
         dp->wins_cap = 2 * n;
     }
-    // the points come back first; the probe kernel (only the pivots need it) then runs under the host's kd build
+    const size_t npiv = bp_npiv_for(n);
+    const int nb = (int)((n + kBpBlock - 1) / kBpBlock);
+    const int nb_pad = (nb + 2 * kBpG - 1) / (2 * kBpG) * (2 * kBpG);
+    dp->bp_nb = nb;
+    dp->bp_nb_pad = nb_pad;
+    dp->bp_npiv = (int)npiv;
+    // segment = as many blocks as fit the shared-memory budget of one CTA (3 CTAs per SM up to d = 16, else 2)
+    const size_t budget = (d <= 16 ? (HVB200_BP_MINB >= 4 ? 55 : 74) : 112) * 1024;
+    int seg = (nb_pad + 31) / 32 * 32;
+    while (seg > 32 && bp_smem_layout(d, bp_R_of(d), seg, (int)npiv).total > budget) seg -= 32;
+    if (const char *e = getenv("HVB200_BP_SEG")) { const int v = atoi(e) / 32 * 32; if (v >= 32 && v < seg) seg = v; }
+    dp->bp_seg_blocks = seg;
+    dp->bp_smem = bp_smem_layout(d, bp_R_of(d), seg, (int)npiv).total;
+    dp->bp_probe_queued = false;
+    if (!dp->share) {
+        // (a shared preparation probes on the device of whichever plan builds it, see bp_prepare_finish)
+        CUDA_TRY(cudaMemsetAsync(dp->wins, 0, n * sizeof(unsigned), us));
+        k_probe_argmax<<<(nprobe * 32 + 127) / 128, 128, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, dp->wins);
+        CUDA_TRY(cudaGetLastError());
+        dp->bp_probe_queued = true;
+    }
+    dp->bp_begun = true;
+    return 0;
+}
+
+static int bp_host_build(DevPlan *dp, BpHostPrep &H)
+{
+    HVB200_NVTX("hvb200:pruned_prepare_host");
+    const size_t n = dp->n;
+    const int d = dp->d, W = (d + 1) / 2;
+    cudaStream_t us = dp->own_stream;
+    const bool dbg = getenv("HVB200_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    unsigned nprobe = 4096;
+    while (nprobe > 256 && (double)nprobe * (double)n > 6e8) nprobe /= 2;
+    if (!dp->bp_probe_queued) {
+        CUDA_TRY(cudaMemsetAsync(dp->wins, 0, n * sizeof(unsigned), us));
+        k_probe_argmax<<<(nprobe * 32 + 127) / 128, 128, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, dp->wins);
+        CUDA_TRY(cudaGetLastError());
+        dp->bp_probe_queued = true;
+    }
     std::vector<unsigned> wins(n);
     std::vector<double> pts_rb;
     if (dp->host_pts.size() != n * (size_t)d || dp->ordered) {
@@ -2211,9 +2242,6 @@ static int bp_prepare(DevPlan *dp)
         CUDA_TRY(cudaStreamSynchronize(us));
     }
     const std::vector<double> &pts = pts_rb.empty() ? dp->host_pts : pts_rb;
-    CUDA_TRY(cudaMemsetAsync(dp->wins, 0, n * sizeof(unsigned), us));
-    k_probe_argmax<<<(nprobe * 32 + 127) / 128, 128, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, dp->wins);
-    CUDA_TRY(cudaGetLastError());
     if (dbg) fprintf(stderr, "bp_prepare: d2h %.2f ms\n", now() - t0);
     // key map of the point set (the same monotone map as the DPX screen, any d <= 64)
     std::vector<double> qlo(d, INFINITY), qhi(d, -INFINITY), qscale(d, 0.0);
@@ -2223,12 +2251,13 @@ static int bp_prepare(DevPlan *dp)
             if (v < qlo[k]) qlo[k] = v;
             if (v > qhi[k]) qhi[k] = v;
         }
+    for (int k = 0; k < HVB200_MAXD; k++) { H.qscale[k] = 0.0; H.qlos[k] = 0.0; }
     for (int k = 0; k < d; k++) {
         const double range = qhi[k] - qlo[k];
         qscale[k] = (range > 0 && std::isfinite(range)) ? (double)kKeyScale / range : 0.0;
         if (!std::isfinite(qscale[k])) qscale[k] = 0.0;
-        dp->bp_qscale[k] = qscale[k];
-        dp->bp_qlos[k] = qlo[k] * qscale[k] * (1.0 + 0x1p-20) + 0x1p-10;
+        H.qscale[k] = qscale[k];
+        H.qlos[k] = qlo[k] * qscale[k] * (1.0 + 0x1p-20) + 0x1p-10;
     }
     // kd-tree order on the normalised coordinates
     std::vector<double> norm(n * (size_t)d);
@@ -2237,34 +2266,15 @@ static int bp_prepare(DevPlan *dp)
     std::vector<unsigned> idx(n);
     for (size_t i = 0; i < n; i++) idx[i] = (unsigned)i;
     if (dbg) fprintf(stderr, "bp_prepare: ranges+norm %.2f ms\n", now() - t0);
-    bp_kd_order(norm, d, idx, 0, n);
+    bp_kd_order(norm, d, idx, 0, n, bp_kd_depth());
     if (dbg) fprintf(stderr, "bp_prepare: kd %.2f ms\n", now() - t0);
     std::vector<unsigned> pos(n);
     for (size_t i = 0; i < n; i++) pos[idx[i]] = (unsigned)i;
-    // (a copy into pageable memory blocks until the probe kernel is done: issued only now, after the kd build)
-    CUDA_TRY(cudaMemcpyAsync(wins.data(), dp->wins, n * sizeof(unsigned), cudaMemcpyDeviceToHost, us));
-    CUDA_TRY(cudaStreamSynchronize(us));               // probe wins are on the host now
-    if (dbg) fprintf(stderr, "bp_prepare: probe wait %.2f ms\n", now() - t0);
-    // pivots: the points that won most probes
-    // pivots: up to 256, about an eighth of a small set (n=1000: 128 pivots 3.75 Tsp/s, 256 pivots 3.1)
-    size_t npiv = std::min<size_t>(n, (size_t)bp_pivot_count());
-    if (!getenv("HVB200_BP_PIVOTS")) npiv = std::min<size_t>(npiv, std::max<size_t>(16, n / 8));
-    std::vector<unsigned> byw(n);
-    for (size_t i = 0; i < n; i++) byw[i] = (unsigned)i;
-    std::partial_sort(byw.begin(), byw.begin() + npiv, byw.end(),
-                      [&](unsigned x, unsigned y) { return wins[x] != wins[y] ? wins[x] > wins[y] : x < y; });
-    std::vector<float> piv32(npiv * (size_t)d);
-    std::vector<unsigned> pividx(npiv);
-    for (size_t i = 0; i < npiv; i++) {
-        pividx[i] = pos[byw[i]];
-        for (int k = 0; k < d; k++) piv32[i * d + k] = (float)pts[(size_t)byw[i] * d + k];
-    }
-    const int nb = (int)((n + kBpBlock - 1) / kBpBlock);
-    const int nb_pad = (nb + 2 * kBpG - 1) / (2 * kBpG) * (2 * kBpG);
+    const int nb = dp->bp_nb, nb_pad = dp->bp_nb_pad;
     const size_t n_pad = (size_t)nb_pad * kBpBlock;
-    std::vector<double> sorted(n_pad * (size_t)d, 0.0);
+    H.sorted.assign(n_pad * (size_t)d, 0.0);
+    std::vector<double> &sorted = H.sorted;
     for (size_t i = 0; i < n; i++) memcpy(&sorted[i * d], &pts[(size_t)idx[i] * d], d * sizeof(double));
-    if (dbg) fprintf(stderr, "bp_prepare: pivots+sorted %.2f ms\n", now() - t0);
     // point keys KP = clamp(ceil f_k(p), 0, S); padding points -1, dummy objective of an odd d = S (always passes)
     std::vector<unsigned short> key(n_pad * (size_t)(2 * W));
     for (size_t i = 0; i < n_pad; i++)
@@ -2279,15 +2289,15 @@ static int bp_prepare(DevPlan *dp)
             }
             key[i * (2 * W) + k] = v;
         }
-    std::vector<unsigned> pkeys((size_t)nb_pad * W * kBpBlock);
+    H.pkeys.resize((size_t)nb_pad * W * kBpBlock);
     for (int b = 0; b < nb_pad; b++)
         for (int j = 0; j < W; j++)
             for (int l = 0; l < kBpBlock; l++) {
                 const size_t i = (size_t)b * kBpBlock + l;
-                pkeys[((size_t)b * W + j) * kBpBlock + l] = (unsigned)key[i * (2 * W) + 2 * j] | ((unsigned)key[i * (2 * W) + 2 * j + 1] << 16);
+                H.pkeys[((size_t)b * W + j) * kBpBlock + l] = (unsigned)key[i * (2 * W) + 2 * j] | ((unsigned)key[i * (2 * W) + 2 * j + 1] << 16);
             }
     // block bounds: per-objective maximum key (signed: padding -1 never raises it), two blocks per word
-    std::vector<unsigned> bpair((size_t)(nb_pad / 2) * d);
+    H.bpair.resize((size_t)(nb_pad / 2) * d);
     for (int pr = 0; pr < nb_pad / 2; pr++)
         for (int k = 0; k < d; k++) {
             unsigned word = 0;
@@ -2298,9 +2308,45 @@ static int bp_prepare(DevPlan *dp)
                     for (int l = 0; l < kBpBlock; l++) m = std::max(m, (int)(short)key[((size_t)b * kBpBlock + l) * (2 * W) + k]);
                 word |= ((unsigned)m & 0xffffu) << (16 * h);
             }
-            bpair[(size_t)pr * d + k] = word;
+            H.bpair[(size_t)pr * d + k] = word;
         }
-    if (dbg) fprintf(stderr, "bp_prepare: keys %.2f ms\n", now() - t0);
+    if (dbg) fprintf(stderr, "bp_prepare: sorted+keys %.2f ms\n", now() - t0);
+    // (a copy into pageable memory blocks until the probe kernel is done: issued only now, after the kd build)
+    CUDA_TRY(cudaMemcpyAsync(wins.data(), dp->wins, n * sizeof(unsigned), cudaMemcpyDeviceToHost, us));
+    CUDA_TRY(cudaStreamSynchronize(us));               // probe wins are on the host now
+    if (dbg) fprintf(stderr, "bp_prepare: probe wait %.2f ms\n", now() - t0);
+    // pivots: the points that won most probes
+    const size_t npiv = (size_t)dp->bp_npiv;
+    std::vector<unsigned> byw(n);
+    for (size_t i = 0; i < n; i++) byw[i] = (unsigned)i;
+    std::partial_sort(byw.begin(), byw.begin() + npiv, byw.end(),
+                      [&](unsigned x, unsigned y) { return wins[x] != wins[y] ? wins[x] > wins[y] : x < y; });
+    H.piv32.resize(npiv * (size_t)d);
+    H.pividx.resize(npiv);
+    for (size_t i = 0; i < npiv; i++) {
+        H.pividx[i] = pos[byw[i]];
+        for (int k = 0; k < d; k++) H.piv32[i * d + k] = (float)pts[(size_t)byw[i] * d + k];
+    }
+    if (dbg) fprintf(stderr, "bp_prepare: pivots %.2f ms\n", now() - t0);
+    return 0;
+}
+
+// Stage 2: host build (own or shared) + uploads.  Called by the first max-min launch of the plan.
+static int bp_prepare_finish(DevPlan *dp)
+{
+    HVB200_NVTX("hvb200:pruned_prepare");
+    const int d = dp->d;
+    cudaStream_t us = dp->own_stream;
+    BpHostPrep own;
+    BpHostPrep *H = &own;
+    if (dp->share) {
+        BpShare *sh = (BpShare *)dp->share;
+        std::call_once(sh->once, [&] { sh->prep.rc = bp_host_build(dp, sh->prep); });
+        H = &sh->prep;
+        if (H->rc) return -1;
+        CUDA_TRY(cudaSetDevice(dp->device));
+    } else if (bp_host_build(dp, own)) return -1;
+    const size_t n_pad = (size_t)dp->bp_nb_pad * kBpBlock;
     if (dp->bp_pts_cap < n_pad * (size_t)d) {
         cudaFree(dp->bp_pts);
         dp->bp_pts = nullptr; dp->bp_pts_cap = 0;
@@ -2311,35 +2357,25 @@ static int bp_prepare(DevPlan *dp)
         CUDA_TRY(cudaMalloc(&dp->bp_piv32, (size_t)kBpMaxPivots * HVB200_MAXD * sizeof(float)));
         CUDA_TRY(cudaMalloc(&dp->bp_pividx, (size_t)kBpMaxPivots * sizeof(unsigned)));
     }
-    if (dp->bp_keys_cap < pkeys.size()) {
+    if (dp->bp_keys_cap < H->pkeys.size()) {
         cudaFree(dp->bp_pkeys);
         dp->bp_pkeys = nullptr; dp->bp_keys_cap = 0;
-        CUDA_TRY(cudaMalloc(&dp->bp_pkeys, pkeys.size() * sizeof(unsigned)));
-        dp->bp_keys_cap = pkeys.size();
+        CUDA_TRY(cudaMalloc(&dp->bp_pkeys, H->pkeys.size() * sizeof(unsigned)));
+        dp->bp_keys_cap = H->pkeys.size();
     }
-    if (dp->bp_pair_cap < bpair.size()) {
+    if (dp->bp_pair_cap < H->bpair.size()) {
         cudaFree(dp->bp_bpair);
         dp->bp_bpair = nullptr; dp->bp_pair_cap = 0;
-        CUDA_TRY(cudaMalloc(&dp->bp_bpair, bpair.size() * sizeof(unsigned)));
-        dp->bp_pair_cap = bpair.size();
+        CUDA_TRY(cudaMalloc(&dp->bp_bpair, H->bpair.size() * sizeof(unsigned)));
+        dp->bp_pair_cap = H->bpair.size();
     }
-    CUDA_TRY(cudaMemcpyAsync(dp->bp_pts, sorted.data(), sorted.size() * sizeof(double), cudaMemcpyHostToDevice, us));
-    CUDA_TRY(cudaMemcpyAsync(dp->bp_piv32, piv32.data(), piv32.size() * sizeof(float), cudaMemcpyHostToDevice, us));
-    CUDA_TRY(cudaMemcpyAsync(dp->bp_pividx, pividx.data(), pividx.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
-    CUDA_TRY(cudaMemcpyAsync(dp->bp_pkeys, pkeys.data(), pkeys.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
-    CUDA_TRY(cudaMemcpyAsync(dp->bp_bpair, bpair.data(), bpair.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
-    CUDA_TRY(cudaStreamSynchronize(us));              // host vectors go out of scope
-    if (dbg) fprintf(stderr, "bp_prepare: uploads %.2f ms\n", now() - t0);
-    dp->bp_nb = nb;
-    dp->bp_nb_pad = nb_pad;
-    dp->bp_npiv = (int)npiv;
-    // segment = as many blocks as fit the shared-memory budget of one CTA (3 CTAs per SM up to d = 16, else 2)
-    const size_t budget = (d <= 16 ? (HVB200_BP_MINB >= 4 ? 55 : 74) : 112) * 1024;
-    int seg = (nb_pad + 31) / 32 * 32;
-    while (seg > 32 && bp_smem_layout(d, bp_R_of(d), seg, (int)npiv).total > budget) seg -= 32;
-    if (const char *e = getenv("HVB200_BP_SEG")) { const int v = atoi(e) / 32 * 32; if (v >= 32 && v < seg) seg = v; }
-    dp->bp_seg_blocks = seg;
-    dp->bp_smem = bp_smem_layout(d, bp_R_of(d), seg, (int)npiv).total;
+    for (int k = 0; k < HVB200_MAXD; k++) { dp->bp_qscale[k] = H->qscale[k]; dp->bp_qlos[k] = H->qlos[k]; }
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_pts, H->sorted.data(), H->sorted.size() * sizeof(double), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_piv32, H->piv32.data(), H->piv32.size() * sizeof(float), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_pividx, H->pividx.data(), H->pividx.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_pkeys, H->pkeys.data(), H->pkeys.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaMemcpyAsync(dp->bp_bpair, H->bpair.data(), H->bpair.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
+    CUDA_TRY(cudaStreamSynchronize(us));              // host vectors go out of scope; the run's stream may be another one
     dp->bp_ready = true;
     return 0;
 }
@@ -2425,12 +2461,6 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     batch -= batch % (uint64_t)(kConsumerThreads * 4);
     if (batch > max_batch) batch = max_batch;
     if (batch < 1) batch = 1;
-    if (dp->dirs_cap < batch * (size_t)(2 * d)) {
-        cudaFree(dp->dirs);
-        dp->dirs = nullptr; dp->dirs_cap = 0;
-        CUDA_TRY(cudaMalloc(&dp->dirs, batch * (size_t)(2 * d) * sizeof(double)));
-        dp->dirs_cap = batch * (size_t)(2 * d);
-    }
     *batch_out = batch;
 
     // kernel selection + launch geometry
@@ -2454,15 +2484,22 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     if (mode == MODE_BP && dp->n / 32 + 64 >= ((size_t)1 << kBpPtBits)) mode = MODE_DPX;   // hit entries hold 23-bit granule (32-point) indices
     if (d > 32 && mode != MODE_BP) mode = MODE_EXACT;
     dp->kernel_used = mode;
-    if ((mode == MODE_DPX || mode == MODE_SCREEN) && !dp->ordered && dp->n >= 1024 && plan->run_samples >= (1u << 20) &&
+    if ((mode == MODE_DPX || mode == MODE_SCREEN || mode == MODE_EXACT) && d <= 32 && !dp->ordered && dp->n >= 1024 && plan->run_samples >= (1u << 20) &&
         !getenv("HVB200_NO_ORDER")) {
         if (order_points(dp)) return -1;
     }
-    if (mode == MODE_BP && !dp->bp_ready && bp_prepare(dp)) return -1;
+    if (mode == MODE_BP && !dp->bp_ready && bp_prepare_begin(dp)) return -1;
     const size_t smem = mode == MODE_DPX ? dp->k_smem_bytes : (mode == MODE_BP ? dp->bp_smem : dp->smem_bytes);
     int occ = 1;
+    dp->fused = mode == MODE_BP && plan->want_fused_hw && d <= 32 && !getenv("HVB200_NO_FUSED");
+    if (!dp->fused && dp->dirs_cap < batch * (size_t)(2 * d)) {       // (a fused run has no direction buffer)
+        cudaFree(dp->dirs);
+        dp->dirs = nullptr; dp->dirs_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->dirs, batch * (size_t)(2 * d) * sizeof(double)));
+        dp->dirs_cap = batch * (size_t)(2 * d);
+    }
     if (mode == MODE_BP) {
-        bp_fn fn = pick_bp<HVB200_MAXD>(d);
+        bp_fn fn = dp->fused ? pick_bp_gen<32>(d) : pick_bp<HVB200_MAXD>(d);
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBpThreads, smem));
@@ -2471,15 +2508,11 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBlockThreads, smem));
-    } else if (d <= 32) {
+    } else {
         maxmin_fn fn = pick_kernel(d, mode);
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
         CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, kBlockThreads, smem));
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute((const void *)k_maxmin_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
-        CUDA_TRY(cudaFuncSetAttribute((const void *)k_maxmin_generic, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k_maxmin_generic, kBlockThreads, smem));
     }
     if (occ < 1) { hvb200_set_error("max-min kernel does not fit on an SM (d=%d)", d); return -1; }
     dp->grid = dp->sm_count * occ;
@@ -2488,6 +2521,15 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
         dp->bp_hits = nullptr; dp->bp_hits_cap = 0;
         CUDA_TRY(cudaMalloc(&dp->bp_hits, (size_t)dp->grid * kBpHitCap * sizeof(uint2)));
         dp->bp_hits_cap = (size_t)dp->grid * kBpHitCap;
+    }
+    if (dp->fused) {
+        const size_t need = (size_t)dp->grid * 2 * d * kBpThreads * bp_R_of(d);
+        if (dp->gen_scratch_cap < need) {
+            cudaFree(dp->gen_scratch);
+            dp->gen_scratch = nullptr; dp->gen_scratch_cap = 0;
+            CUDA_TRY(cudaMalloc(&dp->gen_scratch, need * sizeof(double)));
+            dp->gen_scratch_cap = need;
+        }
     }
     if (mode == MODE_BP) {
         const size_t ch = (size_t)kBpThreads * bp_R_of(d);
@@ -2508,9 +2550,6 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     }
     CUDA_TRY(cudaMemsetAsync(dp->cta_sums, 0, dp->cta_cap * sizeof(double), dp->stream));
     CUDA_TRY(cudaMemsetAsync(dp->counters, 0, 8 * sizeof(ull), dp->stream));
-    dp->pipelined = false;
-    dp->pending_buf = -1;
-    dp->used_recorded[0] = dp->used_recorded[1] = false;
     return 0;
 }
 
@@ -2572,6 +2611,7 @@ extern "C" int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params 
 // directions [i0, i0 + count) of the lattice into rows [offset, offset + count) of the direction buffer
 extern "C" int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count, uint64_t offset)
 {
+    HVB200_NVTX("hvb200:gen_hw");
     DevPlan *dp = (DevPlan *)plan->dev;
     if ((offset + count) * (uint64_t)(2 * hw->d) > dp->dirs_cap) { hvb200_set_error("internal: direction buffer overflow"); return -1; }
     if (hw->nsamples > (1ull << 32)) { hvb200_set_error("DZ2019-HW on the device supports nsamples <= 2^32"); return -1; }
@@ -2586,67 +2626,6 @@ extern "C" int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_para
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
     plan->stats.dirgen_launches++;
-    return 0;
-}
-// Pipelined DZ2019-HW: prefetch(batch b+1) on gen_stream into the buffer that is not in use, then
-// swap() makes the main stream wait for it and points the max-min kernel at it.
-extern "C" int hvb200cu_hw_prefetch(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count)
-{
-    DevPlan *dp = (DevPlan *)plan->dev;
-    if (hw->nsamples > (1ull << 32)) { hvb200_set_error("DZ2019-HW on the device supports nsamples <= 2^32"); return -1; }
-    if (!dp->gen_stream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&dp->gen_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_gen[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_used[i], cudaEventDisableTiming));
-        }
-        CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_begin, cudaEventDisableTiming));
-    }
-    if (!dp->pipelined) {
-        // first prefetch of a run: adopt the run's direction buffer as buffer 0, order the generator
-        // stream behind the run's initial memsets
-        dp->dirs_buf[0] = dp->dirs; dp->dirs_buf_cap[0] = dp->dirs_cap;
-        dp->cur_buf = 1;                      // so that the first prefetch targets buffer 0
-        CUDA_TRY(cudaEventRecord(dp->ev_begin, dp->stream));
-        CUDA_TRY(cudaStreamWaitEvent(dp->gen_stream, dp->ev_begin, 0));
-        dp->pipelined = true;
-    }
-    const int buf = dp->cur_buf ^ 1;
-    const size_t need = count * (size_t)(2 * dp->d);
-    if (dp->dirs_buf_cap[buf] < need) {
-        if (dp->used_recorded[buf]) CUDA_TRY(cudaEventSynchronize(dp->ev_used[buf]));
-        cudaFree(dp->dirs_buf[buf]);
-        dp->dirs_buf[buf] = nullptr; dp->dirs_buf_cap[buf] = 0;
-        const size_t cap = std::max(need, dp->dirs_cap);
-        CUDA_TRY(cudaMalloc(&dp->dirs_buf[buf], cap * sizeof(double)));
-        dp->dirs_buf_cap[buf] = cap;
-    }
-    if (dp->used_recorded[buf]) CUDA_TRY(cudaStreamWaitEvent(dp->gen_stream, dp->ev_used[buf], 0));
-    HwDev P;
-    P.N = hw->nsamples;
-    P.Nrecip = hw->nsamples ? ~0ull / hw->nsamples : 0;
-    P.d = hw->d;
-    for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
-    const int b = span_begin_on(dp, 1, dp->gen_stream);
-    if (gen_hw_staged(hw->d)) k_gen_hw<true><<<(unsigned)((count + 127) / 128), 128, gen_hw_smem_bytes(hw->d), dp->gen_stream>>>(P, i0, count, dp->dirs_buf[buf], dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
-    else k_gen_hw<false><<<(unsigned)((count + 127) / 128), 128, 0, dp->gen_stream>>>(P, i0, count, dp->dirs_buf[buf], dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
-    if (b >= 0) cudaEventRecord(dp->ev_pool[b], dp->gen_stream);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(dp->ev_gen[buf], dp->gen_stream));
-    dp->pending_buf = buf;
-    plan->stats.dirgen_launches++;
-    return 0;
-}
-extern "C" int hvb200cu_hw_swap(struct hvb200_plan *plan)
-{
-    DevPlan *dp = (DevPlan *)plan->dev;
-    if (dp->pending_buf < 0) { hvb200_set_error("internal: swap without prefetch"); return -1; }
-    const int buf = dp->pending_buf;
-    CUDA_TRY(cudaStreamWaitEvent(dp->stream, dp->ev_gen[buf], 0));
-    dp->cur_buf = buf;
-    dp->dirs = dp->dirs_buf[buf];
-    dp->dirs_cap = dp->dirs_buf_cap[buf];
-    dp->pending_buf = -1;
     return 0;
 }
 extern "C" int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count)
@@ -2680,6 +2659,7 @@ extern "C" int hvb200cu_mc_skip(struct hvb200_plan *plan, uint64_t nnormals)
 }
 extern "C" int hvb200cu_gen_mc_device(struct hvb200_plan *plan, uint64_t count)
 {
+    HVB200_NVTX("hvb200:gen_mc");
     DevPlan *dp = (DevPlan *)plan->dev;
     const size_t ndoubles = count * (size_t)dp->d;
     if (dp->staging_dev_cap < ndoubles) {
@@ -2698,6 +2678,7 @@ extern "C" int hvb200cu_gen_mc_device(struct hvb200_plan *plan, uint64_t count)
 }
 extern "C" int hvb200cu_gen_rphi(struct hvb200_plan *plan, const double *u_host, uint64_t count)
 {
+    HVB200_NVTX("hvb200:gen_rphi");
     DevPlan *dp = (DevPlan *)plan->dev;
     if (stage_to_device(plan, dp, u_host, count * (size_t)(dp->d - 1))) return -1;
     const int b = span_begin(dp, 1);
@@ -2770,8 +2751,78 @@ extern "C" int hvb200cu_read_dirs(struct hvb200_plan *plan, uint64_t count, doub
     return 0;
 }
 
+// the arguments of k_maxmin_bp that do not depend on where the directions come from
+static int bp_fill_args(DevPlan *dp, BpArgs &ka, uint64_t count, ull n_chunks)
+{
+    const int d = dp->d;
+    memset(&ka, 0, sizeof ka);
+    ka.pts = dp->bp_pts;
+    ka.piv32 = dp->bp_piv32;
+    ka.piv_idx = dp->bp_pividx;
+    ka.n_piv = dp->bp_npiv;
+    ka.pkeys = dp->bp_pkeys;
+    ka.bpair = dp->bp_bpair;
+    ka.nb = dp->bp_nb;
+    ka.nb_pad = dp->bp_nb_pad;
+    ka.seg_blocks = dp->bp_seg_blocks;
+    ka.count = count;
+    if (dp->bp_chunk_off + n_chunks > dp->bp_chunk_cap) { hvb200_set_error("internal: chunk buffer too small"); return -1; }
+    ka.chunk_sums = dp->bp_chunk_sums + dp->bp_chunk_off;
+    dp->bp_chunk_off += (size_t)n_chunks;
+    ka.chunk_counter = dp->bp_chunk_counter;
+    CUDA_TRY(cudaMemsetAsync(dp->bp_chunk_counter, 0, sizeof(unsigned), dp->stream));
+    ka.slow_counter = dp->counters + 1;
+    ka.capped_counter = dp->counters;
+    ka.hits = dp->bp_hits;
+    for (int k = 0; k < HVB200_MAXD; k++) {
+        ka.qscale[k] = k < d ? dp->bp_qscale[k] : 0.0;
+        ka.qlos[k] = k < d ? dp->bp_qlos[k] : 0.0;
+    }
+    return 0;
+}
+
+extern "C" int hvb200cu_run_is_fused(struct hvb200_plan *plan) { return ((DevPlan *)plan->dev)->fused ? 1 : 0; }
+
+// DZ2019-HW sum with the generator fused into the max-min kernel: `count` directions, position p of the launch being
+// lattice index first + ((p >> shift) * stride << shift) + (p & (2^shift - 1)).  One launch whatever the count: there
+// is no direction buffer to size it by.
+extern "C" int hvb200cu_maxmin_hw_fused(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t first, int shift,
+                                        uint64_t stride, uint64_t count)
+{
+    HVB200_NVTX("hvb200:maxmin_hw_fused");
+    DevPlan *dp = (DevPlan *)plan->dev;
+    const int d = dp->d;
+    if (!dp->fused || dp->kernel_used != MODE_BP) { hvb200_set_error("internal: run was not set up for the fused kernel"); return -1; }
+    if (count == 0) return 0;
+    if (!dp->bp_ready && bp_prepare_finish(dp)) return -1;
+    const ull chunk = (ull)kBpThreads * bp_R_of(d);
+    const ull n_chunks = (count + chunk - 1) / chunk;
+    if (n_chunks > 0xfffffff0ull) { hvb200_set_error("internal: too many chunks for one launch"); return -1; }
+    const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks);
+    BpArgs ka;
+    const int b = span_begin(dp, 0);
+    if (bp_fill_args(dp, ka, count, n_chunks)) return -1;
+    ka.hw.N = hw->nsamples;
+    ka.hw.Nrecip = hw->nsamples ? ~0ull / hw->nsamples : 0;
+    ka.hw.d = hw->d;
+    for (int k = 0; k < HVB200_MAXD; k++) ka.hw.a[k] = hw->a[k];
+    ka.gen_i0 = first;
+    ka.gen_stride = stride;
+    ka.gen_shift = shift;
+    ka.gen_tab = dp->device < 16 ? g_hw_tab[dp->device] : nullptr;
+    ka.gen_ntab = g_hw_ntab;
+    ka.gen_scratch = dp->gen_scratch;
+    bp_fn fn = pick_bp_gen<32>(d);
+    fn<<<grid, kBpThreads, dp->bp_smem, dp->stream>>>(ka);
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.maxmin_launches++;
+    return 0;
+}
+
 extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double *values_host)
 {
+    HVB200_NVTX("hvb200:maxmin");
     DevPlan *dp = (DevPlan *)plan->dev;
     const int d = dp->d;
     if (values_host && dp->values_cap < count) {
@@ -2792,6 +2843,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     a.values = values_host ? dp->values : nullptr;
     a.slow_counter = dp->counters + 1;
     const bool dpx = dp->kernel_used == MODE_DPX, bp = dp->kernel_used == MODE_BP;
+    if (bp && !dp->bp_ready && bp_prepare_finish(dp)) return -1;     // host part of the preparation, behind the queued generator
     const size_t smem = dpx ? dp->k_smem_bytes : (bp ? dp->bp_smem : dp->smem_bytes);
     const ull chunk = bp ? (ull)kBpThreads * bp_R_of(d)
                          : (ull)kConsumerThreads * (dpx ? dp->kR : (dp->kernel_used == MODE_EXACT ? dp->R_exact : dp->R));
@@ -2800,29 +2852,9 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     const int b = span_begin(dp, 0);
     if (bp) {
         BpArgs ka;
-        ka.pts = dp->bp_pts;
-        ka.piv32 = dp->bp_piv32;
-        ka.piv_idx = dp->bp_pividx;
-        ka.n_piv = dp->bp_npiv;
-        ka.pkeys = dp->bp_pkeys;
-        ka.bpair = dp->bp_bpair;
-        ka.nb = dp->bp_nb;
-        ka.nb_pad = dp->bp_nb_pad;
-        ka.seg_blocks = dp->bp_seg_blocks;
+        if (bp_fill_args(dp, ka, count, n_chunks)) return -1;
         ka.dirs = dp->dirs_view ? dp->dirs_view : dp->dirs;
-        ka.count = count;
-        if (dp->bp_chunk_off + n_chunks > dp->bp_chunk_cap) { hvb200_set_error("internal: chunk buffer too small"); return -1; }
-        ka.chunk_sums = dp->bp_chunk_sums + dp->bp_chunk_off;
-        dp->bp_chunk_off += (size_t)n_chunks;
-        ka.chunk_counter = dp->bp_chunk_counter;
-        CUDA_TRY(cudaMemsetAsync(dp->bp_chunk_counter, 0, sizeof(unsigned), dp->stream));
         ka.values = a.values;
-        ka.slow_counter = dp->counters + 1;
-        ka.hits = dp->bp_hits;
-        for (int k = 0; k < HVB200_MAXD; k++) {
-            ka.qscale[k] = k < d ? dp->bp_qscale[k] : 0.0;
-            ka.qlos[k] = k < d ? dp->bp_qlos[k] : 0.0;
-        }
         bp_fn fn = pick_bp<HVB200_MAXD>(d);
         fn<<<grid, kBpThreads, smem, dp->stream>>>(ka);
     } else if (dpx) {
@@ -2845,18 +2877,12 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
         }
         dpx_fn fn = pick_dpx<32>(d);
         fn<<<grid, kBlockThreads, smem, dp->stream>>>(ka);
-    } else if (d <= 32) {
+    } else {
         maxmin_fn fn = pick_kernel(d, dp->kernel_used);
         fn<<<grid, kBlockThreads, smem, dp->stream>>>(a);
-    } else {
-        k_maxmin_generic<<<grid, kBlockThreads, smem, dp->stream>>>(a, d);
     }
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
-    if (dp->pipelined) {
-        CUDA_TRY(cudaEventRecord(dp->ev_used[dp->cur_buf], dp->stream));
-        dp->used_recorded[dp->cur_buf] = true;
-    }
     plan->stats.maxmin_launches++;
     if (values_host) {
         CUDA_TRY(cudaMemcpyAsync(values_host, dp->values, count * sizeof(double), cudaMemcpyDeviceToHost, dp->stream));
@@ -3230,12 +3256,8 @@ extern "C" int hvb200cu_sets_end(struct hvb200_plan *plan, void *ctx, double *hi
 
 extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
 {
+    HVB200_NVTX("hvb200:reduce");
     DevPlan *dp = (DevPlan *)plan->dev;
-    if (dp->pipelined) {
-        // the run's own buffer is buffer 0 again; buffer 1 stays cached for the next pipelined run
-        dp->dirs = dp->dirs_buf[0];
-        dp->dirs_cap = dp->dirs_buf_cap[0];
-    }
     {
         const int b = span_begin(dp, 2);
         if (dp->kernel_used == MODE_BP) k_reduce<<<1, 1024, 0, dp->stream>>>(dp->bp_chunk_sums, (int)dp->bp_chunk_off, dp->out_hilo);
@@ -3313,6 +3335,7 @@ bool nccl_load()
 // available (caller falls back to the host copies), -1 on error, 0 on success.
 extern "C" int hvb200cu_nccl_allgather(struct hvb200_plan **plans, int n, double *pairs_out)
 {
+    HVB200_NVTX("hvb200:nccl_allgather");
     std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (n < 2 || n > 16 || !nccl_load()) return 1;
     if (g_nccl_ndev != n) {
