@@ -1183,6 +1183,7 @@ __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count
     if (capped) atomicAdd(capped_counter, (ull)capped);
 }
 #include "hvb200_bp.cuh"
+#include "hvb200_bpprep.cuh"
 
 static bool gen_hw_staged(int d) { return d >= 7 && d <= 12; }
 static int gen_hw_smem_bytes(int d) { return gen_hw_staged(d) ? 128 * (2 * d + 1) * (int)sizeof(double) : 0; }
@@ -1517,7 +1518,7 @@ struct DevPlan {
     size_t smem_bytes = 0;
     double *pts = nullptr;   size_t pts_cap = 0;       // doubles
     unsigned *keys = nullptr; size_t keys_cap = 0;     // DPX screen: packed 16-bit keys (words)
-    double *qdev = nullptr;              // 3 x 32 doubles: quantisation parameters for k_quantize
+    double *qdev = nullptr;              // 3 x HVB200_MAXD doubles: qlo, qhi, qscale of the point set (k_quantize, device preparation)
     bool resources_ready = false;        // stream / events / small buffers exist (workspace reuse)
     bool ordered = false;                // points already sorted by probe arg-max frequency
     // block-pruned kernel (hvb200_bp.cuh)
@@ -1525,6 +1526,8 @@ struct DevPlan {
                                          // 0.6 ms pageable read-back in bp_prepare)
     bool bp_ready = false, bp_begun = false, bp_probe_queued = false;
     void *share = nullptr;               // BpShare of a single-process multi-GPU call (not owned)
+    BpPrepScratch prep;                  // scratch of the device-side preparation (hvb200_bpprep.cuh)
+    bool bp_on_device = false;           // the preparation of this plan was queued on the device (own_stream, event prep.done)
     bool fused = false;                  // this run: k_maxmin_bp generates its DZ2019-HW directions itself
     double *gen_scratch = nullptr; size_t gen_scratch_cap = 0;   // [grid][2d][CH] per-CTA direction blocks (L2 resident)
     double *bp_pts = nullptr; size_t bp_pts_cap = 0;
@@ -1541,7 +1544,7 @@ struct DevPlan {
     int k_tile_pairs = 0, k_n_tiles = 0, k_stage_bytes = 0;
     size_t k_smem_bytes = 0;
     int kR = 1, kG = 2;
-    double qlo[32] = {0}, qhi[32] = {0}, qscale[32] = {0};
+    double qlo[HVB200_MAXD] = {0}, qhi[HVB200_MAXD] = {0}, qscale[HVB200_MAXD] = {0};
     double *dirs = nullptr;      size_t dirs_cap = 0;      // doubles (the workspace may serve plans of different d)
     const double *dirs_view = nullptr;   // when set, the consumers read this (cached direction sets) instead of `dirs`
     double *cta_sums = nullptr;  int cta_cap = 0;
@@ -1951,7 +1954,7 @@ static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, co
     if (!dp->resources_ready) {
         CUDA_TRY(cudaMalloc(&dp->out_hilo, 2 * sizeof(double)));
         CUDA_TRY(cudaMalloc(&dp->counters, 8 * sizeof(ull)));
-        CUDA_TRY(cudaMalloc(&dp->qdev, 3 * 32 * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&dp->qdev, 3 * HVB200_MAXD * sizeof(double)));
         CUDA_TRY(cudaStreamCreateWithFlags(&dp->own_stream, cudaStreamNonBlocking));
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, plan->device));
@@ -1975,19 +1978,19 @@ static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, co
     }
     if (padded > plan->n * (size_t)d)
         CUDA_TRY(cudaMemsetAsync(dp->pts + plan->n * (size_t)d, 0, (padded - plan->n * (size_t)d) * sizeof(double), us));
-    if (d <= 32) {
-        // ---- DPX keys: per-objective range of the point set, monotone 16-bit quantisation on the device
-        for (int k = 0; k < d; k++) { dp->qlo[k] = INFINITY; dp->qhi[k] = -INFINITY; }
+    {
+        // ---- per-objective range of the point set (key maps of the DPX screen and of the pruned kernel)
+        for (int k = 0; k < HVB200_MAXD; k++) { dp->qlo[k] = INFINITY; dp->qhi[k] = -INFINITY; dp->qscale[k] = 0.0; }
         if (pts_dev) {
-            // per-objective range by a device reduction (the set never visits the host)
-            ull init[2 * 32], res[2 * 32];
-            for (int k = 0; k < 32; k++) { init[k] = 0x7ff0000000000000ull; init[32 + k] = 0ull; }
-            ull *rng = reinterpret_cast<ull *>(dp->qdev);               // 64 of its 96 doubles, overwritten below
+            // by a device reduction (the set never visits the host)
+            ull init[2 * HVB200_MAXD], res[2 * HVB200_MAXD];
+            for (int k = 0; k < HVB200_MAXD; k++) { init[k] = 0x7ff0000000000000ull; init[HVB200_MAXD + k] = 0ull; }
+            ull *rng = reinterpret_cast<ull *>(dp->qdev);               // two thirds of it, overwritten below
             CUDA_TRY(cudaMemcpyAsync(rng, init, sizeof init, cudaMemcpyHostToDevice, us));
-            k_colrange<<<dp->sm_count * 4, 256, 0, us>>>(dp->pts, (ull)plan->n, d, rng, rng + 32);
+            k_colrange<<<dp->sm_count * 4, 256, 0, us>>>(dp->pts, (ull)plan->n, d, rng, rng + HVB200_MAXD);
             CUDA_TRY(cudaMemcpyAsync(res, rng, sizeof res, cudaMemcpyDeviceToHost, us));
             CUDA_TRY(cudaStreamSynchronize(us));
-            for (int k = 0; k < d; k++) { memcpy(&dp->qlo[k], &res[k], 8); memcpy(&dp->qhi[k], &res[32 + k], 8); }
+            for (int k = 0; k < d; k++) { memcpy(&dp->qlo[k], &res[k], 8); memcpy(&dp->qhi[k], &res[HVB200_MAXD + k], 8); }
         } else {
             for (size_t i = 0; i < plan->n; i++)
                 for (int k = 0; k < d; k++) {
@@ -2001,6 +2004,14 @@ static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, co
             dp->qscale[k] = (range > 0 && std::isfinite(range)) ? (double)kKeyScale / range : 0.0;
             if (!std::isfinite(dp->qscale[k])) dp->qscale[k] = 0.0;
         }
+        double qhost[3 * HVB200_MAXD];
+        memcpy(qhost, dp->qlo, HVB200_MAXD * sizeof(double));
+        memcpy(qhost + HVB200_MAXD, dp->qhi, HVB200_MAXD * sizeof(double));
+        memcpy(qhost + 2 * HVB200_MAXD, dp->qscale, HVB200_MAXD * sizeof(double));
+        CUDA_TRY(cudaMemcpyAsync(dp->qdev, qhost, sizeof qhost, cudaMemcpyHostToDevice, us));
+    }
+    if (d <= 32) {
+        // ---- DPX keys: monotone 16-bit quantisation on the device
         const DpxCfg dc = dpx_cfg_for(d);
         dp->kR = dc.R;
         dp->kG = dc.G;
@@ -2020,12 +2031,7 @@ static int plan_upload_impl(struct hvb200_plan *plan, const double *pts_host, co
             dp->keys_cap = words;
         }
         double *qdev = dp->qdev;
-        double qhost[96];
-        memcpy(qhost, dp->qlo, 32 * sizeof(double));
-        memcpy(qhost + 32, dp->qhi, 32 * sizeof(double));
-        memcpy(qhost + 64, dp->qscale, 32 * sizeof(double));
-        CUDA_TRY(cudaMemcpyAsync(qdev, qhost, sizeof qhost, cudaMemcpyHostToDevice, us));
-        k_quantize<<<(unsigned)((words + 255) / 256), 256, 0, us>>>(dp->pts, (ull)plan->n, d, tpairs, (ull)total_pairs, qdev, qdev + 32, qdev + 64, dp->keys);
+        k_quantize<<<(unsigned)((words + 255) / 256), 256, 0, us>>>(dp->pts, (ull)plan->n, d, tpairs, (ull)total_pairs, qdev, qdev + HVB200_MAXD, qdev + 2 * HVB200_MAXD, dp->keys);
         CUDA_TRY(cudaGetLastError());
     }
     // pts_host and qhost are caller/stack memory: the copies must have left them before returning; later
@@ -2049,6 +2055,7 @@ static void devplan_release(DevPlan *dp)
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
     cudaFree(dp->pts_tmp); cudaFree(dp->wins); cudaFree(dp->gen_scratch);
+    bp_prep_scratch_free(&dp->prep);
     cudaFree(dp->bp_hits); cudaFree(dp->bp_chunk_sums); cudaFree(dp->bp_chunk_counter); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
     for (int i = 0; i < 2; i++) {
         if (dp->staging_host[i]) cudaFreeHost(dp->staging_host[i]);
@@ -2175,6 +2182,8 @@ struct BpShare { std::once_flag once; BpHostPrep prep; };
 extern "C" void *hvb200cu_share_new(void) { return new (std::nothrow) BpShare(); }
 extern "C" void hvb200cu_share_free(void *p) { delete (BpShare *)p; }
 
+static int bp_alloc_outputs(DevPlan *dp, size_t pkeys_words, size_t bpair_words);
+static int bp_device_build(DevPlan *dp);
 // Stage 1, at the start of a run: geometry (it depends on n and d only) and the probe kernel, asynchronously.  The
 // host part (stage 2) runs when the first max-min launch is due — by then the direction generator of the first
 // batch has been queued, so the 1.6 ms of host work at cfg3 hide behind it instead of idling the GPU.
@@ -2205,14 +2214,208 @@ static int bp_prepare_begin(DevPlan *dp)
     dp->bp_seg_blocks = seg;
     dp->bp_smem = bp_smem_layout(d, bp_R_of(d), seg, (int)npiv).total;
     dp->bp_probe_queued = false;
-    if (!dp->share) {
-        // (a shared preparation probes on the device of whichever plan builds it, see bp_prepare_finish)
+    // HVB200_BP_PREP=host keeps round 1's host build (kd order by nth_element, keys on the host) as a cross-check
+    const char *where = getenv("HVB200_BP_PREP");
+    dp->bp_on_device = !(where && !strcmp(where, "host"));
+    if (!dp->bp_on_device && !dp->share) {
+        // (a shared host preparation probes on the device of whichever plan builds it, see bp_prepare_finish)
         CUDA_TRY(cudaMemsetAsync(dp->wins, 0, n * sizeof(unsigned), us));
         k_probe_argmax<<<(nprobe * 32 + 127) / 128, 128, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, dp->wins);
         CUDA_TRY(cudaGetLastError());
         dp->bp_probe_queued = true;
     }
+    if (dp->bp_on_device) {
+        if (bp_alloc_outputs(dp, (size_t)nb_pad * ((d + 1) / 2) * kBpBlock, (size_t)(nb_pad / 2) * d)) return -1;
+        for (int k = 0; k < HVB200_MAXD; k++) {
+            dp->bp_qscale[k] = k < d ? dp->qscale[k] : 0.0;
+            dp->bp_qlos[k] = k < d ? dp->qlo[k] * dp->qscale[k] * (1.0 + 0x1p-20) + 0x1p-10 : 0.0;
+        }
+        if (bp_device_build(dp)) return -1;
+    }
     dp->bp_begun = true;
+    return 0;
+}
+
+// FP32 probe pass (hvb200_bpprep.cuh): slices sized so that the grid holds a few waves of CTAs
+static int probe32_launch(DevPlan *dp, BpPrepScratch *sc, unsigned nprobe)
+{
+    const size_t n = dp->n;
+    const int d = dp->d;
+    cudaStream_t us = dp->own_stream;
+    const unsigned groups = (nprobe + kProbeThreads - 1) / kProbeThreads;
+    unsigned nslices = std::max(1u, (unsigned)(dp->sm_count * 6) / groups);
+    unsigned slice = (unsigned)((n + nslices - 1) / nslices);
+    slice = std::max((slice + kProbeTile - 1) / kProbeTile * kProbeTile, (unsigned)kProbeTile);
+    nslices = (unsigned)((n + slice - 1) / slice);
+    if (sc->cap_probe < (size_t)nslices * nprobe) {
+        cudaFree(sc->probe_partial); sc->probe_partial = nullptr; sc->cap_probe = 0;
+        CUDA_TRY(cudaMalloc(&sc->probe_partial, (size_t)nslices * nprobe * sizeof(ull)));
+        sc->cap_probe = (size_t)nslices * nprobe;
+    }
+    const dim3 grid(groups, nslices);
+    if (d <= 8) k_probe32<8><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
+    else if (d <= 16) k_probe32<16><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
+    else if (d <= 32) k_probe32<32><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
+    else k_probe32<64><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
+    k_probe32_wins<<<(nprobe + 255) / 256, 256, 0, us>>>(sc->probe_partial, nprobe, nslices, (unsigned)n, dp->wins);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// device buffers the preparation fills: points in kd order, pivots, point keys, block bounds
+static int bp_alloc_outputs(DevPlan *dp, size_t pkeys_words, size_t bpair_words)
+{
+    const int d = dp->d;
+    const size_t n_pad = (size_t)dp->bp_nb_pad * kBpBlock;
+    if (dp->bp_pts_cap < n_pad * (size_t)d) {
+        cudaFree(dp->bp_pts);
+        dp->bp_pts = nullptr; dp->bp_pts_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->bp_pts, n_pad * (size_t)d * sizeof(double)));
+        dp->bp_pts_cap = n_pad * (size_t)d;
+    }
+    if (!dp->bp_piv32) {
+        CUDA_TRY(cudaMalloc(&dp->bp_piv32, (size_t)kBpMaxPivots * HVB200_MAXD * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&dp->bp_pividx, (size_t)kBpMaxPivots * sizeof(unsigned)));
+    }
+    if (dp->bp_keys_cap < pkeys_words) {
+        cudaFree(dp->bp_pkeys);
+        dp->bp_pkeys = nullptr; dp->bp_keys_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->bp_pkeys, pkeys_words * sizeof(unsigned)));
+        dp->bp_keys_cap = pkeys_words;
+    }
+    if (dp->bp_pair_cap < bpair_words) {
+        cudaFree(dp->bp_bpair);
+        dp->bp_bpair = nullptr; dp->bp_pair_cap = 0;
+        CUDA_TRY(cudaMalloc(&dp->bp_bpair, bpair_words * sizeof(unsigned)));
+        dp->bp_pair_cap = bpair_words;
+    }
+    return 0;
+}
+
+// The whole preparation on the device (hvb200_bpprep.cuh), queued on the plan's own stream; prep.done is recorded
+// behind it.  Host work: the kd tree's shape (segment boundaries per level, from n alone) and ~8 launches per level.
+static int bp_device_build(DevPlan *dp)
+{
+    HVB200_NVTX("hvb200:pruned_prepare_device");
+    const size_t n = dp->n;
+    const int d = dp->d;
+    cudaStream_t us = dp->own_stream;
+    BpPrepScratch *sc = &dp->prep;
+    // ---- tree shape: a node of cnt > 32 points splits into [lo, lo + half) and [lo + half, hi), half = whole blocks
+    std::vector<unsigned> all;                      // the levels' start arrays, one after the other (each ends with n)
+    std::vector<size_t> level_off;
+    std::vector<unsigned> level_nseg;
+    size_t local_off = 0;
+    unsigned local_nseg = 0;
+    {
+        std::vector<unsigned> cur = {0u, (unsigned)n}, next;
+        for (;;) {
+            bool any = false;
+            next.clear();
+            for (size_t s2 = 0; s2 + 1 < cur.size(); s2++) {
+                const unsigned lo = cur[s2], cnt = cur[s2 + 1] - lo;
+                next.push_back(lo);
+                if (cnt > (unsigned)kBpBlock) {
+                    unsigned half = (cnt / 2 + kBpBlock - 1) / kBpBlock * kBpBlock;
+                    if (half >= cnt) half = cnt / 2;
+                    next.push_back(lo + half);
+                    any = true;
+                }
+            }
+            next.push_back((unsigned)n);
+            unsigned biggest = 0;
+            for (size_t s2 = 0; s2 + 1 < cur.size(); s2++) biggest = std::max(biggest, cur[s2 + 1] - cur[s2]);
+            if (!any || biggest <= (unsigned)kKdLocalMax) {
+                // the rest of the tree is finished inside shared memory, one CTA per segment of this level
+                local_off = all.size();
+                local_nseg = any ? (unsigned)cur.size() - 1 : 0;
+                all.insert(all.end(), cur.begin(), cur.end());
+                break;
+            }
+            level_off.push_back(all.size());
+            level_nseg.push_back((unsigned)cur.size() - 1);
+            all.insert(all.end(), cur.begin(), cur.end());
+            cur.swap(next);
+        }
+    }
+    unsigned max_seg = 1;
+    for (unsigned v : level_nseg) max_seg = std::max(max_seg, v);
+    // ---- scratch
+    if (sc->cap_n < n) {
+        for (int i = 0; i < 2; i++) { cudaFree(sc->idx[i]); cudaFree(sc->keys[i]); cudaFree(sc->pkeys64[i]); sc->idx[i] = sc->keys[i] = nullptr; sc->pkeys64[i] = nullptr; }
+        cudaFree(sc->pos); sc->pos = nullptr; sc->cap_n = 0;
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaMalloc(&sc->idx[i], n * sizeof(unsigned)));
+            CUDA_TRY(cudaMalloc(&sc->keys[i], n * sizeof(unsigned)));
+            CUDA_TRY(cudaMalloc(&sc->pkeys64[i], n * sizeof(ull)));
+        }
+        CUDA_TRY(cudaMalloc(&sc->pos, n * sizeof(unsigned)));
+        sc->cap_n = n;
+    }
+    if (sc->cap_starts < all.size() + 2) {
+        cudaFree(sc->starts); sc->starts = nullptr; sc->cap_starts = 0;
+        CUDA_TRY(cudaMalloc(&sc->starts, (all.size() + 2 + 256) * sizeof(unsigned)));
+        sc->cap_starts = all.size() + 2 + 256;
+    }
+    if (sc->cap_minmax < (size_t)max_seg * d * 2) {
+        cudaFree(sc->minmax); sc->minmax = nullptr; sc->cap_minmax = 0;
+        CUDA_TRY(cudaMalloc(&sc->minmax, (size_t)max_seg * d * 2 * sizeof(ull)));
+        sc->cap_minmax = (size_t)max_seg * d * 2;
+    }
+    size_t b1 = 0, b2 = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, b1, (const unsigned *)nullptr, (unsigned *)nullptr, (const unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 32, us));
+    CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, b2, (const ull *)nullptr, (ull *)nullptr, (int)n, 0, 64, us));
+    const size_t need_tmp = std::max(b1, b2);
+    if (sc->cub_bytes < need_tmp) {
+        cudaFree(sc->cub_tmp); sc->cub_tmp = nullptr; sc->cub_bytes = 0;
+        CUDA_TRY(cudaMalloc(&sc->cub_tmp, need_tmp));
+        sc->cub_bytes = need_tmp;
+    }
+    if (!sc->done) CUDA_TRY(cudaEventCreateWithFlags(&sc->done, cudaEventDisableTiming));
+    // the level table goes up first: a copy from pageable memory waits for the work already queued on its stream
+    if (!all.empty()) CUDA_TRY(cudaMemcpyAsync(sc->starts, all.data(), all.size() * sizeof(unsigned), cudaMemcpyHostToDevice, us));
+    const double *qlo = dp->qdev, *qhi = dp->qdev + HVB200_MAXD, *qscale = dp->qdev + 2 * HVB200_MAXD;
+    const unsigned gn = (unsigned)((n + 255) / 256);
+    unsigned nprobe = 4096;
+    while (nprobe > 256 && (double)nprobe * (double)n > 6e8) nprobe /= 2;
+    // ---- probe directions: how often is each point the arg-max (the pivots are the most frequent winners)
+    CUDA_TRY(cudaMemsetAsync(dp->wins, 0, n * sizeof(unsigned), us));
+    if (probe32_launch(dp, sc, nprobe)) return -1;
+    dp->bp_probe_queued = true;
+    // ---- kd order
+    k_iota_u32<<<gn, 256, 0, us>>>(sc->idx[0], (unsigned)n);
+    int cur = 0;
+    for (size_t L = 0; L < level_nseg.size(); L++) {
+        const unsigned nseg = level_nseg[L];
+        const unsigned *starts = sc->starts + level_off[L];
+        int nbits = 0;
+        while ((1u << nbits) < nseg) nbits++;
+        const int vb = std::min(kKdValueBits, 32 - nbits);
+        const ull cells = (ull)nseg * d * 2;
+        k_fill_u64<<<(unsigned)((cells + 255) / 256), 256, 0, us>>>(sc->minmax, cells, ~0ull, 0ull);
+        k_kd_minmax<<<gn, 256, 0, us>>>(dp->pts, sc->idx[cur], (unsigned)n, d, starts, nseg, sc->minmax);
+        k_kd_keys<<<gn, 256, 0, us>>>(dp->pts, sc->idx[cur], (unsigned)n, d, starts, nseg, sc->minmax, qhi, vb, sc->keys[0]);
+        size_t tmp = sc->cub_bytes;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(sc->cub_tmp, tmp, (const unsigned *)sc->keys[0], sc->keys[1], (const unsigned *)sc->idx[cur], sc->idx[cur ^ 1],
+                                                 (int)n, 0, vb + nbits, us));
+        cur ^= 1;
+    }
+    if (local_nseg) k_kd_local<<<local_nseg, 256, 0, us>>>(dp->pts, sc->idx[cur], d, sc->starts + local_off, qhi);
+    // ---- points, keys, bounds in kd order
+    const ull n_pad = (ull)dp->bp_nb_pad * kBpBlock;
+    const int W = (d + 1) / 2;
+    k_bp_gather<<<(unsigned)((n_pad * d + 255) / 256), 256, 0, us>>>(dp->pts, sc->idx[cur], (ull)n, n_pad, d, dp->bp_pts, sc->pos);
+    k_bp_keys<<<(unsigned)(((ull)dp->bp_nb_pad * W * kBpBlock + 255) / 256), 256, 0, us>>>(dp->bp_pts, (ull)n, dp->bp_nb_pad, d, qlo, qscale, dp->bp_pkeys);
+    k_bp_bounds<<<(unsigned)(((ull)(dp->bp_nb_pad / 2) * d + 255) / 256), 256, 0, us>>>(dp->bp_pts, (ull)n, dp->bp_nb, dp->bp_nb_pad, d, qlo, qscale, dp->bp_bpair);
+    // ---- pivots
+    k_bp_pivot_keys<<<gn, 256, 0, us>>>(dp->wins, (unsigned)n, nprobe, sc->pkeys64[0]);
+    {
+        size_t tmp = sc->cub_bytes;
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(sc->cub_tmp, tmp, (const ull *)sc->pkeys64[0], sc->pkeys64[1], (int)n, 0, 46, us));
+    }
+    k_bp_pivots<<<(unsigned)((dp->bp_npiv * d + 255) / 256), 256, 0, us>>>(dp->pts, sc->pkeys64[1], sc->pos, dp->bp_npiv, d, dp->bp_piv32, dp->bp_pividx);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(sc->done, us));
     return 0;
 }
 
@@ -2335,8 +2538,13 @@ static int bp_host_build(DevPlan *dp, BpHostPrep &H)
 static int bp_prepare_finish(DevPlan *dp)
 {
     HVB200_NVTX("hvb200:pruned_prepare");
-    const int d = dp->d;
     cudaStream_t us = dp->own_stream;
+    if (dp->bp_on_device) {
+        // everything was queued by bp_prepare_begin: the run's stream waits for it on the device, the host does not
+        if (dp->stream != us) CUDA_TRY(cudaStreamWaitEvent(dp->stream, dp->prep.done, 0));
+        dp->bp_ready = true;
+        return 0;
+    }
     BpHostPrep own;
     BpHostPrep *H = &own;
     if (dp->share) {
@@ -2346,29 +2554,7 @@ static int bp_prepare_finish(DevPlan *dp)
         if (H->rc) return -1;
         CUDA_TRY(cudaSetDevice(dp->device));
     } else if (bp_host_build(dp, own)) return -1;
-    const size_t n_pad = (size_t)dp->bp_nb_pad * kBpBlock;
-    if (dp->bp_pts_cap < n_pad * (size_t)d) {
-        cudaFree(dp->bp_pts);
-        dp->bp_pts = nullptr; dp->bp_pts_cap = 0;
-        CUDA_TRY(cudaMalloc(&dp->bp_pts, n_pad * (size_t)d * sizeof(double)));
-        dp->bp_pts_cap = n_pad * (size_t)d;
-    }
-    if (!dp->bp_piv32) {
-        CUDA_TRY(cudaMalloc(&dp->bp_piv32, (size_t)kBpMaxPivots * HVB200_MAXD * sizeof(float)));
-        CUDA_TRY(cudaMalloc(&dp->bp_pividx, (size_t)kBpMaxPivots * sizeof(unsigned)));
-    }
-    if (dp->bp_keys_cap < H->pkeys.size()) {
-        cudaFree(dp->bp_pkeys);
-        dp->bp_pkeys = nullptr; dp->bp_keys_cap = 0;
-        CUDA_TRY(cudaMalloc(&dp->bp_pkeys, H->pkeys.size() * sizeof(unsigned)));
-        dp->bp_keys_cap = H->pkeys.size();
-    }
-    if (dp->bp_pair_cap < H->bpair.size()) {
-        cudaFree(dp->bp_bpair);
-        dp->bp_bpair = nullptr; dp->bp_pair_cap = 0;
-        CUDA_TRY(cudaMalloc(&dp->bp_bpair, H->bpair.size() * sizeof(unsigned)));
-        dp->bp_pair_cap = H->bpair.size();
-    }
+    if (bp_alloc_outputs(dp, H->pkeys.size(), H->bpair.size())) return -1;
     for (int k = 0; k < HVB200_MAXD; k++) { dp->bp_qscale[k] = H->qscale[k]; dp->bp_qlos[k] = H->qlos[k]; }
     CUDA_TRY(cudaMemcpyAsync(dp->bp_pts, H->sorted.data(), H->sorted.size() * sizeof(double), cudaMemcpyHostToDevice, us));
     CUDA_TRY(cudaMemcpyAsync(dp->bp_piv32, H->piv32.data(), H->piv32.size() * sizeof(float), cudaMemcpyHostToDevice, us));
@@ -2420,7 +2606,7 @@ static int order_points(DevPlan *dp)
         const size_t total_pairs = (size_t)dp->k_n_tiles * dp->k_tile_pairs;
         const ull words = (ull)total_pairs * d;
         k_quantize<<<(unsigned)((words + 255) / 256), 256, 0, us>>>(dp->pts, (ull)n, d, dp->k_tile_pairs, (ull)total_pairs,
-                                                                   dp->qdev, dp->qdev + 32, dp->qdev + 64, dp->keys);
+                                                                   dp->qdev, dp->qdev + HVB200_MAXD, dp->qdev + 2 * HVB200_MAXD, dp->keys);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaStreamSynchronize(us));           // `order` is host memory; later runs may use another stream
