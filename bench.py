@@ -161,7 +161,10 @@ def workload_name(cfg):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up on; stop(t0, t1) keeps the
+    samples whose timestamps fall inside the timed region [t0, t1] (host clock) — a region shorter than the sampler's
+    start-up would otherwise see none — and falls back to every sample taken under load (warm-up + timed)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -172,12 +175,13 @@ class ClockSampler:
     def start(self):
         try:
             self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -188,20 +192,34 @@ class ClockSampler:
             pass
         try:
             self.tmp.flush()
-            rows = [r.strip().split(",") for r in open(self.tmp.name) if r.strip()]
-            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            rows = [[c.strip() for c in r.strip().split(",")] for r in open(self.tmp.name) if r.strip()]
+            rows = [r for r in rows if len(r) >= 10]
+            window = "warmup+timed"
+            if t0 is not None and t1 is not None:
+                inside = []
+                for r in rows:
+                    try:
+                        ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except ValueError:
+                        continue
+                    if t0 <= ts <= t1:
+                        inside.append(r)
+                if inside:
+                    rows, window = inside, "timed"
+            sm = [float(r[2]) for r in rows]
             if sm:
                 out["sm_mhz"] = float(np.median(sm))
-                out["sm_max_mhz"] = float(rows[0][2])
-                out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
+                out["sm_max_mhz"] = float(rows[0][3])
+                out["power_w_max"] = max(float(r[4]) for r in rows)
                 names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
                 seen = set()
                 for r in rows:
-                    for nm, v in zip(names, r[5:9]):
-                        if v.strip().lower().startswith("active"):
+                    for nm, v in zip(names, r[6:10]):
+                        if v.lower().startswith("active"):
                             seen.add(nm)
                 out["reasons"] = sorted(seen)
                 out["samples"] = len(sm)
+                out["window"] = window
             os.unlink(self.tmp.name)
         except Exception:
             pass
@@ -223,6 +241,7 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keeps NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     c = hvcases.CONFIGS[args.config]
     method, d, N, seed = c["method"], c["d"], c["nsamples"], c["seed"]
@@ -249,14 +268,15 @@ def run_ours(args, rank, local_rank, world):
         result["estimate"] = mb.hv_approx_finalize(d, N, flat)
         return plan.stats()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
+    region_t0 = time.time()
     maxmin_ms = dirgen_ms = 0.0
     launches = 0
     mm_launches = 0
@@ -270,7 +290,7 @@ def run_ours(args, rank, local_rank, world):
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop(region_t0, time.time())
     dev_s = ev0.elapsed_time(ev1) / 1e3
     tt = torch.tensor([dev_s, wall, maxmin_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -302,6 +322,35 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_s = t2.item()
     e2e_value = units_per_step * e2e_steps / e2e_s / 1e9
+
+    # ---------------- single-process leg: ONE call of the reference's own C symbol, all N GPUs from one process ----------------
+    # What a Python/R caller of the drop-in gets: hv_approx_hua_wang / hv_approx_normal (c/hvapprox.h:16-28) with
+    # HVB200_NGPUS=N — host threads per GPU and one ncclAllGather inside the library, no torchrun.  Rank 0 makes the
+    # calls, the other ranks wait at the barrier with their GPUs idle.  Host wall clock around the call.
+    single = None
+    if d <= 31:
+        barrier()
+        if rank == 0:
+            os.environ["HVB200_NGPUS"] = str(world)
+            try:
+                mb.hv_approx(x, ref=ref, maximise=maxi, nsamples=N, seed=seed, method=method)     # contexts, communicator
+                times = []
+                for _ in range(e2e_steps):
+                    t_a = time.perf_counter()
+                    est_single = mb.hv_approx(x, ref=ref, maximise=maxi, nsamples=N, seed=seed, method=method)
+                    times.append(time.perf_counter() - t_a)
+                from moocore_b200 import _api
+                exch = _api._load().hvb200_multi_last_exchange()
+                t_med = float(np.median(times))
+                single = {"value": units_per_step / t_med / 1e9, "unit": UNIT, "ngpus": world, "ms_per_call": 1e3 * t_med,
+                          "estimate": est_single, "rel_diff_vs_ranks": abs(est_single - estimate) / abs(estimate),
+                          "exchange": {0: "none", 1: "nccl", 2: "host"}.get(exch, "?"),
+                          "how": f"{e2e_steps} calls of the drop-in entry point with HVB200_NGPUS={world} from rank 0's process, host buffers in, double out"}
+            except Exception as e:  # pragma: no cover
+                single = {"value": None, "error": str(e)}
+            finally:
+                os.environ.pop("HVB200_NGPUS", None)
+        barrier()
 
     # ---------------- roofline + cpu baseline (rank 0) ----------------
     if rank == 0:
@@ -366,13 +415,14 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config), "kernel": {1: "exact", 2: "screen", 3: "dpx", 4: "pruned"}.get(plan.stats()["kernel"], "?"),
-                       "npoints_after_filter": npts, "parallelism": (f"block-cyclic direction blocks (2^21) x{world}" if cyclic else f"direction-range x{world}"),
+                       "npoints_after_filter": npts, "parallelism": (f"block-cyclic direction blocks of {shard_block(N, world)} x{world}" if cyclic else f"direction-range x{world}"),
                        "l2": "point set (0.8 MB) is L2/shared-memory resident by design; the per-batch direction "
                              "buffer (2 GiB) exceeds L2, no flush needed",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "estimate": estimate, "estimate_e2e": est_e2e, "rel_error_vs_reference": reference_rel_error(args.config, estimate),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes + ref.nbytes + maxi.nbytes),
                     "d2h_bytes_per_step": 32, "steps": e2e_steps},
+            "e2e_single_process": single,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

@@ -92,7 +92,7 @@ MOOCORE_API int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsa
  * the samples [b*block, min((b+1)*block, nsamples)): the block-cyclic shard of rank `first` among `stride`
  * ranks.  DZ2019-HW only (the lattice is index-addressable; its per-direction cost drifts along the index,
  * so interleaved blocks balance the ranks where contiguous ranges do not). */
-#define HVB200_SHARD_BLOCK ((uint64_t)1 << 21)
+#define HVB200_SHARD_BLOCK ((uint64_t)1 << 14)
 /* the block size the library itself uses for `world` ranks: HVB200_SHARD_BLOCK, halved (down to 2^10) until every
  * rank gets at least 4 blocks */
 MOOCORE_API uint64_t hvb200_shard_block(uint_fast32_t nsamples, int world);

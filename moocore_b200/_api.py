@@ -446,7 +446,7 @@ class Plan:
             raise RuntimeError(f"hvb200_plan_run failed ({rc}): {_last_error()}")
         return (out[0], out[1])
 
-    def run_blocks(self, method: str, nsamples: int, first: int, stride: int, block: int = 1 << 21, seed: int = 0,
+    def run_blocks(self, method: str, nsamples: int, first: int, stride: int, block: int = 1 << 14, seed: int = 0,
                    stream: int | None = None):
         """Partial sum over the block-cyclic shard `first` of `stride` (blocks of `block` directions; DZ2019-HW)."""
         if self._h is None:

@@ -596,7 +596,10 @@ int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint3
    directions.  The cost of a direction varies smoothly along a Hua-Wang lattice (its first angle grows with the
    index), so contiguous shards are unbalanced (8 GPUs: 85 % efficiency) while interleaved blocks are not.
    Only the lattice is index-addressable: the MC and Rphi streams are sequential and stay on contiguous ranges. */
-/* block size of the block-cyclic shards: 2^21 directions, halved (down to 2^10) until every rank gets >= 4 blocks */
+/* block size of the block-cyclic shards: 2^14 directions, halved (down to 2^10) until every rank gets >= 4 blocks.
+   The per-direction cost drifts along the lattice; with b blocks per rank the ranks' loads differ by ~1/b of that
+   drift (2^21-direction blocks, 6 per rank at cfg3 on 8 GPUs, left the last rank 4 % behind the first) and the
+   kernels map shard positions to lattice indices arithmetically, so small blocks cost nothing. */
 uint64_t hvb200_shard_block(uint_fast32_t nsamples, int world)
 {
     uint64_t block = HVB200_SHARD_BLOCK;
@@ -633,8 +636,19 @@ int hvb200_plan_run_blocks(hvb200_plan *plan, int method, uint_fast32_t nsamples
         plan->stats.samples = total;
         return 0;
     }
-    /* the blocks of this shard are generated side by side into the direction buffer and evaluated by ONE
-       max-min launch per full buffer: small launches lose ~15 % to start-up and tail */
+    if ((block & (block - 1)) == 0) {
+        /* power-of-two blocks: the generator maps shard positions to lattice indices itself, one launch per buffer */
+        for (uint64_t p0 = 0; p0 < total; p0 += batch) {
+            const uint64_t cnt = (total - p0 < batch) ? total - p0 : batch;
+            if (hvb200cu_gen_hw_mapped(plan, &hw, first * block, __builtin_ctzll(block), stride, p0, cnt, 0)) return -1;
+            if (plan->n && hvb200cu_maxmin(plan, cnt, NULL)) return -1;
+        }
+        if (hvb200cu_run_end(plan, out_hilo)) return -1;
+        plan->stats.samples = total;
+        return 0;
+    }
+    /* other block sizes: the blocks of this shard are generated side by side into the direction buffer and evaluated
+       by ONE max-min launch per full buffer: small launches lose ~15 % to start-up and tail */
     uint64_t filled = 0;
     for (uint64_t lo = first * block; lo < nsamples; lo += stride * block) {
         const uint64_t hi = (nsamples - lo < block) ? nsamples : lo + block;

@@ -10,12 +10,12 @@
 //                uploads the segment boundaries of every level and the device only decides the CONTENT: per level
 //                  k_kd_minmax   per (segment, objective) min / max of the raw coordinates (ordered bit patterns, atomics)
 //                  k_kd_keys     key = segment << vb | fixed-point position of the point inside the segment's range of
-//                                its widest objective (vb = 20 bits); leaves keep their order
+//                                its widest objective (vb = 16 - segment bits, at least 12); leaves keep their order
 //                  cub radix sort of (key, index): inside every segment the points end up ordered by that objective,
 //                                so its left part is the lower "half" — a median split without a selection pass
 //                Once every segment holds at most 1024 points, k_kd_local finishes the tree in ONE launch (a CTA per
 //                segment, bitonic sorts in shared memory).
-//                The order may differ from the host build's where coordinates agree to 2^-20 of the range or two
+//                The order may differ from the host build's where coordinates agree to 2^-vb of the segment's range or two
 //                objectives are equally wide; any order gives the same sample values (max over points is exact and
 //                order-free) — the order only decides how tight the block boxes are.
 //   k_bp_gather  points -> kd order (zero padding rows), inverse permutation
@@ -26,7 +26,8 @@
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 
-static constexpr int kKdValueBits = 20;
+static constexpr int kKdKeyBits = 16;       // segment id + fixed-point position: two 8-bit radix passes per level
+static constexpr int kKdValueBitsMin = 12;
 
 __global__ void __launch_bounds__(256) k_iota_u32(unsigned *__restrict__ a, unsigned n)
 {
@@ -112,20 +113,23 @@ __global__ void __launch_bounds__(256) k_kd_keys(const double *__restrict__ pts,
 // one CTA-wide bitonic sort of {sub-segment | key} orders every sub-segment at once; same split rule as the global
 // levels (left part = whole 32-point blocks).  Replaces 5 global levels (~8 launches each) at n = 1e4.
 // ------------------------------------------------------------------------------------------------
-static constexpr int kKdLocalMax = 1024;
-__global__ void __launch_bounds__(256) k_kd_local(const double *__restrict__ pts, unsigned *__restrict__ idx, int d,
-                                                  const unsigned *__restrict__ starts, const double *__restrict__ qhi)
+static constexpr int kKdLocalMax = 1024, kKdLocalThreads = 1024;
+__global__ void __launch_bounds__(kKdLocalThreads) k_kd_local(const double *__restrict__ pts, unsigned *__restrict__ idx, int d,
+                                                              const unsigned *__restrict__ starts, const double *__restrict__ qhi)
 {
+    constexpr int NW = kKdLocalThreads / 32, MAXSUB = kKdLocalMax / kBpBlock;      // 32 warps, at most 32 sub-segments
     __shared__ ull skey[kKdLocalMax];
     __shared__ unsigned sidx[kKdLocalMax];
-    __shared__ unsigned sb[2][kKdLocalMax / kBpBlock + 2];
+    __shared__ unsigned sb[2][MAXSUB + 2];
     __shared__ unsigned nsub[2];
+    __shared__ double swid[MAXSUB * HVB200_MAXD];       // normalised width of (sub-segment, objective)
+    __shared__ double smin[MAXSUB * HVB200_MAXD];       // its normalised minimum
     const unsigned lo = starts[blockIdx.x], cnt = starts[blockIdx.x + 1] - lo;
     if (cnt <= (unsigned)kBpBlock) return;
     unsigned P = 64;
     while (P < cnt) P <<= 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (unsigned p = tid; p < cnt; p += 256) sidx[p] = idx[lo + p];
+    for (unsigned p = tid; p < cnt; p += kKdLocalThreads) sidx[p] = idx[lo + p];
     if (tid == 0) { sb[0][0] = 0; sb[0][1] = cnt; nsub[0] = 1; }
     int cur = 0;
     for (;;) {
@@ -134,32 +138,43 @@ __global__ void __launch_bounds__(256) k_kd_local(const double *__restrict__ pts
         bool any = false;
         for (unsigned s2 = 0; s2 < ns; s2++) any |= sb[cur][s2 + 1] - sb[cur][s2] > (unsigned)kBpBlock;
         if (!any) break;
-        // ---- keys: warp = sub-segment
-        for (unsigned s2 = warp; s2 < ns; s2 += 8) {
+        // ---- (sub-segment, objective) ranges: one warp per pair
+        for (unsigned t = warp; t < ns * (unsigned)d; t += NW) {
+            const unsigned s2 = t / d;
+            const int k = (int)(t - s2 * d);
+            const unsigned b0 = sb[cur][s2], b1 = sb[cur][s2 + 1];
+            if (b1 - b0 <= (unsigned)kBpBlock) continue;
+            ull mn = ~0ull, mx = 0ull;
+            for (unsigned p = b0 + lane; p < b1; p += 32) {
+                const ull v = (ull)__double_as_longlong(__ldg(pts + (size_t)sidx[p] * d + k));
+                mn = v < mn ? v : mn;
+                mx = v > mx ? v : mx;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const ull ol = __shfl_xor_sync(0xffffffffu, mn, off), oh = __shfl_xor_sync(0xffffffffu, mx, off);
+                mn = ol < mn ? ol : mn;
+                mx = oh > mx ? oh : mx;
+            }
+            if (lane == 0) {
+                const double q = __ldg(qhi + k);
+                const double a = q > 0 ? __longlong_as_double((long long)mn) / q : 0.0, b = q > 0 ? __longlong_as_double((long long)mx) / q : 0.0;
+                swid[t] = b - a;
+                smin[t] = a;
+            }
+        }
+        __syncthreads();
+        // ---- keys: one warp per sub-segment (the first widest objective, like the host build)
+        for (unsigned s2 = warp; s2 < ns; s2 += NW) {
             const unsigned b0 = sb[cur][s2], b1 = sb[cur][s2 + 1];
             if (b1 - b0 <= (unsigned)kBpBlock) {
                 for (unsigned p = b0 + lane; p < b1; p += 32) skey[p] = ((ull)s2 << 32) | (ull)(p - b0);      // a leaf keeps its order
                 continue;
             }
             int bk = 0;
-            double bw = -1.0, bmn = 0.0, bq = 1.0;
-            for (int k = 0; k < d; k++) {
-                ull mn = ~0ull, mx = 0ull;
-                for (unsigned p = b0 + lane; p < b1; p += 32) {
-                    const ull v = (ull)__double_as_longlong(__ldg(pts + (size_t)sidx[p] * d + k));
-                    mn = v < mn ? v : mn;
-                    mx = v > mx ? v : mx;
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const ull ol = __shfl_xor_sync(0xffffffffu, mn, off), oh = __shfl_xor_sync(0xffffffffu, mx, off);
-                    mn = ol < mn ? ol : mn;
-                    mx = oh > mx ? oh : mx;
-                }
-                const double q = __ldg(qhi + k);
-                const double a = q > 0 ? __longlong_as_double((long long)mn) / q : 0.0, b = q > 0 ? __longlong_as_double((long long)mx) / q : 0.0;
-                if (b - a > bw) { bw = b - a; bk = k; bmn = a; bq = q; }
-            }
+            double bw = -1.0;
+            for (int k = 0; k < d; k++) { const double w = swid[s2 * d + k]; if (w > bw) { bw = w; bk = k; } }
+            const double bmn = smin[s2 * d + bk], bq = __ldg(qhi + bk);
             for (unsigned p = b0 + lane; p < b1; p += 32) {
                 const double v = bq > 0 ? __ldg(pts + (size_t)sidx[p] * d + bk) / bq : 0.0;
                 const double t = (bw > 0 ? (v - bmn) / bw : 0.0) * 4294967296.0;
@@ -167,19 +182,17 @@ __global__ void __launch_bounds__(256) k_kd_local(const double *__restrict__ pts
                 skey[p] = ((ull)s2 << 32) | fixed;
             }
         }
-        for (unsigned p = cnt + tid; p < P; p += 256) { skey[p] = ~0ull; sidx[p] = 0xffffffffu; }
+        for (unsigned p = cnt + tid; p < P; p += kKdLocalThreads) { skey[p] = ~0ull; sidx[p] = 0xffffffffu; }
         __syncthreads();
-        // ---- bitonic sort of (skey, sidx) over P slots
+        // ---- bitonic sort of (skey, sidx) over P slots: thread t owns the t-th compare-exchange of a step
         for (unsigned k2 = 2; k2 <= P; k2 <<= 1)
             for (unsigned j = k2 >> 1; j > 0; j >>= 1) {
-                for (unsigned i = tid; i < P; i += 256) {
-                    const unsigned x = i ^ j;
-                    if (x > i) {
-                        const ull a = skey[i], b = skey[x];
-                        if (((i & k2) == 0) ? (a > b) : (a < b)) {
-                            skey[i] = b; skey[x] = a;
-                            const unsigned t = sidx[i]; sidx[i] = sidx[x]; sidx[x] = t;
-                        }
+                if ((unsigned)tid < P / 2) {
+                    const unsigned i = 2 * j * ((unsigned)tid / j) + ((unsigned)tid % j), x = i + j;      // i has bit j clear
+                    const ull a = skey[i], b = skey[x];
+                    if (((i & k2) == 0) ? (a > b) : (a < b)) {
+                        skey[i] = b; skey[x] = a;
+                        const unsigned t = sidx[i]; sidx[i] = sidx[x]; sidx[x] = t;
                     }
                 }
                 __syncthreads();
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(256) k_kd_local(const double *__restrict__ pts
         }
         cur ^= 1;
     }
-    for (unsigned p = tid; p < cnt; p += 256) idx[lo + p] = sidx[p];
+    for (unsigned p = tid; p < cnt; p += kKdLocalThreads) idx[lo + p] = sidx[p];
 }
 __global__ void __launch_bounds__(256) k_bp_gather(const double *__restrict__ pts, const unsigned *__restrict__ idx, ull n, ull n_pad, int d,
                                                    double *__restrict__ sorted, unsigned *__restrict__ pos)
@@ -241,35 +254,40 @@ __global__ void __launch_bounds__(256) k_bp_keys(const double *__restrict__ sort
     const ull i = b * kBpBlock + l;
     pkeys[w] = bp_point_key(sorted, i, n, 2 * j, d, qlo, qscale) | (bp_point_key(sorted, i, n, 2 * j + 1, d, qlo, qscale) << 16);
 }
-__global__ void __launch_bounds__(256) k_bp_bounds(const double *__restrict__ sorted, ull n, int nb, int nb_pad, int d,
-                                                   const double *__restrict__ qlo, const double *__restrict__ qscale, unsigned *__restrict__ bpair)
+// block maxima from the point keys: one warp per (block pair, key word) — lane = point, one max-reduction per half-word
+// and block (signed 16-bit: the padding key -1 never raises a maximum)
+__global__ void __launch_bounds__(256) k_bp_bounds(const unsigned *__restrict__ pkeys, int nb_pad, int d, unsigned *__restrict__ bpair)
 {
-    const ull w = (ull)blockIdx.x * blockDim.x + threadIdx.x;          // pr * d + k
-    if (w >= (ull)(nb_pad / 2) * d) return;
-    const int k = (int)(w % d);
-    const ull pr = w / d;
-    unsigned word = 0;
+    const int W = (d + 1) / 2;
+    const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= (unsigned)(nb_pad / 2) * W) return;
+    const unsigned pr = wid / W, j = wid - pr * W;
+    int m[2][2];
+#pragma unroll
     for (int h = 0; h < 2; h++) {
-        const ull b = 2 * pr + h;
-        int m = -1;                                                     // signed: padding never raises it
-        if (b < (ull)nb)
-            for (int l = 0; l < kBpBlock; l++) m = max(m, (int)(short)bp_point_key(sorted, b * kBpBlock + l, n, k, d, qlo, qscale));
-        word |= ((unsigned)m & 0xffffu) << (16 * h);
+        const unsigned w = __ldg(pkeys + ((size_t)(2 * pr + h) * W + j) * kBpBlock + lane);
+        m[h][0] = __reduce_max_sync(0xffffffffu, (int)(short)(w & 0xffffu));
+        m[h][1] = __reduce_max_sync(0xffffffffu, (int)(short)(w >> 16));
     }
-    bpair[w] = word;
+    if (lane < 2 && 2 * (int)j + (int)lane < d)
+        bpair[(size_t)pr * d + 2 * j + lane] = ((unsigned)m[0][lane] & 0xffffu) | (((unsigned)m[1][lane] & 0xffffu) << 16);
 }
-__global__ void __launch_bounds__(256) k_bp_pivot_keys(const unsigned *__restrict__ wins, unsigned n, unsigned nprobe, ull *__restrict__ keys)
+// pivot ranking keys: (nprobe - wins) in the high bits, the point index in the low IB bits (32-bit keys when the index
+// fits 19 bits: 4 radix passes instead of 6)
+template <typename K, int IB>
+__global__ void __launch_bounds__(256) k_bp_pivot_keys(const unsigned *__restrict__ wins, unsigned n, unsigned nprobe, K *__restrict__ keys)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = ((ull)(nprobe - min(wins[i], nprobe)) << 32) | i;
+    if (i < n) keys[i] = ((K)(nprobe - min(wins[i], nprobe)) << IB) | (K)i;
 }
-__global__ void __launch_bounds__(256) k_bp_pivots(const double *__restrict__ pts, const ull *__restrict__ keys, const unsigned *__restrict__ pos,
+template <typename K, int IB>
+__global__ void __launch_bounds__(256) k_bp_pivots(const double *__restrict__ pts, const K *__restrict__ keys, const unsigned *__restrict__ pos,
                                                    int npiv, int d, float *__restrict__ piv32, unsigned *__restrict__ pividx)
 {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= npiv * d) return;
     const int j = w / d, k = w - j * d;
-    const unsigned o = (unsigned)(keys[j] & 0xffffffffull);
+    const unsigned o = (unsigned)(keys[j] & (((K)1 << IB) - 1));
     piv32[w] = (float)pts[(size_t)o * d + k];
     if (k == 0) pividx[j] = pos[o];
 }

@@ -55,6 +55,9 @@ int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64_t max_batc
 /* direction producers: fill the plan's direction buffer with `count` samples */
 int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count);
 int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count, uint64_t offset);
+/* positions [p0, p0 + count) of a shard: position p is lattice index first + ((p >> shift) * stride << shift) + (p & (2^shift - 1)) */
+int hvb200cu_gen_hw_mapped(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t first, int shift, uint64_t stride,
+                           uint64_t p0, uint64_t count, uint64_t offset);
 int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count);     /* count*d normals */
 /* DZ2019-MC stream generated on the device: begin(seed), skip n normals, then per batch */
 int hvb200cu_mc_begin(struct hvb200_plan *plan, uint32_t seed);

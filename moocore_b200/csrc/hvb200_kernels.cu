@@ -1153,8 +1153,10 @@ __device__ __forceinline__ void hw_direction(const HwDev &P, ull i, const double
 // (row stride 2d + 1 doubles: conflict-free) and the warp copies its block out with coalesced stores.
 // Measured (2e7 directions): staged 3.38 vs 3.6-3.8 ms at d = 10, but slower for d <= 6 (the copy loop outweighs
 // six stores) and for d >= 16 (the staging buffer costs occupancy), so STAGED is used for 7 <= d <= 12 only.
+// Row j of the launch is position p0 + j of a shard, i.e. lattice index first + ((p >> shift) * stride << shift) +
+// (p & (2^shift - 1)): a contiguous range (shift = 62) or the block-cyclic shard of one rank.
 template <bool STAGED>
-__global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count, double *__restrict__ dirs,
+__global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull first, int shift, ull stride, ull p0, ull count, double *__restrict__ dirs,
                                                 ull *capped_counter, const double *__restrict__ tab, int ntab)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1165,7 +1167,9 @@ __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull i0, ull count
     unsigned capped = 0;
     if (j < count) {
         double *out = STAGED ? wrows + lane * row_stride : dirs + j * (ull)row_len;
-        hw_direction(P, i0 + j, tab, ntab, capped, [&](int k, double r, double winv) { out[k] = r; out[d + k] = winv; });
+        const ull p = p0 + j;
+        const ull i = first + (((p >> shift) * stride) << shift) + (p & ((1ull << shift) - 1ull));
+        hw_direction(P, i, tab, ntab, capped, [&](int k, double r, double winv) { out[k] = r; out[d + k] = winv; });
     }
     __syncwarp();
     const ull wfirst = (ull)blockIdx.x * blockDim.x + (ull)warp * 32;      // first sample of this warp
@@ -1806,7 +1810,8 @@ static bool nd_filter_decide(const TfScratch &sc, const double *src, size_t n, i
 {
     const int mode = nd_filter_mode(n);
     if (mode != 2) return mode == 1;
-    const int tile = nd_tile_rows(n, d);
+    // (a small slice per CTA: the sample pass has 2 q-blocks only and needs the slices to fill the GPU)
+    const int tile = std::max(32, std::min(nd_tile_rows(n, d), (int)(n / 296)));
     unsigned host[kNdSample];
     k_fill_u32<<<1, 256>>>(sc.pos, (ull)kNdSample, 1u);
     const dim3 grid((kNdSample + kNdThreads - 1) / kNdThreads, (unsigned)((n + tile - 1) / tile));
@@ -1859,7 +1864,9 @@ extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_
             plan->n = kept;
             rc = plan_upload_impl(plan, nullptr, sc.out);    // ends with a stream synchronisation: the scratch is free afterwards
         } else {
-            rc = plan_upload_impl(plan, pts_host, nullptr);
+            // nothing filtered: the set is on the device already (scratch), a second upload from the host would cost more
+            // than the device-side copy and range reduction
+            rc = plan_upload_impl(plan, nullptr, sc.raw);
         }
         tf_scratch_trim(plan->device);
         return rc;
@@ -2253,10 +2260,22 @@ static int probe32_launch(DevPlan *dp, BpPrepScratch *sc, unsigned nprobe)
         sc->cap_probe = (size_t)nslices * nprobe;
     }
     const dim3 grid(groups, nslices);
-    if (d <= 8) k_probe32<8><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
-    else if (d <= 16) k_probe32<16><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
-    else if (d <= 32) k_probe32<32><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
-    else k_probe32<64><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
+    auto launch = [&](auto dp_tag) {
+        constexpr int DP = decltype(dp_tag)::value;
+        k_probe32<DP><<<grid, kProbeThreads, 0, us>>>(dp->pts, (unsigned)n, d, nprobe, slice, sc->probe_partial);
+    };
+    // (objectives padded to the next size: the pad costs its share of the multiplies)
+    if (d <= 4) launch(std::integral_constant<int, 4>());
+    else if (d <= 6) launch(std::integral_constant<int, 6>());
+    else if (d <= 8) launch(std::integral_constant<int, 8>());
+    else if (d <= 10) launch(std::integral_constant<int, 10>());
+    else if (d <= 12) launch(std::integral_constant<int, 12>());
+    else if (d <= 16) launch(std::integral_constant<int, 16>());
+    else if (d <= 20) launch(std::integral_constant<int, 20>());
+    else if (d <= 24) launch(std::integral_constant<int, 24>());
+    else if (d <= 32) launch(std::integral_constant<int, 32>());
+    else if (d <= 48) launch(std::integral_constant<int, 48>());
+    else launch(std::integral_constant<int, 64>());
     k_probe32_wins<<<(nprobe + 255) / 256, 256, 0, us>>>(sc->probe_partial, nprobe, nslices, (unsigned)n, dp->wins);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -2365,7 +2384,9 @@ static int bp_device_build(DevPlan *dp)
     size_t b1 = 0, b2 = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, b1, (const unsigned *)nullptr, (unsigned *)nullptr, (const unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 32, us));
     CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, b2, (const ull *)nullptr, (ull *)nullptr, (int)n, 0, 64, us));
-    const size_t need_tmp = std::max(b1, b2);
+    size_t b3 = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, b3, (const unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 32, us));
+    const size_t need_tmp = std::max(std::max(b1, b2), b3);
     if (sc->cub_bytes < need_tmp) {
         cudaFree(sc->cub_tmp); sc->cub_tmp = nullptr; sc->cub_bytes = 0;
         CUDA_TRY(cudaMalloc(&sc->cub_tmp, need_tmp));
@@ -2390,7 +2411,7 @@ static int bp_device_build(DevPlan *dp)
         const unsigned *starts = sc->starts + level_off[L];
         int nbits = 0;
         while ((1u << nbits) < nseg) nbits++;
-        const int vb = std::min(kKdValueBits, 32 - nbits);
+        const int vb = std::min(std::max(kKdValueBitsMin, kKdKeyBits - nbits), 32 - nbits);
         const ull cells = (ull)nseg * d * 2;
         k_fill_u64<<<(unsigned)((cells + 255) / 256), 256, 0, us>>>(sc->minmax, cells, ~0ull, 0ull);
         k_kd_minmax<<<gn, 256, 0, us>>>(dp->pts, sc->idx[cur], (unsigned)n, d, starts, nseg, sc->minmax);
@@ -2400,20 +2421,26 @@ static int bp_device_build(DevPlan *dp)
                                                  (int)n, 0, vb + nbits, us));
         cur ^= 1;
     }
-    if (local_nseg) k_kd_local<<<local_nseg, 256, 0, us>>>(dp->pts, sc->idx[cur], d, sc->starts + local_off, qhi);
+    if (local_nseg) k_kd_local<<<local_nseg, kKdLocalThreads, 0, us>>>(dp->pts, sc->idx[cur], d, sc->starts + local_off, qhi);
     // ---- points, keys, bounds in kd order
     const ull n_pad = (ull)dp->bp_nb_pad * kBpBlock;
     const int W = (d + 1) / 2;
     k_bp_gather<<<(unsigned)((n_pad * d + 255) / 256), 256, 0, us>>>(dp->pts, sc->idx[cur], (ull)n, n_pad, d, dp->bp_pts, sc->pos);
     k_bp_keys<<<(unsigned)(((ull)dp->bp_nb_pad * W * kBpBlock + 255) / 256), 256, 0, us>>>(dp->bp_pts, (ull)n, dp->bp_nb_pad, d, qlo, qscale, dp->bp_pkeys);
-    k_bp_bounds<<<(unsigned)(((ull)(dp->bp_nb_pad / 2) * d + 255) / 256), 256, 0, us>>>(dp->bp_pts, (ull)n, dp->bp_nb, dp->bp_nb_pad, d, qlo, qscale, dp->bp_bpair);
+    k_bp_bounds<<<(unsigned)(((ull)(dp->bp_nb_pad / 2) * W * 32 + 255) / 256), 256, 0, us>>>(dp->bp_pkeys, dp->bp_nb_pad, d, dp->bp_bpair);
     // ---- pivots
-    k_bp_pivot_keys<<<gn, 256, 0, us>>>(dp->wins, (unsigned)n, nprobe, sc->pkeys64[0]);
-    {
+    if (n <= (1u << 19) && nprobe <= 4096) {
+        unsigned *k0 = reinterpret_cast<unsigned *>(sc->pkeys64[0]), *k1 = reinterpret_cast<unsigned *>(sc->pkeys64[1]);
+        k_bp_pivot_keys<unsigned, 19><<<gn, 256, 0, us>>>(dp->wins, (unsigned)n, nprobe, k0);
+        size_t tmp = sc->cub_bytes;
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(sc->cub_tmp, tmp, (const unsigned *)k0, k1, (int)n, 0, 32, us));
+        k_bp_pivots<unsigned, 19><<<(unsigned)((dp->bp_npiv * d + 255) / 256), 256, 0, us>>>(dp->pts, k1, sc->pos, dp->bp_npiv, d, dp->bp_piv32, dp->bp_pividx);
+    } else {
+        k_bp_pivot_keys<ull, 32><<<gn, 256, 0, us>>>(dp->wins, (unsigned)n, nprobe, sc->pkeys64[0]);
         size_t tmp = sc->cub_bytes;
         CUDA_TRY(cub::DeviceRadixSort::SortKeys(sc->cub_tmp, tmp, (const ull *)sc->pkeys64[0], sc->pkeys64[1], (int)n, 0, 46, us));
+        k_bp_pivots<ull, 32><<<(unsigned)((dp->bp_npiv * d + 255) / 256), 256, 0, us>>>(dp->pts, sc->pkeys64[1], sc->pos, dp->bp_npiv, d, dp->bp_piv32, dp->bp_pividx);
     }
-    k_bp_pivots<<<(unsigned)((dp->bp_npiv * d + 255) / 256), 256, 0, us>>>(dp->pts, sc->pkeys64[1], sc->pos, dp->bp_npiv, d, dp->bp_piv32, dp->bp_pividx);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(sc->done, us));
     return 0;
@@ -2792,10 +2819,16 @@ static int stage_to_device(struct hvb200_plan *plan, DevPlan *dp, const double *
 
 extern "C" int hvb200cu_gen_hw(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count)
 {
-    return hvb200cu_gen_hw_at(plan, hw, i0, count, 0);
+    return hvb200cu_gen_hw_mapped(plan, hw, i0, 62, 1, 0, count, 0);
 }
 // directions [i0, i0 + count) of the lattice into rows [offset, offset + count) of the direction buffer
 extern "C" int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t i0, uint64_t count, uint64_t offset)
+{
+    return hvb200cu_gen_hw_mapped(plan, hw, i0, 62, 1, 0, count, offset);
+}
+// positions [p0, p0 + count) of the shard (first, shift, stride) into rows [offset, offset + count) of the direction buffer
+extern "C" int hvb200cu_gen_hw_mapped(struct hvb200_plan *plan, const hvb200_hw_params *hw, uint64_t first, int shift, uint64_t stride,
+                                      uint64_t p0, uint64_t count, uint64_t offset)
 {
     HVB200_NVTX("hvb200:gen_hw");
     DevPlan *dp = (DevPlan *)plan->dev;
@@ -2806,9 +2839,12 @@ extern "C" int hvb200cu_gen_hw_at(struct hvb200_plan *plan, const hvb200_hw_para
     P.Nrecip = hw->nsamples ? ~0ull / hw->nsamples : 0;
     P.d = hw->d;
     for (int k = 0; k < HVB200_MAXD; k++) P.a[k] = hw->a[k];
+    const double *tab = dp->device < 16 ? g_hw_tab[dp->device] : nullptr;
+    double *out = dp->dirs + offset * (uint64_t)(2 * hw->d);
+    const unsigned grid = (unsigned)((count + 127) / 128);
     const int b = span_begin(dp, 1);
-    if (gen_hw_staged(hw->d)) k_gen_hw<true><<<(unsigned)((count + 127) / 128), 128, gen_hw_smem_bytes(hw->d), dp->stream>>>(P, i0, count, dp->dirs + offset * (uint64_t)(2 * hw->d), dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
-    else k_gen_hw<false><<<(unsigned)((count + 127) / 128), 128, 0, dp->stream>>>(P, i0, count, dp->dirs + offset * (uint64_t)(2 * hw->d), dp->counters, dp->device < 16 ? g_hw_tab[dp->device] : nullptr, g_hw_ntab);
+    if (gen_hw_staged(hw->d)) k_gen_hw<true><<<grid, 128, gen_hw_smem_bytes(hw->d), dp->stream>>>(P, first, shift, stride, p0, count, out, dp->counters, tab, g_hw_ntab);
+    else k_gen_hw<false><<<grid, 128, 0, dp->stream>>>(P, first, shift, stride, p0, count, out, dp->counters, tab, g_hw_ntab);
     span_end(dp, b);
     CUDA_TRY(cudaGetLastError());
     plan->stats.dirgen_launches++;

@@ -20,11 +20,11 @@ def shard_range(nsamples: int, rank: int, world: int) -> Tuple[int, int]:
     return (nsamples * rank) // world, (nsamples * (rank + 1)) // world
 
 
-SHARD_BLOCK = 1 << 21      # HVB200_SHARD_BLOCK of include/hvapprox_b200.h
+SHARD_BLOCK = 1 << 14      # HVB200_SHARD_BLOCK of include/hvapprox_b200.h
 
 
 def shard_block(nsamples: int, world: int) -> int:
-    """Block size used for `world` ranks (hvb200_shard_block): 2^21 directions, halved down to 2^10 until every
+    """Block size used for `world` ranks (hvb200_shard_block): 2^14 directions, halved down to 2^10 until every
     rank gets at least 4 blocks."""
     block = SHARD_BLOCK
     while block > (1 << 10) and block * max(1, world) * 4 > nsamples:

@@ -103,4 +103,4 @@ def test_shard_block_matches_the_library():
     for N in (1, 1000, 262144, 10**6, 10**8, 2**31):
         for world in (1, 2, 8, 16):
             assert shard_block(N, world) == L.hvb200_shard_block(ctypes.c_uint64(N), world)
-            assert (1 << 10) <= shard_block(N, world) <= (1 << 21)
+            assert (1 << 10) <= shard_block(N, world) <= (1 << 14)
