@@ -139,6 +139,16 @@ MOOCORE_API int hvb200_hv_approx_sets(int method, const double *data, const size
                                       dimension_t nobjs, const double *ref, const boolvec *maximise,
                                       uint_fast32_t nsamples, uint32_t seed, int device, double *volumes_out);
 
+/* Hypervolume-CONTRIBUTION approximation on the direction set of hv_approx (the polar-coordinate estimator of the DZ2019
+ * paper cited at c/hvapprox.h:20-24; the reference itself only has the exact c/hv_contrib.c, so this is an extension and
+ * its parity is unpinned): contrib_out[i] ~ HV(P) - HV(P \ {p_i}) for each of the npoints rows (0 for rows that do not
+ * strictly dominate ref), *hv_out (optional) the hypervolume estimate of the same direction set.  nobjs <= 32.
+ * ignore_dominated != 0 follows hv_contributions(..., ignore_dominated = true) of c/hv_contrib.c:348: strictly dominated
+ * points are removed first and get 0; with 0 they stay in the set and shield the points that dominate them. */
+MOOCORE_API int hvb200_hv_contributions_approx(int method, const double *data, size_t npoints, dimension_t nobjs,
+                                               const double *ref, const boolvec *maximise, uint_fast32_t nsamples,
+                                               uint32_t seed, int device, int ignore_dominated, double *contrib_out, double *hv_out);
+
 /* Single-process multi-GPU: evaluate one estimate sharded over `ndevices` GPUs
  * (devices 0..ndevices-1, contiguous index ranges, partial sums combined with one NCCL
  * all-gather when libnccl can be loaded, else by per-device copies). */

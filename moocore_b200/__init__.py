@@ -11,6 +11,7 @@ from ._api import (  # noqa: F401
     hv_approx,
     hv_approx_range,
     hv_approx_sets,
+    hv_contributions_approx,
     hv_approx_shard,
     hv_approx_finalize,
     Plan,
@@ -31,6 +32,7 @@ __all__ = [
     "hv_approx",
     "hv_approx_range",
     "hv_approx_sets",
+    "hv_contributions_approx",
     "hv_approx_shard",
     "hv_approx_finalize",
     "Plan",

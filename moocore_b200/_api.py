@@ -102,6 +102,10 @@ def _load() -> ctypes.CDLL:
     L.hvb200_hv_approx_sets.restype = ctypes.c_int
     L.hvb200_hv_approx_sets.argtypes = [ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.c_uint8,
                                         _c_double_p, _c_u8_p, u64, u32, ctypes.c_int, _c_double_p]
+    L.hvb200_hv_contributions_approx.restype = ctypes.c_int
+    L.hvb200_hv_contributions_approx.argtypes = [ctypes.c_int, _c_double_p, size_t, dim_t, _c_double_p, _c_u8_p, u64, u32, ctypes.c_int,
+                                                 ctypes.c_int, _c_double_p, ctypes.POINTER(ctypes.c_double)]
+    L.hvb200_multi_last_exchange.restype = ctypes.c_int
     L.hvb200_plan_run_blocks.restype = ctypes.c_int
     L.hvb200_plan_run_blocks.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, u64, vp, _c_double_p]
     L.hvb200_plan_last_stats.restype = ctypes.c_int
@@ -285,6 +289,43 @@ def hv_approx_sets(
     if rc != 0:
         raise RuntimeError(f"moocore_b200: hv_approx_sets failed ({rc}): {_last_error()}")
     return out
+
+
+def hv_contributions_approx(
+    points,
+    /,
+    ref,
+    *,
+    maximise: bool | Sequence[bool] = False,
+    nsamples: int = 262_144,
+    seed: int | np.random.Generator | None = None,
+    method: Literal["DZ2019-HW", "DZ2019-MC", "Rphi-FWE+"] = "Rphi-FWE+",
+    ignore_dominated: bool = True,
+    device: int = 0,
+    return_hv: bool = False,
+):
+    """Approximate hypervolume contributions ``HV(P) - HV(P \\ {p_i})`` of every row of ``points`` from the direction
+    set of ``hv_approx`` (same arguments).  For each direction the point attaining ``max_p min_k`` is credited with
+    ``s1^d - s2^d`` (largest and second largest value), so the contributions and the hypervolume estimate come from ONE
+    pass.  Rows that do not strictly dominate ``ref`` (and duplicates) get 0.  ``ignore_dominated`` as in
+    ``moocore.hv_contributions`` (_moocore.py): True removes strictly dominated rows first (they get 0 and do not shield
+    the rows that dominate them), False keeps them in the set.  Extension: the reference only computes
+    exact contributions (``moocore.hv_contributions``); with ``return_hv=True`` the estimate of the hypervolume itself
+    is returned as well."""
+    if method not in METHOD_IDS:
+        raise ValueError(f"Unknown method = {method}")
+    points, ref, maxi, nsamples, nobj = _prepare(points, ref, maximise, nsamples)
+    if nobj < 2:
+        raise ValueError("hv_contributions_approx needs at least 2 objectives")
+    out = np.zeros(points.shape[0])
+    hv = ctypes.c_double(0.0)
+    L = _load()
+    rc = L.hvb200_hv_contributions_approx(METHOD_IDS[method], _dp(points), points.shape[0], nobj, _dp(ref), maxi.ctypes.data_as(_c_u8_p),
+                                          nsamples, _get_seed_for_c(seed) if method == "DZ2019-MC" else 0, device, 1 if ignore_dominated else 0,
+                                          _dp(out), ctypes.byref(hv))
+    if rc != 0:
+        raise RuntimeError(f"moocore_b200: hv_contributions_approx failed ({rc}): {_last_error()}")
+    return (out, float(hv.value)) if return_hv else out
 
 
 def _refset_common(points, ref, maximise, check_all_positive=False):

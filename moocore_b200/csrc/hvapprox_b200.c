@@ -804,6 +804,91 @@ int hvb200_hv_approx_sets(int method, const double *data, const size_t *cumsizes
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* hypervolume-contribution approximation (second half)                     */
+/* ------------------------------------------------------------------------------------------ */
+/* contrib_out[i] ~ HV(P) - HV(P \ {p_i}) (P without its strictly dominated points when ignore_dominated) from the direction set of `method`: for every direction the arg-max point
+   is credited with s1^d - s2^d (largest and second largest max-min value), see hvb200_contrib.cuh.  Points that do not
+   strictly dominate ref get 0, like every point when none does.  The reference has no approximate implementation
+   (c/hv_contrib.c is exact): parity is unpinned, the estimate is cross-checked against the exact contributions. */
+int hvb200_hv_contributions_approx(int method, const double *data, size_t npoints, dimension_t nobjs, const double *ref,
+                                   const boolvec *maximise, uint_fast32_t nsamples_, uint32_t seed, int device,
+                                   int ignore_dominated, double *contrib_out, double *hv_out)
+{
+    tls_error[0] = 0;
+    const int d = (int)nobjs;
+    const uint64_t nsamples = (uint64_t)nsamples_;
+    for (size_t i = 0; i < npoints; i++) contrib_out[i] = 0.0;
+    if (hv_out) *hv_out = 0.0;
+    if (d < 2 || d > MOOCORE_HVAPPROX_DIMENSION_MAX + 1) { hvb200_set_error("nobjs = %d outside [2, %d]", d, MOOCORE_HVAPPROX_DIMENSION_MAX + 1); return -2; }
+    if (nsamples == 0) { hvb200_set_error("nsamples must be positive"); return -2; }
+    if (device < 0 || device >= hvb200cu_device_count()) {
+        hvb200_set_error("CUDA device %d not available (%d visible); this library has no CPU fallback", device, hvb200cu_device_count());
+        return -3;
+    }
+    /* transform_and_filter (c/hvapprox.c:30-66) keeping the original row of every surviving point */
+    double *pts = malloc((npoints ? npoints : 1) * (size_t)d * sizeof *pts);
+    size_t *orig = malloc((npoints ? npoints : 1) * sizeof *orig);
+    if (!pts || !orig) { free(pts); free(orig); hvb200_set_error("out of host memory"); return -4; }
+    size_t kept = 0;
+    for (size_t i = 0; i < npoints; i++) {
+        int k;
+        for (k = 0; k < d; k++) {
+            const double v = maximise[k] ? data[i * (size_t)d + k] - ref[k] : ref[k] - data[i * (size_t)d + k];
+            if (!(v > 0)) break;
+            pts[kept * (size_t)d + k] = v;
+        }
+        if (k == d) orig[kept++] = i;
+    }
+    int rc = 0;
+    if (ignore_dominated && kept > 1) {
+        /* hv_contributions(..., ignore_dominated = true) of the reference (c/hv_contrib.c:348): strictly dominated points
+           are taken out first (contribution 0) and do not shield the points that dominate them; duplicates stay */
+        unsigned *flags = malloc(kept * sizeof *flags);
+        if (!flags) { hvb200_set_error("out of host memory"); rc = -4; }
+        else if (hvb200cu_nd_strict_flags(device, pts, kept, d, flags)) rc = -1;
+        else {
+            size_t m = 0;
+            for (size_t j = 0; j < kept; j++)
+                if (flags[j]) {
+                    if (m != j) { memmove(pts + m * (size_t)d, pts + j * (size_t)d, (size_t)d * sizeof *pts); orig[m] = orig[j]; }
+                    m++;
+                }
+            kept = m;
+        }
+        free(flags);
+    }
+    if (rc == 0 && kept) {
+        hvb200_plan *plan = calloc(1, sizeof *plan);
+        double *sums = malloc(kept * sizeof *sums);
+        void *ctx = NULL;
+        double hilo[2] = {0.0, 0.0};
+        if (!plan || !sums) { hvb200_set_error("out of host memory"); rc = -4; }
+        if (rc == 0) {
+            plan->device = device;
+            plan->d = d;
+            plan->n = kept;
+            plan->kernel = HVB200_KERNEL_EXACT;
+            plan->no_ndfilter = 1;                    /* a dominated point can be the second best of a direction */
+            if (hvb200cu_plan_upload(plan, pts)) rc = -1;
+        }
+        if (rc == 0 && hvb200cu_contrib_begin(plan, &ctx)) rc = -1;
+        if (rc == 0 && run_range_ex(plan, method, nsamples, seed, 0, nsamples, NULL, hilo, NULL, NULL, ctx)) rc = -1;
+        if (ctx && hvb200cu_contrib_end(plan, ctx, rc == 0 ? sums : NULL)) rc = -1;
+        if (rc == 0) {
+            const long double c_d = hvb200_cd[d];
+            for (size_t j = 0; j < kept; j++) contrib_out[orig[j]] = (double)(c_d * ((long double)sums[j] / (long double)nsamples));
+            if (hv_out) *hv_out = hvb200_finalize(nobjs, nsamples_, hilo, 1);
+        }
+        if (plan && plan->dev) hvb200cu_plan_free(plan);
+        free(plan);
+        free(sums);
+    }
+    free(pts);
+    free(orig);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* epsilon indicator (c/epsilon.h:197-221; python/src/moocore/libmoocore.h:24-25)              */
 /* ------------------------------------------------------------------------------------------ */
 static double epsilon_common(int mult, const double *data, size_t n, dimension_t dim, const double *ref, size_t ref_size,

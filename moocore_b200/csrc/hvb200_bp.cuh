@@ -35,6 +35,9 @@
 #ifndef HVB200_BP_R2
 #define HVB200_BP_R2 1
 #endif
+#ifndef HVB200_BP_ENDBAR
+#define HVB200_BP_ENDBAR 0       // 1: the warps of a CTA start every chunk together (development switch)
+#endif
 #ifndef HVB200_BP_MINB
 #define HVB200_BP_MINB 3
 #endif
@@ -101,7 +104,7 @@ __host__ __device__ inline BpSmem bp_smem_layout(int D, int R, int seg_blocks, i
     s.best = o; o += (size_t)CH * 8;
     s.piv = o;  o += ((size_t)n_piv * D * 4 + 15) & ~(size_t)15;
     s.list = o; o += (size_t)(kBpThreads / 32) * (CH + 8) * 2;
-    s.bar = o;  o += 32;
+    s.bar = o;  o += 64;             // mbarrier, counters, per-warp hit counts
     s.red = o;  o += 8 * 8;
     s.total = o;
     return s;
@@ -191,14 +194,18 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
     long long *bestbits = reinterpret_cast<long long *>(smem_raw + L.best);  // [CH]
     float *piv = reinterpret_cast<float *>(smem_raw + L.piv);                // [n_piv][D]
     ull *bar = reinterpret_cast<ull *>(smem_raw + L.bar);
-    unsigned *ctr = reinterpret_cast<unsigned *>(bar + 1);                   // [0] hit entries, [1] next block of phase C, [2] next chunk
+    unsigned *ctr = reinterpret_cast<unsigned *>(bar + 1);                   // [1] next block of phase C, [2], [3] next chunk (alternating)
+    unsigned *hcnt = ctr + 4;                                                // [8] hit entries of each warp's list
     double *red = reinterpret_cast<double *>(smem_raw + L.red);
     const int mstride = L.mask_stride;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned short *slist = reinterpret_cast<unsigned short *>(smem_raw + L.list) + warp * LCAP;   // this warp's pair list
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); ctr[0] = 0; ctr[1] = kBpThreads / 32; }
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); ctr[1] = kBpThreads / 32; }
+    // every warp appends to its own eighth of the CTA's hit list: the count is a warp-uniform register, no atomics
+    constexpr unsigned WCAP = kBpHitCap / (kBpThreads / 32);
     uint2 *hits = a.hits + (size_t)blockIdx.x * kBpHitCap;
+    uint2 *whits = hits + (size_t)warp * WCAP;
     for (int i = tid; i < a.n_piv * D; i += kBpThreads) piv[i] = a.piv32[i];
     {
         // row CH of the threshold planes: the key -(S+1) in every half-word -> no point passes
@@ -227,8 +234,9 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
 
     // chunks are handed out dynamically (their cost varies with the directions); the first one is static
     ull chunk = blockIdx.x;
+    unsigned cpar = 0;                // which of ctr[2], ctr[3] carries this chunk's successor
     while (chunk < n_chunks) {
-        if (tid == 0) ctr[2] = atomicAdd(a.chunk_counter, 1u);      // consumed after the barriers of this chunk
+        if (tid == 0) ctr[2 + cpar] = atomicAdd(a.chunk_counter, 1u);      // consumed behind the barriers of this chunk
         const ull chunk_base = chunk * CH;
         if (!resident && tid == 0) {
             // first segment of this chunk; the previous chunk's phase B is behind several CTA barriers
@@ -406,6 +414,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
             const int seg_real = min(seg_nb, a.nb - seg0);                         // real (non-padding) blocks
             // blocks are handed out dynamically (the first one per warp is fixed): their pair counts differ a lot
             int b = warp;
+            unsigned hcount = 0;                                                   // entries in this warp's hit list
 #pragma unroll 1
             while (b < seg_real) {
                 int b_next = 0;
@@ -487,13 +496,15 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                     if (c0 | c1 | c2 | c3) {
                         const unsigned cm = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : c3));
                         const unsigned of = lane == 0 ? off[0] : (lane == 1 ? off[1] : (lane == 2 ? off[2] : off[3]));
+                        const bool mine = lane < 4 && cm != 0u;
+                        const unsigned nz = __ballot_sync(0xffffffffu, mine);              // bit u: pair u has candidates
                         bool spilled = false;
-                        if (lane < 4 && cm) {
-                            unsigned slot;
-                            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(smem_u32(ctr)) : "memory");
-                            if (slot < (unsigned)kBpHitCap) hits[slot] = make_uint2(((of >> 4) << kBpPtBits) | blk, cm);
+                        if (mine) {
+                            const unsigned slot = hcount + __popc(nz & ((1u << lane) - 1u));
+                            if (slot < WCAP) whits[slot] = make_uint2(((of >> 4) << kBpPtBits) | blk, cm);
                             else spilled = true;
                         }
+                        hcount += __popc(nz);
                         const unsigned sp = __ballot_sync(0xffffffffu, spilled);
                         if (sp) {
                             // the CTA's hit list is full (never seen in practice): evaluate in place
@@ -508,13 +519,22 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                 }
                 __syncwarp();                 // the list is rewritten for the warp's next block
             }
+            if (lane == 0) hcnt[warp] = min(hcount, WCAP);
             __syncthreads();
 
             // ---- phase D: lane = hit entry, exact FP64 evaluation of its candidate points
             {
-                const unsigned nc = min(ctr[0], (unsigned)kBpHitCap);
-                for (unsigned i = tid; i < nc; i += kBpThreads) {
-                    const uint2 e = hits[i];
+                // the eight warp lists as one flat index range: entry i lives in list w at i - first[w]
+                unsigned first[kBpThreads / 32 + 1];
+                first[0] = 0;
+#pragma unroll
+                for (int w = 0; w < kBpThreads / 32; w++) first[w + 1] = first[w] + hcnt[w];
+                for (unsigned i = tid; i < first[kBpThreads / 32]; i += kBpThreads) {
+                    unsigned w = 0, base = 0;
+#pragma unroll
+                    for (int t = 1; t < kBpThreads / 32; t++)
+                        if (i >= first[t]) { w = t; base = first[t]; }
+                    const uint2 e = hits[(size_t)w * WCAP + (i - base)];
                     const unsigned dl = e.x >> kBpPtBits, blk = e.x & ((1u << kBpPtBits) - 1u);
                     unsigned cm = e.y;
                     while (cm) {
@@ -526,7 +546,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                 }
             }
             __syncthreads();
-            if (tid == 0) { ctr[0] = 0; ctr[1] = kBpThreads / 32; }
+            if (tid == 0) ctr[1] = kBpThreads / 32;
         }
 
         double acc = 0.0;
@@ -538,16 +558,16 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                 if (a.values) a.values[chunk_base + (ull)r * kBpThreads + tid] = v;
             }
         }
-        // fixed-shape reduction of the chunk: lanes, then the 8 warps
+        // fixed-shape reduction of the chunk: the lanes of a warp here, the 8 warp sums of every chunk in k_reduce (one
+        // slot per (chunk, warp): the result does not depend on which CTA ran which chunk, and no CTA barrier is needed)
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-        if (lane == 0) red[warp] = acc;
+        if (lane == 0) a.chunk_sums[chunk * (kBpThreads / 32) + warp] = acc;
+        chunk = (ull)gridDim.x + ctr[2 + cpar];      // written by thread 0 before this chunk's barriers; its twin serves the next chunk
+        cpar ^= 1u;
+#if HVB200_BP_ENDBAR
         __syncthreads();
-        const ull next = (ull)gridDim.x + ctr[2];
-        if (tid == 0)
-            a.chunk_sums[chunk] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-        __syncthreads();                       // red and ctr[2] are rewritten by the next chunk
-        chunk = next;
+#endif
     }
 
 #pragma unroll

@@ -35,6 +35,7 @@ struct hvb200_plan {
     /* device side (owned by the CUDA TU) */
     void *dev;             /* struct dev_plan*                                                  */
     int want_fused_hw;     /* the run being started is a DZ2019-HW sum: the max-min kernel may generate its directions itself */
+    int no_ndfilter;       /* keep dominated points (contribution approximation: they can be the second best) */
     void *share;           /* preparation shared by the plans of one multi-GPU call (hvb200cu_share_new), or NULL */
     hvb200_stats stats;
 };
@@ -101,6 +102,11 @@ int hvb200cu_sets_end(struct hvb200_plan *plan, void *ctx, double *hilo_host);
    point set on several devices (built once, by whichever plan needs it first) */
 void *hvb200cu_share_new(void);
 void hvb200cu_share_free(void *share);
+
+/* hypervolume-contribution approximation: a per-batch sink like the batched sets (passed as sets_ctx) */
+int hvb200cu_nd_strict_flags(int device, const double *pts_host, size_t n, int d, unsigned *flags_host);
+int hvb200cu_contrib_begin(struct hvb200_plan *plan, void **ctx_out);
+int hvb200cu_contrib_end(struct hvb200_plan *plan, void *ctx, double *contrib_host);
 
 /* pinned staging buffer for host-produced streams (MC normals, Rphi u); grows on demand */
 double *hvb200cu_staging(struct hvb200_plan *plan, size_t ndoubles);

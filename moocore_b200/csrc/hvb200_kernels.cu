@@ -883,6 +883,47 @@ __global__ void __launch_bounds__(1024) k_reduce(const double *__restrict__ cta_
     }
     if (tid == 0) { out_hilo[0] = sh[0]; out_hilo[1] = sl[0]; }
 }
+// Long runs of the pruned kernel leave one partial sum per (chunk, warp) — 1.6 M of them for 1e8 directions — which one
+// CTA would walk for half a millisecond.  Stage 1: CTA g reduces the fixed slice [g S, (g + 1) S) to one (hi, lo) pair
+// with the same tree; stage 2 adds the pairs.  The shape depends on n only, so the result stays deterministic.
+static constexpr int kReduceSlice = 1 << 15;
+__global__ void __launch_bounds__(1024) k_reduce_slices(const double *__restrict__ sums, ull n, double *__restrict__ pairs)
+{
+    __shared__ double sh[1024], sl[1024];
+    const int tid = threadIdx.x;
+    const ull i0 = (ull)blockIdx.x * kReduceSlice, i1 = min(n, i0 + (ull)kReduceSlice);
+    double hi = 0.0, lo = 0.0;
+    for (ull i = i0 + tid; i < i1; i += 1024) dd_add(hi, lo, sums[i], 0.0);
+    sh[tid] = hi; sl[tid] = lo;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) {
+        if (tid < off) {
+            double h = sh[tid], l = sl[tid];
+            dd_add(h, l, sh[tid + off], sl[tid + off]);
+            sh[tid] = h; sl[tid] = l;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { pairs[2 * blockIdx.x] = sh[0]; pairs[2 * blockIdx.x + 1] = sl[0]; }
+}
+__global__ void __launch_bounds__(1024) k_reduce_pairs(const double *__restrict__ pairs, int n, double *out_hilo)
+{
+    __shared__ double sh[1024], sl[1024];
+    const int tid = threadIdx.x;
+    double hi = 0.0, lo = 0.0;
+    for (int i = tid; i < n; i += 1024) dd_add(hi, lo, pairs[2 * i], pairs[2 * i + 1]);
+    sh[tid] = hi; sl[tid] = lo;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) {
+        if (tid < off) {
+            double h = sh[tid], l = sl[tid];
+            dd_add(h, l, sh[tid + off], sl[tid + off]);
+            sh[tid] = h; sl[tid] = l;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { out_hilo[0] = sh[0]; out_hilo[1] = sl[0]; }
+}
 
 // ------------------------------------------------------------------------------------------------
 // K2: DZ2019-HW directions
@@ -1188,6 +1229,7 @@ __global__ void __launch_bounds__(128) k_gen_hw(const HwDev P, ull first, int sh
 }
 #include "hvb200_bp.cuh"
 #include "hvb200_bpprep.cuh"
+#include "hvb200_contrib.cuh"
 
 static bool gen_hw_staged(int d) { return d >= 7 && d <= 12; }
 static int gen_hw_smem_bytes(int d) { return gen_hw_staged(d) ? 128 * (2 * d + 1) * (int)sizeof(double) : 0; }
@@ -1365,8 +1407,9 @@ __global__ void __launch_bounds__(256) k_fill_u32(unsigned *__restrict__ a, ull 
 // to 1) when a dominator turns up — a single thread walking the whole set is latency-bound (4 ms at n = 1e4).
 // Points q = qi * qstride for qi < qcount, flags indexed by qi (qstride = 1, qcount = n: the whole set; a strided
 // sample first tells whether the full pass is worth its time).
+// strict = 1: only strict dominance clears a flag (duplicates stay; the contribution approximation's ignore_dominated).
 __global__ void __launch_bounds__(kNdThreads) k_nd_flags(const double *__restrict__ pts, ull n, int d, int tile, unsigned *flags,
-                                                         ull qstride, ull qcount)
+                                                         ull qstride, ull qcount, int strict = 0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sp = reinterpret_cast<double *>(smem_raw);                  // [tile][d]
@@ -1388,7 +1431,7 @@ __global__ void __launch_bounds__(kNdThreads) k_nd_flags(const double *__restric
             if (pk < qv[k]) break;
             greater |= pk > qv[k];
         }
-        if (k == d && (greater || t0 + (ull)j < q)) { flags[qi] = 0u; return; }
+        if (k == d && (greater || (!strict && t0 + (ull)j < q))) { flags[qi] = 0u; return; }
     }
 }
 __global__ void __launch_bounds__(256) k_gather_flagged(const double *__restrict__ src, ull n, int d, const unsigned *__restrict__ flags,
@@ -1537,8 +1580,9 @@ struct DevPlan {
     double *bp_pts = nullptr; size_t bp_pts_cap = 0;
     float *bp_piv32 = nullptr; unsigned *bp_pividx = nullptr;
     uint2 *bp_hits = nullptr; size_t bp_hits_cap = 0;    // per-CTA hit lists of phase C
-    double *bp_chunk_sums = nullptr; size_t bp_chunk_cap = 0, bp_chunk_off = 0;   // one partial sum per chunk of the run
+    double *bp_chunk_sums = nullptr; size_t bp_chunk_cap = 0, bp_chunk_off = 0;   // one partial sum per (chunk, warp) of the run
     unsigned *bp_chunk_counter = nullptr;
+    double *reduce_pairs = nullptr; size_t reduce_pairs_cap = 0;        // (hi, lo) of the slices of a long run's partial sums
     unsigned *bp_pkeys = nullptr, *bp_bpair = nullptr; size_t bp_keys_cap = 0, bp_pair_cap = 0;
     int bp_nb = 0, bp_nb_pad = 0, bp_seg_blocks = 0, bp_npiv = 0;
     size_t bp_smem = 0;
@@ -1843,10 +1887,29 @@ static int nd_filter_device(const TfScratch &sc, const double *src, double *dst,
     return 0;
 }
 
+// flags_host[i] = 1 unless some other point strictly dominates point i (transformed space: larger is better);
+// duplicates keep their flags.  Used by the contribution approximation (ignore_dominated).
+extern "C" int hvb200cu_nd_strict_flags(int device, const double *pts_host, size_t n, int d, unsigned *flags_host)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(tf_mutex[device < 16 ? device : 15]);
+    TfScratch sc;
+    if (tf_scratch_acquire(device, n, d, sc)) return -1;
+    CUDA_TRY(cudaMemcpy(sc.raw, pts_host, n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice));
+    const int tile = nd_tile_rows(n, d);
+    k_fill_u32<<<(unsigned)((n + 255) / 256), 256>>>(sc.flags, (ull)n, 1u);
+    const dim3 grid((unsigned)((n + kNdThreads - 1) / kNdThreads), (unsigned)((n + tile - 1) / tile));
+    k_nd_flags<<<grid, kNdThreads, (size_t)tile * d * sizeof(double)>>>(sc.raw, (ull)n, d, tile, sc.flags, 1ull, (ull)n, 1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(flags_host, sc.flags, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    tf_scratch_trim(device);
+    return 0;
+}
+
 extern "C" int hvb200cu_plan_upload(struct hvb200_plan *plan, const double *pts_host)
 {
     plan->n_dominated = 0;
-    if (nd_filter_mode(plan->n)) {
+    if (!plan->no_ndfilter && nd_filter_mode(plan->n)) {
         CUDA_TRY(cudaSetDevice(plan->device));
         std::lock_guard<std::mutex> lock(tf_mutex[plan->device < 16 ? plan->device : 15]);
         TfScratch sc;
@@ -2061,7 +2124,7 @@ static void devplan_release(DevPlan *dp)
 {
     cudaFree(dp->pts); cudaFree(dp->keys); cudaFree(dp->dirs); cudaFree(dp->cta_sums); cudaFree(dp->values);
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
-    cudaFree(dp->pts_tmp); cudaFree(dp->wins); cudaFree(dp->gen_scratch);
+    cudaFree(dp->pts_tmp); cudaFree(dp->wins); cudaFree(dp->gen_scratch); cudaFree(dp->reduce_pairs);
     bp_prep_scratch_free(&dp->prep);
     cudaFree(dp->bp_hits); cudaFree(dp->bp_chunk_sums); cudaFree(dp->bp_chunk_counter); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
     for (int i = 0; i < 2; i++) {
@@ -2746,7 +2809,7 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     }
     if (mode == MODE_BP) {
         const size_t ch = (size_t)kBpThreads * bp_R_of(d);
-        const size_t need = (size_t)(plan->run_total / ch) + (size_t)(plan->run_total / batch) + 8;
+        const size_t need = (size_t)(kBpThreads / 32) * ((size_t)(plan->run_total / ch) + (size_t)(plan->run_total / batch) + 8);
         if (dp->bp_chunk_cap < need) {
             cudaFree(dp->bp_chunk_sums);
             dp->bp_chunk_sums = nullptr; dp->bp_chunk_cap = 0;
@@ -2988,9 +3051,10 @@ static int bp_fill_args(DevPlan *dp, BpArgs &ka, uint64_t count, ull n_chunks)
     ka.nb_pad = dp->bp_nb_pad;
     ka.seg_blocks = dp->bp_seg_blocks;
     ka.count = count;
-    if (dp->bp_chunk_off + n_chunks > dp->bp_chunk_cap) { hvb200_set_error("internal: chunk buffer too small"); return -1; }
+    const size_t slots = (size_t)n_chunks * (kBpThreads / 32);           // one per (chunk, warp)
+    if (dp->bp_chunk_off + slots > dp->bp_chunk_cap) { hvb200_set_error("internal: chunk buffer too small"); return -1; }
     ka.chunk_sums = dp->bp_chunk_sums + dp->bp_chunk_off;
-    dp->bp_chunk_off += (size_t)n_chunks;
+    dp->bp_chunk_off += slots;
     ka.chunk_counter = dp->bp_chunk_counter;
     CUDA_TRY(cudaMemsetAsync(dp->bp_chunk_counter, 0, sizeof(unsigned), dp->stream));
     ka.slow_counter = dp->counters + 1;
@@ -3399,6 +3463,7 @@ extern "C" int hvb200cu_gd_common(int device, const double *X_host, size_t nx, c
 
 // ---- batched point sets ------------------------------------------------------------------------
 struct SetsCtx {
+    int kind = 0;                        // first member of every per-batch sink: 0 = batched sets, 1 = contributions
     double *pts = nullptr;
     unsigned *off = nullptr;
     double *partial = nullptr, *hilo = nullptr;
@@ -3445,8 +3510,10 @@ extern "C" int hvb200cu_sets_begin(struct hvb200_plan *plan, const double *pts_h
     CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
     return 0;
 }
+static int contrib_batch(struct hvb200_plan *plan, void *ctx, uint64_t count);
 extern "C" int hvb200cu_sets_maxmin(struct hvb200_plan *plan, void *ctx, uint64_t count)
 {
+    if (*(const int *)ctx == 1) return contrib_batch(plan, ctx, count);
     DevPlan *dp = (DevPlan *)plan->dev;
     SetsCtx *c = (SetsCtx *)ctx;
     sets_fn fn = pick_sets<16>(dp->d);
@@ -3476,13 +3543,127 @@ extern "C" int hvb200cu_sets_end(struct hvb200_plan *plan, void *ctx, double *hi
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// hypervolume-contribution approximation (hvb200_contrib.cuh): per batch of directions k_top2, a stable sort of
+// (arg-max, delta) and one warp per point adding its run — deterministic whatever the schedule
+// ------------------------------------------------------------------------------------------------
+struct ContribCtx {
+    int kind = 1;
+    double *contrib = nullptr;           // [n] running sums of s1^d - s2^d
+    double *delta[2] = {nullptr, nullptr};
+    unsigned *arg[2] = {nullptr, nullptr};
+    void *cub_tmp = nullptr;
+    size_t cap = 0, cub_bytes = 0;
+};
+typedef void (*top2_fn)(const double *, int, int, int, const double *, ull, double *, unsigned *, double *);
+template <int D>
+static top2_fn pick_top2(int d)
+{
+    if constexpr (D < 2) {
+        return nullptr;
+    } else {
+        if (d == D) return (top2_fn)k_top2<D>;
+        return pick_top2<D - 1>(d);
+    }
+}
+extern "C" int hvb200cu_contrib_begin(struct hvb200_plan *plan, void **ctx_out)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    *ctx_out = nullptr;
+    if (dp->d > 32) { hvb200_set_error("contribution approximation supports at most 32 objectives"); return -2; }
+    ContribCtx *c = new (std::nothrow) ContribCtx();
+    if (!c) { hvb200_set_error("out of host memory"); return -4; }
+    *ctx_out = c;
+    CUDA_TRY(cudaSetDevice(dp->device));
+    CUDA_TRY(cudaMalloc(&c->contrib, dp->n * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(c->contrib, 0, dp->n * sizeof(double), dp->own_stream));
+    CUDA_TRY(cudaStreamSynchronize(dp->own_stream));
+    return 0;
+}
+static int contrib_batch(struct hvb200_plan *plan, void *ctx, uint64_t count)
+{
+    HVB200_NVTX("hvb200:contributions");
+    DevPlan *dp = (DevPlan *)plan->dev;
+    ContribCtx *c = (ContribCtx *)ctx;
+    const int d = dp->d;
+    if (count == 0) return 0;
+    if (count > 0x7fffffffull) { hvb200_set_error("internal: contribution batch too large"); return -1; }
+    if (c->cap < count) {
+        for (int i = 0; i < 2; i++) { cudaFree(c->delta[i]); cudaFree(c->arg[i]); c->delta[i] = nullptr; c->arg[i] = nullptr; }
+        c->cap = 0;
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaMalloc(&c->delta[i], count * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&c->arg[i], count * sizeof(unsigned)));
+        }
+        c->cap = count;
+    }
+    int key_bits = 1;
+    while (key_bits < 32 && (1ull << key_bits) <= dp->n) key_bits++;
+    size_t need = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, need, (const unsigned *)nullptr, (unsigned *)nullptr, (const double *)nullptr, (double *)nullptr,
+                                             (int)count, 0, key_bits, dp->stream));
+    if (c->cub_bytes < need) {
+        cudaFree(c->cub_tmp); c->cub_tmp = nullptr; c->cub_bytes = 0;
+        CUDA_TRY(cudaMalloc(&c->cub_tmp, need));
+        c->cub_bytes = need;
+    }
+    top2_fn fn = pick_top2<32>(d);
+    const size_t smem = 2 * (size_t)dp->stage_bytes + 2 * sizeof(ull) + 8 * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem_limit()));
+    const ull chunk = (ull)kTop2Threads * (d <= 12 ? 2 : 1);
+    const ull n_chunks = (count + chunk - 1) / chunk;
+    const unsigned grid = (unsigned)std::min<ull>((ull)std::min(dp->grid, 2 * dp->sm_count), n_chunks);
+    const int b = span_begin(dp, 0);
+    fn<<<grid, kTop2Threads, smem, dp->stream>>>(dp->pts, dp->n_tiles, dp->tile_points, dp->stage_bytes, dp->dirs_view ? dp->dirs_view : dp->dirs,
+                                                  (ull)count, c->delta[0], c->arg[0], dp->cta_sums);
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    size_t tmp = c->cub_bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, (const unsigned *)c->arg[0], c->arg[1], (const double *)c->delta[0], c->delta[1],
+                                             (int)count, 0, key_bits, dp->stream));
+    k_contrib_accumulate<<<(unsigned)(((ull)dp->n * 32 + 255) / 256), 256, 0, dp->stream>>>(c->arg[1], c->delta[1], (ull)count, (unsigned)dp->n, c->contrib);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.maxmin_launches++;
+    return 0;
+}
+extern "C" int hvb200cu_contrib_end(struct hvb200_plan *plan, void *ctx, double *contrib_host)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    ContribCtx *c = (ContribCtx *)ctx;
+    int rc = 0;
+    if (c && contrib_host && c->contrib) {
+        if (cudaMemcpyAsync(contrib_host, c->contrib, dp->n * sizeof(double), cudaMemcpyDeviceToHost, dp->stream) != cudaSuccess ||
+            cudaStreamSynchronize(dp->stream) != cudaSuccess) {
+            hvb200_set_error("reading the contributions back failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = -1;
+        }
+    }
+    if (c) {
+        cudaFree(c->contrib);
+        for (int i = 0; i < 2; i++) { cudaFree(c->delta[i]); cudaFree(c->arg[i]); }
+        cudaFree(c->cub_tmp);
+        delete c;
+    }
+    return rc;
+}
+
 extern "C" int hvb200cu_run_end(struct hvb200_plan *plan, double out_hilo[2])
 {
     HVB200_NVTX("hvb200:reduce");
     DevPlan *dp = (DevPlan *)plan->dev;
     {
         const int b = span_begin(dp, 2);
-        if (dp->kernel_used == MODE_BP) k_reduce<<<1, 1024, 0, dp->stream>>>(dp->bp_chunk_sums, (int)dp->bp_chunk_off, dp->out_hilo);
+        if (dp->kernel_used == MODE_BP && dp->bp_chunk_off > (size_t)2 * kReduceSlice) {
+            const int nsl = (int)((dp->bp_chunk_off + kReduceSlice - 1) / kReduceSlice);
+            if (dp->reduce_pairs_cap < (size_t)nsl) {
+                cudaFree(dp->reduce_pairs);
+                dp->reduce_pairs = nullptr; dp->reduce_pairs_cap = 0;
+                CUDA_TRY(cudaMalloc(&dp->reduce_pairs, (size_t)nsl * 2 * sizeof(double)));
+                dp->reduce_pairs_cap = (size_t)nsl;
+            }
+            k_reduce_slices<<<nsl, 1024, 0, dp->stream>>>(dp->bp_chunk_sums, (ull)dp->bp_chunk_off, dp->reduce_pairs);
+            k_reduce_pairs<<<1, 1024, 0, dp->stream>>>(dp->reduce_pairs, nsl, dp->out_hilo);
+        } else if (dp->kernel_used == MODE_BP) k_reduce<<<1, 1024, 0, dp->stream>>>(dp->bp_chunk_sums, (int)dp->bp_chunk_off, dp->out_hilo);
         else k_reduce<<<1, 1024, 0, dp->stream>>>(dp->cta_sums, dp->grid, dp->out_hilo);
         span_end(dp, b);
         CUDA_TRY(cudaGetLastError());
