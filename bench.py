@@ -234,7 +234,7 @@ def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
 
     import moocore_b200 as mb
-    from moocore_b200.sharding import gather_partials, shard_block, shard_range
+    from moocore_b200.sharding import gather_partials, mc_shard_start, shard_block, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; moocore_b200 has no CPU fallback")
@@ -262,8 +262,14 @@ def run_ours(args, rank, local_rank, world):
     cyclic = world > 1 and method == "DZ2019-HW"      # block-cyclic shards balance the ranks
 
     def step_resident():
-        hilo = (plan.run_blocks(method, N, rank, world, block=shard_block(N, world), seed=seed, stream=stream) if cyclic
-                else plan.run(method, N, seed, i0, i1, stream))
+        if cyclic:
+            hilo = plan.run_blocks(method, N, rank, world, block=shard_block(N, world), seed=seed, stream=stream)
+        elif world > 1 and method == "DZ2019-MC":
+            # pair-range shards of the MT19937 stream: nobody parses a prefix (sharding.mc_shard_start)
+            j0, j1 = mc_shard_start(plan, N, seed, rank, world, device=dev)
+            hilo = plan.run(method, N, seed, j0, j1, stream)
+        else:
+            hilo = plan.run(method, N, seed, i0, i1, stream)
         flat = gather_partials(hilo, device=dev)
         result["estimate"] = mb.hv_approx_finalize(d, N, flat)
         return plan.stats()

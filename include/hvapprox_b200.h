@@ -101,6 +101,38 @@ MOOCORE_API int hvb200_plan_run_blocks(hvb200_plan *plan, int method, uint_fast3
                                        double out_hilo[2]);
 MOOCORE_API int hvb200_plan_last_stats(const hvb200_plan *plan, hvb200_stats *out);
 
+/* DZ2019-MC shards that do not parse each other's part of the stream.  A sample's position in the MT19937 stream is data
+ * dependent (every rejected ziggurat draw shifts what follows, c/rng.c:71-99), so a contiguous sample range starting at
+ * i0 > 0 costs a parse of the whole prefix.  Instead rank g owns the PAIR range [pair0, pair0 + npairs) of the stream
+ * (one pair = two tempered words = one next64 of c/mt19937/mt19937.h:46-49; reached by MT19937 jump-ahead), describes
+ * it with hvb200_plan_mc_segment_scan, the ranks all-gather the descriptions (160 bytes each), and
+ * hvb200_mc_segments_resolve gives every rank the pair at which its parse starts, the normals it drops to reach a sample
+ * boundary and the samples [i0, i1) it evaluates — a partition of [0, nsamples) whose per-sample values are those of the
+ * sequential stream bit for bit.  Protocol per rank:
+ *     hvb200_mc_segment_layout(nsamples, d, world, rank, &p0, &np)   (returns 1: too short to be worth it, use [i0,i1) ranges)
+ *     hvb200_plan_mc_segment_scan(plan, seed, p0, np, &mine);  all-gather -> segs[world]
+ *     hvb200_mc_segments_resolve(segs, world, d, nsamples, starts)
+ *     hvb200_plan_set_mc_start(plan, starts[rank].pair, starts[rank].discard)
+ *     hvb200_plan_run(plan, HVB200_METHOD_MC, nsamples, seed, starts[rank].i0, starts[rank].i1, ...)
+ * The last rank's range is open-ended (npairs = UINT64_MAX): nobody depends on its description, so its scan only
+ * looks at the head. */
+typedef struct hvb200_mc_segment {
+    uint64_t pair0, npairs;
+    uint64_t merge;        /* first pair (relative to pair0) at which the parses of all 16 incoming skip states start an attempt */
+    uint64_t head[16];     /* normals emitted by attempts starting in [pair0, pair0 + merge) for incoming skip state s          */
+    uint64_t body;         /* normals emitted by attempts starting in [pair0 + merge, pair0 + npairs)                            */
+    uint64_t skip_out;     /* pairs of the next segment that this segment's last attempt consumes                                */
+} hvb200_mc_segment;
+typedef struct hvb200_mc_start { uint64_t pair, discard, i0, i1; } hvb200_mc_start;
+MOOCORE_API int hvb200_mc_segment_layout(uint_fast32_t nsamples, dimension_t nobjs, int world, int rank,
+                                         uint64_t *pair0, uint64_t *npairs);
+MOOCORE_API int hvb200_plan_mc_segment_scan(hvb200_plan *plan, uint32_t seed, uint64_t pair0, uint64_t npairs,
+                                            hvb200_mc_segment *out);
+MOOCORE_API int hvb200_mc_segments_resolve(const hvb200_mc_segment *segs, int world, dimension_t nobjs,
+                                           uint_fast32_t nsamples, hvb200_mc_start *starts);
+/* one-shot: applies to the next DZ2019-MC run / sample_values call of the plan */
+MOOCORE_API int hvb200_plan_set_mc_start(hvb200_plan *plan, uint64_t pair, uint64_t discard);
+
 /* (double)(c_d * (sum / (long double)nsamples)), c/hvapprox.c:256-257,691-692,863-864; the
  * `npairs` (hi, lo) partial sums are added in index order in long double. */
 MOOCORE_API double hvb200_finalize(dimension_t nobjs, uint_fast32_t nsamples,

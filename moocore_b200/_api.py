@@ -42,6 +42,37 @@ class Stats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class McSegment(ctypes.Structure):
+    """hvb200_mc_segment of include/hvapprox_b200.h: what a rank knows about its pair range of the MC stream."""
+
+    _fields_ = [
+        ("pair0", ctypes.c_uint64),
+        ("npairs", ctypes.c_uint64),
+        ("merge", ctypes.c_uint64),
+        ("head", ctypes.c_uint64 * 16),
+        ("body", ctypes.c_uint64),
+        ("skip_out", ctypes.c_uint64),
+    ]
+    WORDS = 21
+
+    def to_list(self) -> list:
+        return [self.pair0, self.npairs, self.merge, *self.head, self.body, self.skip_out]
+
+    @classmethod
+    def from_list(cls, v) -> "McSegment":
+        v = [int(x) for x in v]
+        return cls(v[0], v[1], v[2], (ctypes.c_uint64 * 16)(*v[3:19]), v[19], v[20])
+
+
+class McStart(ctypes.Structure):
+    """hvb200_mc_start: where a rank's parse starts, what it drops, and its sample range."""
+
+    _fields_ = [("pair", ctypes.c_uint64), ("discard", ctypes.c_uint64), ("i0", ctypes.c_uint64), ("i1", ctypes.c_uint64)]
+
+
+MC_OPEN_END = (1 << 64) - 1
+
+
 def library_path() -> str:
     # HVB200_LIBRARY: development override (A/B-testing differently tuned builds)
     return os.environ.get("HVB200_LIBRARY") or os.path.join(_HERE, _LIBNAME)
@@ -108,6 +139,14 @@ def _load() -> ctypes.CDLL:
     L.hvb200_multi_last_exchange.restype = ctypes.c_int
     L.hvb200_plan_run_blocks.restype = ctypes.c_int
     L.hvb200_plan_run_blocks.argtypes = [vp, ctypes.c_int, u64, u32, u64, u64, u64, vp, _c_double_p]
+    L.hvb200_mc_segment_layout.restype = ctypes.c_int
+    L.hvb200_mc_segment_layout.argtypes = [u64, dim_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.hvb200_plan_mc_segment_scan.restype = ctypes.c_int
+    L.hvb200_plan_mc_segment_scan.argtypes = [vp, u32, u64, u64, ctypes.POINTER(McSegment)]
+    L.hvb200_mc_segments_resolve.restype = ctypes.c_int
+    L.hvb200_mc_segments_resolve.argtypes = [ctypes.POINTER(McSegment), ctypes.c_int, dim_t, u64, ctypes.POINTER(McStart)]
+    L.hvb200_plan_set_mc_start.restype = ctypes.c_int
+    L.hvb200_plan_set_mc_start.argtypes = [vp, u64, u64]
     L.hvb200_plan_last_stats.restype = ctypes.c_int
     L.hvb200_plan_last_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     L.hvb200_finalize.restype = ctypes.c_double
@@ -499,6 +538,22 @@ class Plan:
             raise RuntimeError(f"hvb200_plan_run_blocks failed ({rc}): {_last_error()}")
         return (out[0], out[1])
 
+    def mc_segment_scan(self, seed: int, pair0: int, npairs: int) -> McSegment:
+        """Describe the pair range [pair0, pair0 + npairs) of the DZ2019-MC stream (hvb200_plan_mc_segment_scan);
+        npairs = MC_OPEN_END for the last rank's open-ended range."""
+        if self._h is None:
+            raise RuntimeError("empty plan")
+        seg = McSegment()
+        rc = _load().hvb200_plan_mc_segment_scan(self._h, seed, pair0, npairs, ctypes.byref(seg))
+        if rc != 0:
+            raise RuntimeError(f"hvb200_plan_mc_segment_scan failed ({rc}): {_last_error()}")
+        return seg
+
+    def set_mc_start(self, pair: int, discard: int) -> None:
+        """The next DZ2019-MC run of this plan starts its parse at `pair` and drops `discard` normals first."""
+        if self._h is not None and _load().hvb200_plan_set_mc_start(self._h, pair, discard) != 0:
+            raise RuntimeError(_last_error())
+
     def stats(self) -> dict:
         s = Stats()
         if self._h is not None:
@@ -555,6 +610,26 @@ def directions(method: str, nobj: int, nsamples: int, seed: int = 0, i0: int = 0
     return out
 
 
+def mc_segment_layout(nsamples: int, nobj: int, world: int, rank: int):
+    """(pair0, npairs) of rank's pair range of the DZ2019-MC stream, or None when the stream is too short for
+    pair-range shards to pay (hvb200_mc_segment_layout)."""
+    p0, n = ctypes.c_uint64(), ctypes.c_uint64()
+    rc = _load().hvb200_mc_segment_layout(nsamples, nobj, world, rank, ctypes.byref(p0), ctypes.byref(n))
+    if rc < 0:
+        raise ValueError(_last_error())
+    return None if rc == 1 else (p0.value, n.value)
+
+
+def mc_segments_resolve(segments, nobj: int, nsamples: int):
+    """Per rank (pair, discard, i0, i1) from the gathered segment descriptions (hvb200_mc_segments_resolve)."""
+    world = len(segments)
+    segs = (McSegment * world)(*segments)
+    starts = (McStart * world)()
+    if _load().hvb200_mc_segments_resolve(segs, world, nobj, nsamples, starts) != 0:
+        raise RuntimeError(f"hvb200_mc_segments_resolve failed: {_last_error()}")
+    return [(st.pair, st.discard, st.i0, st.i1) for st in starts]
+
+
 def hv_approx_range(points, ref, *, maximise=False, nsamples: int, seed: int = 0, method: str, i0: int, i1: int,
                     device: int = 0, stream: int | None = None):
     """One shard of an estimate: the (hi, lo) partial sum over samples [i0, i1) on `device`."""
@@ -570,6 +645,10 @@ def hv_approx_shard(points, ref, *, maximise=False, nsamples: int, seed: int = 0
     with Plan(points, ref, maximise, device=device, allow_extension=allow_extension) as plan:
         if method == "DZ2019-HW" and world > 1:
             return plan.run_blocks(method, nsamples, rank, world, block=shard_block(nsamples, world), seed=seed, stream=stream)
+        if method == "DZ2019-MC" and world > 1:
+            from .sharding import mc_shard_start
+            i0, i1 = mc_shard_start(plan, nsamples, seed, rank, world, device=device)
+            return plan.run(method, nsamples, seed, i0, i1, stream)
         i0, i1 = shard_range(nsamples, rank, world)
         return plan.run(method, nsamples, seed, i0, i1, stream)
 

@@ -449,8 +449,17 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
         hw_params_init(&hw, d, nsamples);
     } else if (method == HVB200_METHOD_MC && mc_on_device) {
         /* the stream is sequential: skip the normals of samples [0, i0) */
-        int rc = hvb200cu_mc_begin(plan, seed);
-        if (rc == 0) rc = hvb200cu_mc_skip(plan, i0 * (uint64_t)d);
+        int rc;
+        if (plan->mc_seek) {
+            /* a shard that owns a pair range of the stream (hvb200_plan_set_mc_start): jump there, then drop the
+               normals in front of its first whole sample */
+            plan->mc_seek = 0;
+            rc = hvb200cu_mc_begin_at(plan, seed, plan->mc_pair);
+            if (rc == 0) rc = hvb200cu_mc_skip(plan, plan->mc_discard);
+        } else {
+            rc = hvb200cu_mc_begin(plan, seed);
+            if (rc == 0) rc = hvb200cu_mc_skip(plan, i0 * (uint64_t)d);
+        }
         if (rc == 2) mc_on_device = 0;      /* a ziggurat tail loop beyond the device's skip tables: host generator */
         else if (rc) return -1;
     }
@@ -592,6 +601,67 @@ int hvb200_plan_run(hvb200_plan *plan, int method, uint_fast32_t nsamples, uint3
 {
     return run_range(plan, method, (uint64_t)nsamples, seed, i0, i1, cuda_stream, out_hilo, NULL, NULL);
 }
+/* ---- DZ2019-MC shards by pair ranges of the MT19937 stream (no rank parses another rank's part) ------------- */
+/* pairs of tempered words per emitted normal of the 256-layer ziggurat (c/rng.c:71-99): 98.8 % of the attempts take one
+   pair and emit; measured on 4e7 normals.  Only the balance of the last rank depends on it. */
+#define HVB200_MC_PAIRS_PER_NORMAL 1.02201
+int hvb200_mc_segment_layout(uint_fast32_t nsamples, dimension_t nobjs, int world, int rank, uint64_t *pair0, uint64_t *npairs)
+{
+    if (world < 1 || rank < 0 || rank >= world || !pair0 || !npairs) { hvb200_set_error("bad MC segment request (rank %d of %d)", rank, world); return -2; }
+    const long double normals = (long double)nsamples * (long double)nobjs;
+    uint64_t W = (uint64_t)(normals * (long double)HVB200_MC_PAIRS_PER_NORMAL / (long double)world);
+    /* short streams are cheaper to parse from the start than to describe */
+    if (world == 1 || W < ((uint64_t)1 << 20)) { *pair0 = 0; *npairs = 0; return 1; }
+    *pair0 = W * (uint64_t)rank;
+    *npairs = rank == world - 1 ? UINT64_MAX : W;
+    return 0;
+}
+int hvb200_plan_mc_segment_scan(hvb200_plan *plan, uint32_t seed, uint64_t pair0, uint64_t npairs, hvb200_mc_segment *out)
+{
+    if (!plan || !out) { hvb200_set_error("NULL plan or output"); return -2; }
+    tls_error[0] = 0;
+    uint64_t v[20];
+    const int rc = hvb200cu_mc_scan_segment(plan, seed, pair0, npairs, npairs != UINT64_MAX, v);
+    if (rc) return rc > 0 ? -10 - rc : -1;        /* -12: tail loop beyond the device tables, -13: parses did not merge */
+    out->pair0 = pair0; out->npairs = npairs; out->merge = v[0];
+    for (int s = 0; s < 16; s++) out->head[s] = v[1 + s];
+    out->body = v[17]; out->skip_out = v[18];
+    return 0;
+}
+int hvb200_mc_segments_resolve(const hvb200_mc_segment *segs, int world, dimension_t nobjs, uint_fast32_t nsamples,
+                               hvb200_mc_start *starts)
+{
+    if (!segs || !starts || world < 1 || nobjs < 1) { hvb200_set_error("bad arguments"); return -2; }
+    const uint64_t d = nobjs, N = (uint64_t)nsamples;
+    uint64_t s_in = 0, Q = 0;        /* skip state at the head of segment g; normals emitted before it */
+    if (segs[0].pair0 != 0) { hvb200_set_error("the first MC segment must start at pair 0"); return -2; }
+    for (int g = 0; g < world; g++) {
+        if (g + 1 < world && (segs[g].npairs == UINT64_MAX || segs[g + 1].pair0 != segs[g].pair0 + segs[g].npairs)) {
+            hvb200_set_error("MC segments %d and %d are not adjacent", g, g + 1); return -2;
+        }
+        if (s_in > 15 || segs[g].merge < 15) { hvb200_set_error("corrupt MC segment %d", g); return -2; }
+        /* the parse of segment g starts s_in pairs into it; the first normal it emits has index Q */
+        const uint64_t first = Q;
+        uint64_t i0 = (first + d - 1) / d;
+        starts[g].pair = segs[g].pair0 + s_in;
+        starts[g].discard = i0 * d - first;
+        if (i0 > N) i0 = N;
+        starts[g].i0 = i0;
+        starts[g].i1 = N;
+        if (g) starts[g - 1].i1 = i0;
+        Q = first + segs[g].head[s_in] + segs[g].body;
+        s_in = segs[g].skip_out;
+    }
+    for (int g = 0; g < world; g++) if (starts[g].i1 < starts[g].i0) starts[g].i1 = starts[g].i0;
+    return 0;
+}
+int hvb200_plan_set_mc_start(hvb200_plan *plan, uint64_t pair, uint64_t discard)
+{
+    if (!plan) { hvb200_set_error("NULL plan (no point strictly dominates ref)"); return -2; }
+    plan->mc_seek = 1; plan->mc_pair = pair; plan->mc_discard = discard;
+    return 0;
+}
+
 /* Block-cyclic shard of a DZ2019-HW estimate: blocks b = first, first + stride, ... of `block` consecutive
    directions.  The cost of a direction varies smoothly along a Hua-Wang lattice (its first angle grows with the
    index), so contiguous shards are unbalanced (8 GPUs: 85 % efficiency) while interleaved blocks are not.
@@ -1112,6 +1182,11 @@ typedef struct {
     hvb200_plan *plan;      /* kept alive until the exchange step */
     void *share;            /* host-side preparation shared by the shards (same point set on every GPU) */
     char err[512];
+    /* DZ2019-MC by pair ranges: phase 1 = create + describe the own range, phase 2 = run from the resolved start */
+    int phase;              /* 0: everything in one go, 1: plan + segment scan, 2: run */
+    uint64_t pair0, npairs;
+    hvb200_mc_segment seg;
+    hvb200_mc_start start;
 } shard_job;
 
 /* how the last multi-GPU call of this thread combined its partial sums: 0 = one device (nothing to exchange),
@@ -1123,9 +1198,23 @@ static void *shard_main(void *arg)
 {
     shard_job *j = arg;
     hvb200_plan *plan = NULL;
+    if (j->phase == 2) {
+        plan = j->plan;
+        if (j->rc || j->empty || !plan) return NULL;
+        j->rc = hvb200_plan_set_mc_start(plan, j->start.pair, j->start.discard);
+        if (j->rc == 0) j->rc = hvb200_plan_run(plan, j->method, j->nsamples, j->seed, j->start.i0, j->start.i1, NULL, j->hilo);
+        if (j->rc) snprintf(j->err, sizeof j->err, "%s", tls_error);
+        return NULL;
+    }
     j->hilo[0] = j->hilo[1] = 0.0;
     j->rc = plan_create_shared(&plan, j->data, j->npoints, j->nobjs, j->ref, j->maximise, j->device, j->share);
     if (j->rc == 0 && !plan) { j->empty = 1; return NULL; }
+    if (j->phase == 1) {
+        if (j->rc == 0) j->rc = hvb200_plan_mc_segment_scan(plan, j->seed, j->pair0, j->npairs, &j->seg);
+        if (j->rc) snprintf(j->err, sizeof j->err, "%s", tls_error);
+        j->plan = plan;
+        return NULL;
+    }
     if (j->rc == 0 && j->stride > 1 && j->method == HVB200_METHOD_HW)
         j->rc = hvb200_plan_run_blocks(plan, j->method, j->nsamples, j->seed, hvb200_shard_block(j->nsamples, j->stride), (uint64_t)j->device, (uint64_t)j->stride, NULL, j->hilo);
     else if (j->rc == 0) j->rc = hvb200_plan_run(plan, j->method, j->nsamples, j->seed, j->i0, j->i1, NULL, j->hilo);
@@ -1158,14 +1247,44 @@ double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, di
         j->i1 = (uint64_t)nsamples * (uint64_t)(g + 1) / (uint64_t)ndevices;
         j->stride = ndevices;
     }
-    if (ndevices == 1) {
-        shard_main(&jobs[0]);
-    } else {
-        int started[16] = {0};
-        for (int g = 0; g < ndevices; g++) started[g] = pthread_create(&th[g], NULL, shard_main, &jobs[g]) == 0;
-        for (int g = 0; g < ndevices; g++) {
-            if (started[g]) pthread_join(th[g], NULL);
-            else shard_main(&jobs[g]);               /* no thread: this shard runs inline, it is never dropped */
+    /* DZ2019-MC on several GPUs: every shard owns a pair range of the stream (nobody parses a prefix); two rounds of
+       threads with the host-side resolve step in between.  HVB200_MC_SHARD=prefix keeps the contiguous sample ranges. */
+    int mc_segments = 0;
+    if (method == HVB200_METHOD_MC && ndevices > 1 && !(getenv("HVB200_MC") && !strcmp(getenv("HVB200_MC"), "host")) &&
+        !(getenv("HVB200_MC_SHARD") && !strcmp(getenv("HVB200_MC_SHARD"), "prefix"))) {
+        mc_segments = 1;
+        for (int g = 0; g < ndevices; g++)
+            if (hvb200_mc_segment_layout(nsamples, nobjs, ndevices, g, &jobs[g].pair0, &jobs[g].npairs) != 0) mc_segments = 0;
+    }
+    for (int round = 0; round < (mc_segments ? 2 : 1); round++) {
+        for (int g = 0; g < ndevices; g++) jobs[g].phase = mc_segments ? round + 1 : 0;
+        if (ndevices == 1) {
+            shard_main(&jobs[0]);
+        } else {
+            int started[16] = {0};
+            for (int g = 0; g < ndevices; g++) started[g] = pthread_create(&th[g], NULL, shard_main, &jobs[g]) == 0;
+            for (int g = 0; g < ndevices; g++) {
+                if (started[g]) pthread_join(th[g], NULL);
+                else shard_main(&jobs[g]);               /* no thread: this shard runs inline, it is never dropped */
+            }
+        }
+        if (mc_segments && round == 0) {
+            int bad = 0, any_empty = 0;
+            hvb200_mc_segment segs[16];
+            hvb200_mc_start starts[16];
+            for (int g = 0; g < ndevices; g++) { bad |= jobs[g].rc != 0; any_empty |= jobs[g].empty; segs[g] = jobs[g].seg; }
+            if (any_empty) break;
+            if (!bad && hvb200_mc_segments_resolve(segs, ndevices, nobjs, nsamples, starts) == 0) {
+                for (int g = 0; g < ndevices; g++) jobs[g].start = starts[g];
+            } else {
+                /* a tail loop beyond the device tables, or parses that did not merge (both ~1e-12 per pair): fall back to
+                   contiguous sample ranges, where the run itself switches to the host generator if it has to */
+                for (int g = 0; g < ndevices; g++) {
+                    jobs[g].rc = 0; jobs[g].err[0] = 0;
+                    jobs[g].start.pair = 0; jobs[g].start.discard = jobs[g].i0 * (uint64_t)nobjs;
+                    jobs[g].start.i0 = jobs[g].i0; jobs[g].start.i1 = jobs[g].i1;
+                }
+            }
         }
     }
     double pairs[32];

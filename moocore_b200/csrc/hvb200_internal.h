@@ -36,6 +36,8 @@ struct hvb200_plan {
     void *dev;             /* struct dev_plan*                                                  */
     int want_fused_hw;     /* the run being started is a DZ2019-HW sum: the max-min kernel may generate its directions itself */
     int no_ndfilter;       /* keep dominated points (contribution approximation: they can be the second best) */
+    int mc_seek;           /* the next DZ2019-MC run starts at pair mc_pair (hvb200_plan_set_mc_start) and discards mc_discard normals */
+    uint64_t mc_pair, mc_discard;
     void *share;           /* preparation shared by the plans of one multi-GPU call (hvb200cu_share_new), or NULL */
     hvb200_stats stats;
 };
@@ -62,6 +64,8 @@ int hvb200cu_gen_hw_mapped(struct hvb200_plan *plan, const hvb200_hw_params *hw,
 int hvb200cu_gen_mc(struct hvb200_plan *plan, const double *normals_host, uint64_t count);     /* count*d normals */
 /* DZ2019-MC stream generated on the device: begin(seed), skip n normals, then per batch */
 int hvb200cu_mc_begin(struct hvb200_plan *plan, uint32_t seed);
+int hvb200cu_mc_begin_at(struct hvb200_plan *plan, uint32_t seed, uint64_t pair0);      /* the stream from pair `pair0` on */
+int hvb200cu_mc_scan_segment(struct hvb200_plan *plan, uint32_t seed, uint64_t pair0, uint64_t npairs, int want_body, uint64_t out[20]);
 int hvb200cu_mc_skip(struct hvb200_plan *plan, uint64_t nnormals);
 int hvb200cu_gen_mc_device(struct hvb200_plan *plan, uint64_t count);
 int hvb200cu_gen_rphi(struct hvb200_plan *plan, const double *u_host, uint64_t count);         /* count*(d-1) u   */

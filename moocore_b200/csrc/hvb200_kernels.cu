@@ -2931,6 +2931,30 @@ extern "C" int hvb200cu_mc_begin(struct hvb200_plan *plan, uint32_t seed)
     if (!dp->mc) dp->mc = new McGen();
     return mcgen_begin(dp, dp->mc, seed);
 }
+// the stream from pair `pair0` on (jump-ahead), for shards that own a pair range
+extern "C" int hvb200cu_mc_begin_at(struct hvb200_plan *plan, uint32_t seed, uint64_t pair0)
+{
+    DevPlan *dp = (DevPlan *)plan->dev;
+    CUDA_TRY(cudaSetDevice(dp->device));
+    if (!dp->mc) dp->mc = new McGen();
+    return mcgen_begin(dp, dp->mc, seed, pair0);
+}
+extern "C" int hvb200cu_mc_scan_segment(struct hvb200_plan *plan, uint32_t seed, uint64_t pair0, uint64_t npairs,
+                                        int want_body, uint64_t out[20])
+{
+    HVB200_NVTX("hvb200:mc_scan_segment");
+    DevPlan *dp = (DevPlan *)plan->dev;
+    CUDA_TRY(cudaSetDevice(dp->device));
+    if (!dp->mc) dp->mc = new McGen();
+    dp->stream = dp->own_stream;             // outside a run: the plan's own stream, a fresh list of timing spans
+    dp->spans.clear();
+    dp->ev_next = 0;
+    if (const int rc = mcgen_begin(dp, dp->mc, seed, pair0)) return rc;
+    ull tmp[20];
+    const int rc = mcgen_scan_segment(plan, dp, dp->mc, npairs, want_body, tmp);
+    if (rc == 0) for (int i = 0; i < 20; i++) out[i] = tmp[i];
+    return rc;
+}
 extern "C" int hvb200cu_mc_skip(struct hvb200_plan *plan, uint64_t nnormals)
 {
     DevPlan *dp = (DevPlan *)plan->dev;

@@ -254,6 +254,23 @@ __global__ void __launch_bounds__(256) k_zig_scatter(const unsigned *__restrict_
     if (j == npairs - 1) scalars[1] = (ull)epos[j] + eflag[j];         // normals available in this batch
 }
 
+// Range end of a pair-addressed segment (mcgen_count_range): the attempts partition the pairs, so exactly one real
+// attempt start j satisfies j < limit <= j + L_j.  It reports where the attempts behind the limit begin and how many
+// normals the attempts that start before the limit emit.
+__global__ void __launch_bounds__(256) k_zig_range_end(const ull *__restrict__ fscan, const unsigned *__restrict__ eflag,
+                                                       const unsigned *__restrict__ epos, const unsigned char *__restrict__ L,
+                                                       ull npairs, ull limit, ull *scalars)
+{
+    const ull j = (ull)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npairs || j >= limit) return;
+    const bool start = (j == 0) || ((fscan[j - 1] & 15ull) == 0);
+    const ull Lj = L[j] ? L[j] : 1;
+    if (start && j + Lj >= limit) {
+        scalars[0] = j + Lj;
+        scalars[1] = (ull)epos[j] + eflag[j];
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static int mcgen_reserve(DevPlan *dp, McGen *g, size_t pairs)
 {
@@ -289,7 +306,7 @@ static int mcgen_reserve(DevPlan *dp, McGen *g, size_t pairs)
     return 0;
 }
 
-static int mcgen_begin(DevPlan *dp, McGen *g, uint32_t seed)
+static int mcgen_begin(DevPlan *dp, McGen *g, uint32_t seed, ull pair0 = 0)
 {
     if (!g->tables_ready) {
         static double wi[256], fi[256];
@@ -309,6 +326,14 @@ static int mcgen_begin(DevPlan *dp, McGen *g, uint32_t seed)
     for (int i = 0; i < kMtN; i++) {
         key[i] = seed;
         seed = 1812433253u * (seed ^ (seed >> 30)) + (unsigned)i + 1u;
+    }
+    // a stream that starts at pair `pair0` (DZ2019-MC shards that own a pair range, hvb200_plan_mc_segment_scan): the
+    // state window 2*pair0 words ahead, by the jump-ahead polynomial t^(2 pair0) mod phi applied on the host
+    // (hvb200_mtjump.c: 64 squarings of a degree-19937 polynomial and one 20 560-word convolution, ~0.1 s)
+    if (pair0) {
+        static thread_local unsigned poly[kMtN], jumped[kMtN];
+        if (hvb200_mtjump_poly(2 * pair0, poly) || hvb200_mtjump_apply_host(key, poly, jumped)) return -1;
+        memcpy(key, jumped, sizeof key);
     }
     CUDA_TRY(cudaMemcpyAsync(g->state, key, sizeof key, cudaMemcpyHostToDevice, dp->stream));
     CUDA_TRY(cudaStreamSynchronize(dp->stream));          // `key` is on the stack
@@ -423,66 +448,156 @@ static int mcgen_generate(struct hvb200_plan *plan, DevPlan *dp, McGen *g, unsig
     return 0;
 }
 
+// Make `target` pairs resident at the head of g->words (generating what is missing), classify every pair and scan
+// the skip maps from s = 0 at pair 0 (the head of the buffer is always an attempt start).
+static int mcgen_fill_classify(struct hvb200_plan *plan, DevPlan *dp, McGen *g, size_t target)
+{
+    if (mcgen_reserve(dp, g, target)) return -1;
+    if (g->have_pairs < target) {
+        const size_t missing_words = 2 * (target - g->have_pairs);
+        const int nblocks = (int)((missing_words + kMtN - 1) / kMtN);
+        const int b = span_begin(dp, 1);
+        const int rc = mcgen_generate(plan, dp, g, g->words + 2 * g->have_pairs, nblocks);
+        span_end(dp, b);
+        if (rc) return -1;
+        g->have_pairs += (size_t)nblocks * kMtN / 2;
+    }
+    const ull P = g->have_pairs;
+    const unsigned grid = (unsigned)((P + 255) / 256);
+    const int b = span_begin(dp, 1);
+    CUDA_TRY(cudaMemsetAsync(g->scalars, 0, 4 * sizeof(ull), dp->stream));
+    k_zig_classify<<<grid, 256, 0, dp->stream>>>(g->words, P, g->L, g->emit, g->val, g->ftab, g->scalars);
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(g->cub_tmp, g->cub_tmp_bytes, g->ftab, g->fscan, SkipCompose(), (int)P, dp->stream));
+    k_zig_flags<<<grid, 256, 0, dp->stream>>>(g->fscan, g->emit, P, g->eflag, g->scalars);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g->cub_tmp, g->cub_tmp_bytes, g->eflag, g->epos, (int)P, dp->stream));
+    span_end(dp, b);
+    CUDA_TRY(cudaGetLastError());
+    plan->stats.dirgen_launches += 2;
+    return 0;
+}
+// Drop the first `next` pairs of the buffer (they are consumed); the rest moves to the head.
+static int mcgen_consume(DevPlan *dp, McGen *g, ull next)
+{
+    const ull P = g->have_pairs;
+    const size_t left = (size_t)(P - next);
+    if (left && next) {
+        // ranges may overlap when more than half of the buffer is left: go through a bounce copy
+        if (next >= left) {
+            CUDA_TRY(cudaMemcpyAsync(g->words, g->words + 2 * next, 2 * left * sizeof(unsigned), cudaMemcpyDeviceToDevice, dp->stream));
+        } else {
+            unsigned *tmp = nullptr;
+            CUDA_TRY(cudaMalloc(&tmp, 2 * left * sizeof(unsigned)));
+            CUDA_TRY(cudaMemcpyAsync(tmp, g->words + 2 * next, 2 * left * sizeof(unsigned), cudaMemcpyDeviceToDevice, dp->stream));
+            CUDA_TRY(cudaMemcpyAsync(g->words, tmp, 2 * left * sizeof(unsigned), cudaMemcpyDeviceToDevice, dp->stream));
+            CUDA_TRY(cudaStreamSynchronize(dp->stream));
+            cudaFree(tmp);
+        }
+    }
+    g->have_pairs = left;
+    return 0;
+}
+static int mcgen_read_scalars(DevPlan *dp, McGen *g)
+{
+    CUDA_TRY(cudaMemcpyAsync(g->scalars_host, g->scalars, 4 * sizeof(ull), cudaMemcpyDeviceToHost, dp->stream));
+    CUDA_TRY(cudaStreamSynchronize(dp->stream));
+    if (g->scalars_host[2] || getenv("HVB200_MC_FORCE_TAIL_OVERFLOW")) {
+        hvb200_set_error("ziggurat tail loop longer than %d pairs (device limit)", kZigMaxL);
+        return 2;                       // the caller continues this run with the host generator
+    }
+    return 0;
+}
+
 // Produce the next `need` normals of the stream into `normals_dev` (nullptr = discard).
 static int mcgen_normals(struct hvb200_plan *plan, DevPlan *dp, McGen *g, ull need, double *normals_dev)
 {
     if (need == 0) return 0;
     if (need > 0x7fff0000ull) { hvb200_set_error("internal: MC batch too large"); return -1; }
-    size_t target = (size_t)(need + need / 32 + 2048);           // ~1.4 % of draws are rejected or consume extra pairs
+    size_t target = (size_t)(need + need / 32 + 2048);           // ~2.2 % of the pairs do not end up as a normal
     for (int attempt = 0; attempt < 8; attempt++) {
-        if (mcgen_reserve(dp, g, target)) return -1;
-        if (g->have_pairs < target) {
-            const size_t missing_words = 2 * (target - g->have_pairs);
-            const int nblocks = (int)((missing_words + kMtN - 1) / kMtN);
-            const int b = span_begin(dp, 1);
-            const int rc = mcgen_generate(plan, dp, g, g->words + 2 * g->have_pairs, nblocks);
-            span_end(dp, b);
-            if (rc) return -1;
-            g->have_pairs += (size_t)nblocks * kMtN / 2;
-        }
+        if (mcgen_fill_classify(plan, dp, g, target)) return -1;
         const ull P = g->have_pairs;
         const unsigned grid = (unsigned)((P + 255) / 256);
         const int b = span_begin(dp, 1);
-        CUDA_TRY(cudaMemsetAsync(g->scalars, 0, 4 * sizeof(ull), dp->stream));
-        k_zig_classify<<<grid, 256, 0, dp->stream>>>(g->words, P, g->L, g->emit, g->val, g->ftab, g->scalars);
-        CUDA_TRY(cub::DeviceScan::InclusiveScan(g->cub_tmp, g->cub_tmp_bytes, g->ftab, g->fscan, SkipCompose(), (int)P, dp->stream));
-        k_zig_flags<<<grid, 256, 0, dp->stream>>>(g->fscan, g->emit, P, g->eflag, g->scalars);
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(g->cub_tmp, g->cub_tmp_bytes, g->eflag, g->epos, (int)P, dp->stream));
         k_zig_scatter<<<grid, 256, 0, dp->stream>>>(g->eflag, g->epos, g->val, g->L, P, need, normals_dev, g->scalars);
         span_end(dp, b);
         CUDA_TRY(cudaGetLastError());
-        plan->stats.dirgen_launches += 3;
-        CUDA_TRY(cudaMemcpyAsync(g->scalars_host, g->scalars, 4 * sizeof(ull), cudaMemcpyDeviceToHost, dp->stream));
-        CUDA_TRY(cudaStreamSynchronize(dp->stream));
-        if (g->scalars_host[2] || getenv("HVB200_MC_FORCE_TAIL_OVERFLOW")) {
-            hvb200_set_error("ziggurat tail loop longer than %d pairs (device limit)", kZigMaxL);
-            return 2;                       // the caller continues this run with the host generator
-        }
+        plan->stats.dirgen_launches++;
+        if (const int rc = mcgen_read_scalars(dp, g)) return rc;
         // the last kZigMaxL pairs may hold attempts whose look-ahead leaves the batch: never end there
-        if (g->scalars_host[1] >= need && g->scalars_host[0] + 2 * kZigMaxL <= P) {
-            // keep the pairs behind the last used attempt for the next batch
-            const ull next = g->scalars_host[0];
-            const size_t left = (size_t)(P - next);
-            if (left) {
-                // ranges may overlap when more than half of the buffer is left: go through a bounce copy
-                if (2 * next >= 2 * left) {
-                    CUDA_TRY(cudaMemcpyAsync(g->words, g->words + 2 * next, 2 * left * sizeof(unsigned), cudaMemcpyDeviceToDevice, dp->stream));
-                } else {
-                    unsigned *tmp = nullptr;
-                    CUDA_TRY(cudaMalloc(&tmp, 2 * left * sizeof(unsigned)));
-                    CUDA_TRY(cudaMemcpyAsync(tmp, g->words + 2 * next, 2 * left * sizeof(unsigned), cudaMemcpyDeviceToDevice, dp->stream));
-                    CUDA_TRY(cudaMemcpyAsync(g->words, tmp, 2 * left * sizeof(unsigned), cudaMemcpyDeviceToDevice, dp->stream));
-                    CUDA_TRY(cudaStreamSynchronize(dp->stream));
-                    cudaFree(tmp);
-                }
-            }
-            g->have_pairs = left;
-            return 0;
-        }
+        if (g->scalars_host[1] >= need && g->scalars_host[0] + 2 * kZigMaxL <= P)
+            return mcgen_consume(dp, g, g->scalars_host[0]);     // keep the pairs behind the last used attempt
         target += target / 16 + 4096;       // not enough accepted draws: extend the batch and redo
     }
     hvb200_set_error("internal: MC generator could not produce %llu normals", need);
     return -1;
+}
+
+// ---- pair-addressed segments (DZ2019-MC shards that do not parse the stream prefix) ---------------------------------
+// A sample's position in the MT19937 stream is data dependent (c/rng.c:71-99: every rejected draw shifts what follows),
+// so a shard that starts at sample i0 > 0 had to parse the whole prefix.  Instead every rank owns a PAIR range
+// [pair0, pair0 + npairs) of the stream, reached by jump-ahead, and the ranks exchange what the parse of a range needs
+// from its predecessors: the skip state s_in (how many pairs at the head of the range still belong to an attempt that
+// started before it) and the number of normals emitted before it.  The parses for the 16 possible s_in coincide from the
+// first pair at which all of them start an attempt (a few tens of pairs into the range: 98 % of the attempts consume one
+// pair), so a range is described by
+//     merge        the first such pair (relative to pair0),
+//     head[s]      the normals emitted by the attempts that start in [s, merge) when s_in = s        (host walk over the
+//                  device's own classification of the head, so that both passes take the same accept/reject decisions),
+//     body         the normals emitted by the attempts that start in [merge, npairs)                  (one device pass),
+//     skip_out     the pairs of the NEXT range that the last attempt of this one consumes.
+// mcgen_scan_segment computes them; hvb200_mc_segments_resolve (host C) turns the gathered descriptions into each
+// rank's first pair, the normals it discards to reach a sample boundary, and its sample range.
+static constexpr int kMcHead = 4096;
+static int mcgen_scan_segment(struct hvb200_plan *plan, DevPlan *dp, McGen *g, ull npairs, int want_body, ull out[20])
+{
+    // out: [0] merge, [1..16] head[s], [17] body, [18] skip_out, [19] reserved
+    if (npairs != ~0ull && npairs < 4 * (ull)kMcHead) { hvb200_set_error("MC segment too short (%llu pairs)", npairs); return -1; }
+    const size_t batch = (size_t)1 << 26;
+    size_t target = 2 * (size_t)kMcHead;
+    if (mcgen_fill_classify(plan, dp, g, target)) return -1;
+    static thread_local unsigned char hL[kMcHead], hE[kMcHead];
+    CUDA_TRY(cudaMemcpyAsync(hL, g->L, kMcHead, cudaMemcpyDeviceToHost, dp->stream));
+    CUDA_TRY(cudaMemcpyAsync(hE, g->emit, kMcHead, cudaMemcpyDeviceToHost, dp->stream));
+    CUDA_TRY(cudaStreamSynchronize(dp->stream));
+    int pos[16];
+    ull cnt[16];
+    for (int s = 0; s < 16; s++) { pos[s] = s; cnt[s] = 0; }
+    for (;;) {
+        int lo = 0, hi = 0;
+        for (int s = 1; s < 16; s++) { if (pos[s] < pos[lo]) lo = s; if (pos[s] > pos[hi]) hi = s; }
+        if (pos[lo] == pos[hi]) break;
+        const int p = pos[lo];
+        if (p >= kMcHead - kZigMaxL || hL[p] == 0) { hvb200_set_error("MC segment: the 16 parses did not merge within %d pairs", kMcHead); return 3; }
+        if (hE[p] == 2) { hvb200_set_error("ziggurat tail loop longer than %d pairs (device limit)", kZigMaxL); return 2; }
+        // every parse standing at p takes the same step
+        for (int s = 0; s < 16; s++) if (pos[s] == p) { pos[s] = p + hL[p]; cnt[s] += hE[p] == 1; }
+    }
+    const ull merge = (ull)pos[0];
+    out[0] = merge;
+    for (int s = 0; s < 16; s++) out[1 + s] = cnt[s];
+    out[17] = out[18] = out[19] = 0;
+    if (npairs == ~0ull || !want_body) return 0;
+    // body: attempts starting in [merge, npairs), batch by batch; each batch begins at an attempt start
+    if (mcgen_consume(dp, g, merge)) return -1;
+    ull remaining = npairs - merge, body = 0;
+    for (;;) {
+        target = (size_t)std::min<ull>(batch, remaining + 64);
+        if (mcgen_fill_classify(plan, dp, g, target)) return -1;
+        const ull P = g->have_pairs;
+        const ull limit = remaining + 2 * kZigMaxL <= P ? remaining : P - 2 * kZigMaxL;
+        const int b = span_begin(dp, 1);
+        k_zig_range_end<<<(unsigned)((P + 255) / 256), 256, 0, dp->stream>>>(g->fscan, g->eflag, g->epos, g->L, P, limit, g->scalars);
+        span_end(dp, b);
+        CUDA_TRY(cudaGetLastError());
+        plan->stats.dirgen_launches++;
+        if (const int rc = mcgen_read_scalars(dp, g)) return rc;
+        const ull next = g->scalars_host[0];
+        if (next < limit || next > limit + kZigMaxL) { hvb200_set_error("internal: MC segment scan lost its range end"); return -1; }
+        body += g->scalars_host[1];
+        if (next >= remaining) { out[17] = body; out[18] = next - remaining; return 0; }
+        if (mcgen_consume(dp, g, next)) return -1;
+        remaining -= next;
+    }
 }
 
 static void mcgen_free(McGen *g)

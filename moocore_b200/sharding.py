@@ -43,6 +43,53 @@ def shard_blocks(nsamples: int, rank: int, world: int, block: int = SHARD_BLOCK)
     return [(lo, min(lo + block, nsamples)) for lo in range(rank * block, nsamples, world * block)]
 
 
+def mc_shard_start(plan, nsamples: int, seed: int, rank: int, world: int, group=None, device=None):
+    """Sample range [i0, i1) of `rank` for a DZ2019-MC estimate, with the plan primed to start its parse there.
+
+    The MT19937/ziggurat stream is sequential (c/rng.c:71-99), so a contiguous sample range starting at i0 > 0 costs a
+    parse of the whole prefix (rank 7 of 8 parsed 7/8 of the stream).  Here every rank describes its own PAIR range of
+    the stream (Plan.mc_segment_scan: one pass over 1/world of it), the descriptions (21 words) are all-gathered, and
+    every rank resolves the same partition of [0, nsamples) from them (mc_segments_resolve); per-sample values are the
+    sequential stream's bit for bit.  Short streams, HVB200_MC=host and HVB200_MC_SHARD=prefix keep shard_range."""
+    import os
+
+    from . import _api
+
+    lay = None
+    if not plan.empty and os.environ.get("HVB200_MC") != "host" and os.environ.get("HVB200_MC_SHARD") != "prefix":
+        lay = _api.mc_segment_layout(nsamples, plan.nobj, world, rank)
+    if lay is None:
+        return shard_range(nsamples, rank, world)
+    seg = plan.mc_segment_scan(seed, lay[0], lay[1])
+    words = gather_words(seg.to_list(), group=group, device=device)
+    segs = [_api.McSegment.from_list(words[g * _api.McSegment.WORDS:(g + 1) * _api.McSegment.WORDS]) for g in range(world)]
+    pair, discard, i0, i1 = _api.mc_segments_resolve(segs, plan.nobj, nsamples)[rank]
+    plan.set_mc_start(pair, discard)
+    return i0, i1
+
+
+def gather_words(words: Sequence[int], group=None, device=None):
+    """All-gather a short list of unsigned 64-bit words per rank (as int64 bit patterns); flat list, rank-major."""
+    import torch
+    import torch.distributed as dist
+
+    def wrap(v):
+        v = int(v)
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return [int(w) for w in words]
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) != "nccl":
+        device = None                            # gloo (CPU tests): host tensors
+    elif isinstance(device, int):
+        device = torch.device("cuda", device)
+    send = torch.tensor([wrap(w) for w in words], dtype=torch.int64, device=device)
+    recv = torch.empty(len(words) * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return [v + (1 << 64) if v < 0 else v for v in recv.cpu().tolist()]
+
+
 _gather_cache = {}
 
 
