@@ -18,13 +18,16 @@
 //   phase B   lane = direction.  Brute-force DPX screen of the block bounds (n/32 virtual points):
 //             bitmask of the blocks that may hold a point above b0; 32x32 bit transposes (warp
 //             shuffles) turn it into one word per (block, 32 directions) in shared memory.
-//   phase C   warp = block, lane = point.  The block's keys sit in registers; the warp walks the set
-//             bits of the block's direction words, tests its 32 points against that direction's
-//             thresholds (W VIADDMNMX + one vote) and appends {direction, block, candidate mask} to the
-//             CTA's hit list (global memory, L2 resident).
-//   phase D   lane = hit entry.  Exact FP64 evaluation of its candidate points (the reference's
-//             products and comparisons), folded into the direction's max with a shared-memory
-//             atomicMax on the bit pattern (max is exact and order-free, values are >= 0).
+//   phase C   lane = point.  One thread per block first turns the block's direction words into "quads" — four
+//             surviving directions of the block per entry, padded with a nothing-passes row — in ONE list per CTA
+//             (global memory, L2 resident; its slots come from a shared counter).  The eight warps then take equal
+//             shares of that list whatever blocks the quads belong to: a warp keeps the keys of the current block in
+//             registers (reloaded when the block changes), tests its 32 points against the four directions'
+//             thresholds (W VIADDMNMX + one vote each) and every candidate lane appends {direction, point} to
+//             the warp's part of the CTA's hit list.
+//   phase D   lane = candidate.  Exact FP64 evaluation (the reference's products and comparisons), folded
+//             into the direction's max with a shared-memory atomicMax on the bit pattern (max is exact and
+//             order-free, values are >= 0).
 //   Large point sets are processed in segments of blocks; the thresholds are refreshed from the
 //   running max between segments.
 //
@@ -65,7 +68,9 @@ struct BpArgs {
     unsigned *chunk_counter;  // dynamic chunk hand-out (zeroed before the launch)
     double *values;
     ull *slow_counter;
-    uint2 *hits;              // [grid][kBpHitCap] hit lists
+    uint2 *hits;              // [grid][kBpHitCap] hit lists: {direction of the chunk, point} per candidate
+    uint4 *quads;             // [grid][seg_blocks * CH / 4] the CTA's list of surviving (direction, block) pairs, four
+                              // directions of one block per entry (L2 resident)
     double qscale[HVB200_MAXD], qlos[HVB200_MAXD];
     // GEN = true (DZ2019-HW sums): the CTA generates the directions of its chunk itself (hw_direction) into a private
     // scratch block [2D][CH] (objective-major: coalesced for the lane = direction phases), which stays in L2 — there is
@@ -83,7 +88,7 @@ struct BpArgs {
 
 // shared-memory carve-up, used by the kernel and by the host to size the launch.
 // Thresholds for phase C are stored as planes of 16-byte words [plane][CH + 1] (row CH = "nothing
-// passes", the padding entry of the pair lists) plus one tail plane of 1, 2 or 4 words per row.
+// passes", the padding entry of the pair lists); the last plane holds the 1, 2 or 3 tail words of a row.
 struct BpSmem {
     size_t thr, tail, bnd, mask, best, piv, list, bar, red, total;
     int mask_stride, Q, TW;
@@ -96,14 +101,14 @@ __host__ __device__ inline BpSmem bp_smem_layout(int D, int R, int seg_blocks, i
     const int rem = W - 4 * s.Q;
     s.TW = rem == 3 ? 4 : rem;
     size_t o = 0;
-    s.thr = o;  o += (size_t)s.Q * (CH + 1) * 16;
-    s.tail = o; o += ((size_t)(CH + 1) * s.TW * 4 + 15) & ~(size_t)15;
+    s.thr = o;  o += (size_t)(s.Q + (s.TW ? 1 : 0)) * (CH + 1) * 16;      // the tail words sit in plane Q (16-byte rows
+    s.tail = o;                                                            // like the others: one address per direction)
     s.bnd = o;  o += (size_t)(seg_blocks / 2) * D * 4;
     s.mask_stride = seg_blocks + 1;
     s.mask = o; o += ((size_t)DW * s.mask_stride * 4 + 15) & ~(size_t)15;
     s.best = o; o += (size_t)CH * 8;
     s.piv = o;  o += ((size_t)n_piv * D * 4 + 15) & ~(size_t)15;
-    s.list = o; o += (size_t)(kBpThreads / 32) * (CH + 8) * 2;
+    s.list = o; o += (size_t)(kBpThreads / 32) * 32 * 16;         // per warp: 32 staged quads of the CTA's pair list
     s.bar = o;  o += 64;             // mbarrier, counters, per-warp hit counts
     s.red = o;  o += 8 * 8;
     s.total = o;
@@ -135,6 +140,34 @@ __device__ __forceinline__ unsigned bp_transpose32(unsigned x, int lane)
         x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
     }
     return x;
+}
+
+// shared-memory loads by 32-bit shared-window address: phase C's inner loop addresses four threshold rows per
+// iteration, and generic pointers cost it a window-base computation per load
+__device__ __forceinline__ uint4 bp_lds128(unsigned addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+// (the staged quads are rewritten between batches: this one orders itself against the surrounding stores)
+__device__ __forceinline__ uint4 bp_lds128_ordered(unsigned addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 bp_lds64(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned bp_lds32(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
 // 3-input FP32 min (FMNMX3, sm_100+): NaN operands are ignored like fminf
@@ -182,13 +215,13 @@ template <int D, int R, bool GEN>
 __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_maxmin_bp(const __grid_constant__ BpArgs a)
 {
     constexpr int G = kBpG, W = (D + 1) / 2, CH = kBpThreads * R, DW = CH / 32;
-    constexpr int Q = W / 4, REM = W - 4 * Q, TW = REM == 3 ? 4 : REM, CHP = CH + 1, LCAP = CH + 8;
+    constexpr int Q = W / 4, REM = W - 4 * Q, TW = REM == 3 ? 4 : REM, CHP = CH + 1;
     static_assert((G * D) % 4 == 0, "group of block pairs must be whole 16-byte words");
     static_assert(CH <= (1 << (32 - kBpPtBits)), "direction index must fit the candidate entry");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const BpSmem L = bp_smem_layout(D, R, a.seg_blocks, a.n_piv);
     uint4 *thr4 = reinterpret_cast<uint4 *>(smem_raw + L.thr);               // [Q][CHP]
-    unsigned *thrt = reinterpret_cast<unsigned *>(smem_raw + L.tail);        // [CHP][TW]
+    uint4 *thrt = thr4 + Q * CHP;                                            // [CHP] tail words of a row (TW of them used)
     unsigned *bnd = reinterpret_cast<unsigned *>(smem_raw + L.bnd);          // [seg_blocks/2][D]
     unsigned *maskT = reinterpret_cast<unsigned *>(smem_raw + L.mask);       // [DW][mask_stride]
     long long *bestbits = reinterpret_cast<long long *>(smem_raw + L.best);  // [CH]
@@ -200,8 +233,12 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
     const int mstride = L.mask_stride;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned short *slist = reinterpret_cast<unsigned short *>(smem_raw + L.list) + warp * LCAP;   // this warp's pair list
-    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); ctr[1] = kBpThreads / 32; }
+    uint4 *sq = reinterpret_cast<uint4 *>(smem_raw + L.list) + warp * 32;                          // this warp's staged quads
+    // the CTA's pair list: per quad four 16-bit threshold-row offsets, and the quad's block
+    const size_t qcap = (size_t)a.seg_blocks * (CH / 4);
+    unsigned short *qoff = reinterpret_cast<unsigned short *>(a.quads + (size_t)blockIdx.x * qcap);
+    unsigned *qblk = reinterpret_cast<unsigned *>(qoff + qcap * 4);
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); ctr[1] = 0; }
     // every warp appends to its own eighth of the CTA's hit list: the count is a warp-uniform register, no atomics
     constexpr unsigned WCAP = kBpHitCap / (kBpThreads / 32);
     uint2 *hits = a.hits + (size_t)blockIdx.x * kBpHitCap;
@@ -211,7 +248,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
         // row CH of the threshold planes: the key -(S+1) in every half-word -> no point passes
         const unsigned v = ((unsigned)(-(kKeyScale + 1)) & 0xffffu) * 0x10001u;
         if (tid < Q) thr4[tid * CHP + CH] = make_uint4(v, v, v, v);
-        if (tid < TW) thrt[CH * TW + tid] = v;
+        if (TW && tid == 0) thrt[CH] = make_uint4(v, v, v, v);
     }
     __syncthreads();
     unsigned phase = 0;                                            // parity of the bounds barrier
@@ -338,9 +375,9 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                     }
 #pragma unroll
                     for (int q = 0; q < Q; q++) thr4[q * CHP + dl] = make_uint4(tw[4 * q], tw[4 * q + 1], tw[4 * q + 2], tw[4 * q + 3]);
-                    if constexpr (TW == 1) thrt[dl] = tw[4 * Q];
-                    if constexpr (TW == 2) *reinterpret_cast<uint2 *>(thrt + 2 * dl) = make_uint2(tw[4 * Q], tw[4 * Q + 1]);
-                    if constexpr (TW == 4) *reinterpret_cast<uint4 *>(thrt + 4 * dl) = make_uint4(tw[4 * Q], tw[4 * Q + 1], tw[4 * Q + 2], tw[4 * Q + 3]);
+                    if constexpr (TW == 1) *reinterpret_cast<unsigned *>(thrt + dl) = tw[4 * Q];
+                    if constexpr (TW == 2) *reinterpret_cast<uint2 *>(thrt + dl) = make_uint2(tw[4 * Q], tw[4 * Q + 1]);
+                    if constexpr (TW == 4) thrt[dl] = make_uint4(tw[4 * Q], tw[4 * Q + 1], tw[4 * Q + 2], tw[4 * Q + 3]);
 #pragma unroll
                     for (int k = 0; k < D; k++) negT[r][k] *= 0x10001u;
                 } else {
@@ -410,119 +447,160 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                 tma_load_1d(bnd, a.bpair + (size_t)((seg0 + a.seg_blocks) / 2) * D, bytes, bar);
             }
 
-            // ---- phase C: warp = block, lane = point
+            // ---- phase C: the CTA's list of quads, then lane = point
             const int seg_real = min(seg_nb, a.nb - seg0);                         // real (non-padding) blocks
-            // blocks are handed out dynamically (the first one per warp is fixed): their pair counts differ a lot
-            int b = warp;
-            unsigned hcount = 0;                                                   // entries in this warp's hit list
+            // lane = (block, direction word): DW lanes share a block.  A segmented warp scan of the words' bit counts gives
+            // every lane the position of its first direction in the block's run of quads; the slots of the run come from
+            // the CTA's counter.  No lane expands more than one 32-bit word, so a crowded block costs what a sparse one does.
+            {
+                constexpr int BPS = 32 / DW;                                       // blocks per warp step
+                const int sub = lane / DW, wl = lane % DW;
 #pragma unroll 1
-            while (b < seg_real) {
-                int b_next = 0;
-                if (lane == 0) b_next = (int)atomicAdd(ctr + 1, 1u);
-                const unsigned myw = (lane < DW) ? maskT[lane * mstride + b] : 0u;
-                // flat list of the block's surviving directions: lane = direction word, warp scan of the bit counts
-                const int cnt = __popc(myw);
-                int incl = cnt;
+                for (int b0 = warp * BPS; b0 < seg_real; b0 += (kBpThreads / 32) * BPS) {
+                    const int b = b0 + sub;
+                    unsigned m = b < seg_real ? maskT[wl * mstride + b] : 0u;
+                    const int cnt = __popc(m);
+                    int incl = cnt;
 #pragma unroll
-                for (int off = 1; off < DW; off <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, off);
-                    if (lane >= off) incl += t;
+                    for (int off = 1; off < DW; off <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, off, DW);
+                        if (wl >= off) incl += t;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, DW - 1, DW);
+                    if (__ballot_sync(0xffffffffu, total != 0) == 0u) continue;
+                    const unsigned nq = (unsigned)(total + 3) >> 2;
+                    unsigned qbase = 0;
+                    if (wl == 0 && total) qbase = atomicAdd(ctr + 1, nq);
+                    qbase = __shfl_sync(0xffffffffu, qbase, 0, DW);
+                    unsigned short *run = qoff + (size_t)qbase * 4;                // 16-bit byte offsets of threshold rows
+                    unsigned short *dst = run + (incl - cnt);
+                    while (m) {
+                        const unsigned off = (unsigned)(wl * 32 + __ffs((int)m) - 1) * 16u;
+                        m &= m - 1;
+                        *dst++ = (unsigned short)off;
+                    }
+                    if (wl == DW - 1)
+                        for (int p = total; p < (int)(nq * 4); p++) run[p] = (unsigned short)(CH * 16);      // row CH: nothing passes
+                    for (unsigned i = wl; i < nq; i += DW) qblk[qbase + i] = (unsigned)b;
                 }
-                const int total = __shfl_sync(0xffffffffu, incl, DW - 1);
-                const unsigned blk = (unsigned)(seg0 + b);
-                b = __shfl_sync(0xffffffffu, b_next, 0);
-                if (total == 0) continue;
-                unsigned kw[W];
-#pragma unroll
-                for (int j = 0; j < W; j++) kw[j] = __ldg(a.pkeys + ((size_t)blk * W + j) * 32 + lane);
-                {
-                    unsigned w = myw;
-                    int o = incl - cnt;
-                    while (w) {
-                        const int bit = __ffs((int)w) - 1;
-                        w &= w - 1;
-                        slist[o++] = (unsigned short)((lane * 32 + bit) * 16);      // byte offset of the direction's threshold row
+            }
+            __syncthreads();
+            unsigned hcount = 0;                                                   // entries in this warp's hit list
+            {
+                const unsigned nquads = ctr[1];
+                const unsigned qlo = (unsigned)((ull)nquads * (unsigned)warp / (kBpThreads / 32));
+                const unsigned qhi = (unsigned)((ull)nquads * (unsigned)(warp + 1) / (kBpThreads / 32));
+                unsigned tb_s = (unsigned)__cvta_generic_to_shared(thr4);
+                unsigned sq_s = (unsigned)__cvta_generic_to_shared(sq);
+                asm volatile("" : "+r"(tb_s), "+r"(sq_s));          // computed once: not rematerialised inside the loop
+                const unsigned lt_mask = (1u << lane) - 1u;
+                const uint2 *qo2 = reinterpret_cast<const uint2 *>(qoff);
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+                if (qlo + lane < qhi) { const uint2 o = qo2[qlo + lane]; nxt = make_uint4(o.x, o.y, qblk[qlo + lane], 0u); }
+#pragma unroll 1
+                for (unsigned base = qlo; base < qhi; base += 32) {
+                    const int nq = (int)min(32u, qhi - base);
+                    sq[lane] = nxt;
+                    __syncwarp();
+                    if (base + 32 + lane < qhi) {                                   // next batch, under this one's work
+                        const uint2 o = qo2[base + 32 + lane];
+                        nxt = make_uint4(o.x, o.y, qblk[base + 32 + lane], 0u);
                     }
-                    if (lane < 4) slist[total + lane] = (unsigned short)(CH * 16);      // padding: the "nothing passes" row
-                }
-                __syncwarp();
-#pragma unroll 2
-                for (int j = 0; j < total; j += 4) {
-                    const uint2 e = *reinterpret_cast<const uint2 *>(slist + j);
-                    const unsigned off[4] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16};
-                    unsigned m16[4] = {0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu};
-                    const unsigned char *tb = reinterpret_cast<const unsigned char *>(thr4);
-                    const unsigned char *tt = reinterpret_cast<const unsigned char *>(thrt);
+                    int j = 0;
+                    uint4 e = bp_lds128_ordered(sq_s);
+#pragma unroll 1
+                    while (j < nq) {
+                        // a run of quads of one block: its keys stay in registers
+                        const unsigned cur = e.z;
+                        unsigned kw[W];
+                        {
+                            const unsigned *kp = a.pkeys + (size_t)(seg0 + (int)cur) * (W * 32) + lane;
 #pragma unroll
-                    for (int q = 0; q < Q; q++) {
-                        uint4 t[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) t[u] = *reinterpret_cast<const uint4 *>(tb + q * CHP * 16 + off[u]);
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            m16[u] = __viaddmin_s16x2(kw[4 * q + 0], t[u].x, m16[u]);
-                            m16[u] = __viaddmin_s16x2(kw[4 * q + 1], t[u].y, m16[u]);
-                            m16[u] = __viaddmin_s16x2(kw[4 * q + 2], t[u].z, m16[u]);
-                            m16[u] = __viaddmin_s16x2(kw[4 * q + 3], t[u].w, m16[u]);
+                            for (int i = 0; i < W; i++) kw[i] = __ldg(kp + i * 32);
                         }
-                    }
-                    if constexpr (TW == 1) {
+                        const unsigned pt = (unsigned)(seg0 + (int)cur) * kBpBlock + lane;
+#pragma unroll 1
+                        do {
+                            j++;
+                            const uint4 e_next = bp_lds128_ordered(sq_s + (unsigned)j * 16u);      // one quad ahead (entry 32 is never used)
+                            const unsigned off[4] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16};
+                            unsigned ad[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) m16[u] = __viaddmin_s16x2(kw[4 * Q], *reinterpret_cast<const unsigned *>(tt + (off[u] >> 2)), m16[u]);
-                    }
-                    if constexpr (TW == 2) {
+                            for (int u = 0; u < 4; u++) ad[u] = tb_s + off[u];
+                            unsigned m16[4] = {0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu};
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const uint2 t = *reinterpret_cast<const uint2 *>(tt + (off[u] >> 1));
-                            m16[u] = __viaddmin_s16x2(kw[4 * Q], t.x, m16[u]);
-                            m16[u] = __viaddmin_s16x2(kw[4 * Q + 1], t.y, m16[u]);
-                        }
-                    }
-                    if constexpr (TW == 4) {
+                            for (int q = 0; q < Q; q++) {
+                                uint4 t[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const uint4 t = *reinterpret_cast<const uint4 *>(tt + off[u]);
-                            m16[u] = __viaddmin_s16x2(kw[4 * Q], t.x, m16[u]);
-                            m16[u] = __viaddmin_s16x2(kw[4 * Q + 1], t.y, m16[u]);
-                            m16[u] = __viaddmin_s16x2(kw[4 * Q + 2], t.z, m16[u]);
-                        }
-                    }
-                    // sign bits clear in both halves <=> candidate.  About a quarter of the pairs hold one: lanes 0..3
-                    // publish one {direction, block, candidate mask} entry per pair with candidates
-                    const unsigned c0 = __ballot_sync(0xffffffffu, (m16[0] & 0x80008000u) == 0u);
-                    const unsigned c1 = __ballot_sync(0xffffffffu, (m16[1] & 0x80008000u) == 0u);
-                    const unsigned c2 = __ballot_sync(0xffffffffu, (m16[2] & 0x80008000u) == 0u);
-                    const unsigned c3 = __ballot_sync(0xffffffffu, (m16[3] & 0x80008000u) == 0u);
-                    if (c0 | c1 | c2 | c3) {
-                        const unsigned cm = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : c3));
-                        const unsigned of = lane == 0 ? off[0] : (lane == 1 ? off[1] : (lane == 2 ? off[2] : off[3]));
-                        const bool mine = lane < 4 && cm != 0u;
-                        const unsigned nz = __ballot_sync(0xffffffffu, mine);              // bit u: pair u has candidates
-                        bool spilled = false;
-                        if (mine) {
-                            const unsigned slot = hcount + __popc(nz & ((1u << lane) - 1u));
-                            if (slot < WCAP) whits[slot] = make_uint2(((of >> 4) << kBpPtBits) | blk, cm);
-                            else spilled = true;
-                        }
-                        hcount += __popc(nz);
-                        const unsigned sp = __ballot_sync(0xffffffffu, spilled);
-                        if (sp) {
-                            // the CTA's hit list is full (never seen in practice): evaluate in place
+                                for (int u = 0; u < 4; u++) t[u] = bp_lds128(ad[u] + q * CHP * 16);
 #pragma unroll
-                            for (int u = 0; u < 4; u++)
-                                if (((sp >> u) & 1u) && (m16[u] & 0x80008000u) == 0u) {
-                                    bp_candidate_cold<D, R, GEN>(a, cdirs, off[u] >> 4, blk * kBpBlock + lane, bestbits);
-                                    slow++;
+                                for (int u = 0; u < 4; u++) {
+                                    m16[u] = __viaddmin_s16x2(kw[4 * q + 0], t[u].x, m16[u]);
+                                    m16[u] = __viaddmin_s16x2(kw[4 * q + 1], t[u].y, m16[u]);
+                                    m16[u] = __viaddmin_s16x2(kw[4 * q + 2], t[u].z, m16[u]);
+                                    m16[u] = __viaddmin_s16x2(kw[4 * q + 3], t[u].w, m16[u]);
                                 }
-                        }
+                            }
+                            if constexpr (TW == 1) {
+                                unsigned t[4];
+#pragma unroll
+                                for (int u = 0; u < 4; u++) t[u] = bp_lds32(ad[u] + Q * CHP * 16);
+#pragma unroll
+                                for (int u = 0; u < 4; u++) m16[u] = __viaddmin_s16x2(kw[4 * Q], t[u], m16[u]);
+                            }
+                            if constexpr (TW == 2) {
+                                uint2 t[4];
+#pragma unroll
+                                for (int u = 0; u < 4; u++) t[u] = bp_lds64(ad[u] + Q * CHP * 16);
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    m16[u] = __viaddmin_s16x2(kw[4 * Q], t[u].x, m16[u]);
+                                    m16[u] = __viaddmin_s16x2(kw[4 * Q + 1], t[u].y, m16[u]);
+                                }
+                            }
+                            if constexpr (TW == 4) {
+                                uint4 t[4];
+#pragma unroll
+                                for (int u = 0; u < 4; u++) t[u] = bp_lds128(ad[u] + Q * CHP * 16);
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    m16[u] = __viaddmin_s16x2(kw[4 * Q], t[u].x, m16[u]);
+                                    m16[u] = __viaddmin_s16x2(kw[4 * Q + 1], t[u].y, m16[u]);
+                                    m16[u] = __viaddmin_s16x2(kw[4 * Q + 2], t[u].z, m16[u]);
+                                }
+                            }
+                            // sign bits clear in both halves <=> candidate.  About a quarter of the pairs hold one: every
+                            // candidate lane publishes its own {direction, point} entry
+                            unsigned c[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) c[u] = __ballot_sync(0xffffffffu, (m16[u] & 0x80008000u) == 0u);
+                            if (c[0] | c[1] | c[2] | c[3]) {
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    if (c[u]) {
+                                        if ((c[u] >> lane) & 1u) {
+                                            const unsigned slot = hcount + __popc(c[u] & lt_mask);
+                                            if (slot < WCAP) whits[slot] = make_uint2(off[u] >> 4, pt);
+                                            else {
+                                                // the warp's hit list is full (never seen in practice): evaluate in place
+                                                bp_candidate_cold<D, R, GEN>(a, cdirs, off[u] >> 4, pt, bestbits);
+                                                slow++;
+                                            }
+                                        }
+                                        hcount += __popc(c[u]);
+                                    }
+                                }
+                            }
+                            e = e_next;
+                        } while (j < nq && e.z == cur);
                     }
+                    __syncwarp();                 // the staged quads are overwritten by the next batch
                 }
-                __syncwarp();                 // the list is rewritten for the warp's next block
             }
             if (lane == 0) hcnt[warp] = min(hcount, WCAP);
             __syncthreads();
 
-            // ---- phase D: lane = hit entry, exact FP64 evaluation of its candidate points
+            // ---- phase D: lane = candidate, exact FP64 evaluation
             {
                 // the eight warp lists as one flat index range: entry i lives in list w at i - first[w]
                 unsigned first[kBpThreads / 32 + 1];
@@ -535,18 +613,12 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                     for (int t = 1; t < kBpThreads / 32; t++)
                         if (i >= first[t]) { w = t; base = first[t]; }
                     const uint2 e = hits[(size_t)w * WCAP + (i - base)];
-                    const unsigned dl = e.x >> kBpPtBits, blk = e.x & ((1u << kBpPtBits) - 1u);
-                    unsigned cm = e.y;
-                    while (cm) {
-                        const int q = __ffs((int)cm) - 1;
-                        cm &= cm - 1;
-                        bp_candidate<D, R, GEN>(a, cdirs, dl, blk * kBpBlock + q, bestbits);
-                        slow++;
-                    }
+                    bp_candidate<D, R, GEN>(a, cdirs, e.x, e.y, bestbits);
+                    slow++;
                 }
             }
             __syncthreads();
-            if (tid == 0) ctr[1] = kBpThreads / 32;
+            if (tid == 0) ctr[1] = 0;
         }
 
         double acc = 0.0;

@@ -1580,6 +1580,7 @@ struct DevPlan {
     double *bp_pts = nullptr; size_t bp_pts_cap = 0;
     float *bp_piv32 = nullptr; unsigned *bp_pividx = nullptr;
     uint2 *bp_hits = nullptr; size_t bp_hits_cap = 0;    // per-CTA hit lists of phase C
+    uint4 *bp_quads = nullptr; size_t bp_quads_cap = 0;  // per-CTA lists of surviving (direction, block) quads
     double *bp_chunk_sums = nullptr; size_t bp_chunk_cap = 0, bp_chunk_off = 0;   // one partial sum per (chunk, warp) of the run
     unsigned *bp_chunk_counter = nullptr;
     double *reduce_pairs = nullptr; size_t reduce_pairs_cap = 0;        // (hi, lo) of the slices of a long run's partial sums
@@ -2126,7 +2127,7 @@ static void devplan_release(DevPlan *dp)
     cudaFree(dp->out_hilo); cudaFree(dp->counters); cudaFree(dp->staging_dev); cudaFree(dp->qdev);
     cudaFree(dp->pts_tmp); cudaFree(dp->wins); cudaFree(dp->gen_scratch); cudaFree(dp->reduce_pairs);
     bp_prep_scratch_free(&dp->prep);
-    cudaFree(dp->bp_hits); cudaFree(dp->bp_chunk_sums); cudaFree(dp->bp_chunk_counter); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
+    cudaFree(dp->bp_hits); cudaFree(dp->bp_quads); cudaFree(dp->bp_chunk_sums); cudaFree(dp->bp_chunk_counter); cudaFree(dp->bp_pts); cudaFree(dp->bp_piv32); cudaFree(dp->bp_pividx); cudaFree(dp->bp_pkeys); cudaFree(dp->bp_bpair);
     for (int i = 0; i < 2; i++) {
         if (dp->staging_host[i]) cudaFreeHost(dp->staging_host[i]);
         if (dp->staging_free[i]) cudaEventDestroy(dp->staging_free[i]);
@@ -2798,6 +2799,16 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
         CUDA_TRY(cudaMalloc(&dp->bp_hits, (size_t)dp->grid * kBpHitCap * sizeof(uint2)));
         dp->bp_hits_cap = (size_t)dp->grid * kBpHitCap;
     }
+    if (mode == MODE_BP) {
+        // worst case: every direction of a chunk survives in every block of a segment
+        const size_t need = (size_t)dp->grid * (size_t)dp->bp_seg_blocks * (size_t)(kBpThreads * bp_R_of(d) / 4);
+        if (dp->bp_quads_cap < need) {
+            cudaFree(dp->bp_quads);
+            dp->bp_quads = nullptr; dp->bp_quads_cap = 0;
+            CUDA_TRY(cudaMalloc(&dp->bp_quads, need * sizeof(uint4)));
+            dp->bp_quads_cap = need;
+        }
+    }
     if (dp->fused) {
         const size_t need = (size_t)dp->grid * 2 * d * kBpThreads * bp_R_of(d);
         if (dp->gen_scratch_cap < need) {
@@ -3084,6 +3095,7 @@ static int bp_fill_args(DevPlan *dp, BpArgs &ka, uint64_t count, ull n_chunks)
     ka.slow_counter = dp->counters + 1;
     ka.capped_counter = dp->counters;
     ka.hits = dp->bp_hits;
+    ka.quads = dp->bp_quads;
     for (int k = 0; k < HVB200_MAXD; k++) {
         ka.qscale[k] = k < d ? dp->bp_qscale[k] : 0.0;
         ka.qlos[k] = k < d ? dp->bp_qlos[k] : 0.0;

@@ -71,13 +71,20 @@ def test_layout_sized_segments_and_many_cut_points():
         # balance: the four sample ranges are within 1 % of each other
         sizes = [i1 - i0 for _, _, i0, i1 in starts]
         assert max(sizes) - min(sizes) < 0.01 * N / 4, sizes
-        seen = set()
-        for off in range(40):
+        # cuts inside an attempt (skip_out > 0: ~1.3 % of the positions) and heads whose parses merge late (an attempt of
+        # several pairs among the first 15: ~17 %) are the cases a wrong s_in or head count would break
+        interesting, plain = [], []
+        for off in range(600):
             cut = 1_000_000 + off
+            a = plan.mc_segment_scan(seed, 0, cut)
+            b = plan.mc_segment_scan(seed, cut, MC_OPEN_END)
+            (interesting if a.skip_out or b.merge > 15 else plain).append(cut)
+            if a.skip_out:
+                assert len(set(b.head)) > 1 or b.merge > 15
+        assert any(plan.mc_segment_scan(seed, 0, c).skip_out for c in interesting), "no cut inside an attempt among 600"
+        for cut in interesting[:60] + plain[:10]:
             got, starts, segs = sharded_values(plan, N, seed, [0, cut])
-            assert np.array_equal(got, want), off
-            seen.add(int(segs[0].skip_out))
-        assert len(seen) >= 2, seen
+            assert np.array_equal(got, want), (cut, starts)
 
 
 def test_segment_scan_errors():

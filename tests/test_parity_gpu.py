@@ -288,10 +288,19 @@ def test_multi_gpu_single_process_matches_single(mb):
         from moocore_b200 import _api
         assert _api._load().hvb200_multi_last_exchange() == 1       # the partial sums went through ncclAllGather
         c = mb.hv_approx(x, ref=ref, nsamples=300_000, seed=42, method="DZ2019-MC")
+        # long enough for the shards to own pair ranges of the MT19937 stream (hvb200_mc_segment_layout) ...
+        e = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=42, method="DZ2019-MC")
+        os.environ["HVB200_MC_SHARD"] = "prefix"         # ... and the same estimate from contiguous sample ranges
+        try:
+            f = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=42, method="DZ2019-MC")
+        finally:
+            del os.environ["HVB200_MC_SHARD"]
     finally:
         del os.environ["HVB200_NGPUS"]
     assert rel(a, b) < 1e-14
     assert rel(c, mb.hv_approx(x, ref=ref, nsamples=300_000, seed=42, method="DZ2019-MC")) < 1e-14
+    single = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=42, method="DZ2019-MC")
+    assert rel(e, single) < 1e-14 and rel(f, single) < 1e-14
 
 
 # ---------------------------------------------------------------------------------------------
