@@ -610,8 +610,13 @@ int hvb200_mc_segment_layout(uint_fast32_t nsamples, dimension_t nobjs, int worl
     if (world < 1 || rank < 0 || rank >= world || !pair0 || !npairs) { hvb200_set_error("bad MC segment request (rank %d of %d)", rank, world); return -2; }
     const long double normals = (long double)nsamples * (long double)nobjs;
     uint64_t W = (uint64_t)(normals * (long double)HVB200_MC_PAIRS_PER_NORMAL / (long double)world);
-    /* short streams are cheaper to parse from the start than to describe */
-    if (world == 1 || W < ((uint64_t)1 << 20)) { *pair0 = 0; *npairs = 0; return 1; }
+    /* short streams are cheaper to parse from the start than to describe: the jump-ahead polynomial costs ~10 ms of host
+       time per rank, a prefix parse 0.12 ms per million normals (cfg2, 5e6 normals on 2 GPUs: 1.3 ms from the start,
+       10.6 ms by pair ranges).  HVB200_MC_SEGMENT_MIN (pairs per rank) moves the threshold (tests). */
+    uint64_t wmin = (uint64_t)1 << 26;
+    const char *e = getenv("HVB200_MC_SEGMENT_MIN");
+    if (e && atoll(e) >= 4 * 4096) wmin = (uint64_t)atoll(e);
+    if (world == 1 || W < wmin) { *pair0 = 0; *npairs = 0; return 1; }
     *pair0 = W * (uint64_t)rank;
     *npairs = rank == world - 1 ? UINT64_MAX : W;
     return 0;

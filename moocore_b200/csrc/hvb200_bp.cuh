@@ -82,7 +82,7 @@ struct BpArgs {
     int gen_shift;
     const double *gen_tab;
     int gen_ntab;
-    double *gen_scratch;      // [grid][2D][CH]
+    double *gen_scratch;      // [grid]{[D][CH] FP64 r, [D][CH] FP32 winv rounded down} = 12 D CH bytes per CTA
     ull *capped_counter;
 };
 
@@ -282,9 +282,17 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
             tma_load_1d(bnd, a.bpair, bytes, bar);
         }
         bool valid[R];
-        const double *cdirs = GEN ? a.gen_scratch + (size_t)blockIdx.x * (2 * D * CH) : a.dirs + chunk_base * (2 * D);
+        // the CTA's scratch block: r in FP64 (the exact evaluations read it), winv = RN(1/r) only feeds the threshold keys
+        // and is kept in FP32 rounded DOWN (a lower threshold lets more candidates through, never fewer): 120 instead
+        // of 160 bytes per direction of L2 footprint
+        constexpr size_t kScratchDoubles = (size_t)D * CH + (size_t)D * CH / 2;
+        const double *cdirs = GEN ? a.gen_scratch + (size_t)blockIdx.x * kScratchDoubles : a.dirs + chunk_base * (2 * D);
+        const float *cwinv = reinterpret_cast<const float *>(a.gen_scratch + (size_t)blockIdx.x * kScratchDoubles + (size_t)D * CH);
         // component k of direction dl of this chunk: reciprocal weight r (k < D) and winv (D <= k < 2D)
-        auto dirv = [&](int dl, int k) { return GEN ? __ldcg(cdirs + (size_t)k * CH + dl) : __ldg(cdirs + (size_t)dl * (2 * D) + k); };
+        auto dirv = [&](int dl, int k) {
+            if constexpr (GEN) return k < D ? __ldcg(cdirs + (size_t)k * CH + dl) : (double)__ldcg(cwinv + (size_t)(k - D) * CH + dl);
+            else return __ldg(cdirs + (size_t)dl * (2 * D) + k);
+        };
         if constexpr (GEN) {
             // ---- generator: every thread produces its R directions of the chunk (the previous chunk's readers are
             //      behind the barrier that ended it; the other threads read these rows only in phase D, behind barriers)
@@ -293,9 +301,10 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                 const ull p = chunk_base + (ull)r * kBpThreads + tid;
                 if (p < a.count) {
                     const ull i = a.gen_i0 + (((p >> a.gen_shift) * a.gen_stride) << a.gen_shift) + (p & ((1ull << a.gen_shift) - 1ull));
-                    double *o = a.gen_scratch + (size_t)blockIdx.x * (2 * D * CH) + r * kBpThreads + tid;
+                    double *o = a.gen_scratch + (size_t)blockIdx.x * kScratchDoubles + r * kBpThreads + tid;
+                    float *ow = reinterpret_cast<float *>(a.gen_scratch + (size_t)blockIdx.x * kScratchDoubles + (size_t)D * CH) + r * kBpThreads + tid;
                     hw_direction(a.hw, i, a.gen_tab, a.gen_ntab, capped,
-                                 [&](int k, double rk, double wk) { __stcg(o + (size_t)k * CH, rk); __stcg(o + (size_t)(D + k) * CH, wk); });
+                                 [&](int k, double rk, double wk) { __stcg(o + (size_t)k * CH, rk); __stcg(ow + (size_t)k * CH, __double2float_rd(wk)); });
                 }
             }
         }
@@ -477,11 +486,11 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                     while (m) {
                         const unsigned off = (unsigned)(wl * 32 + __ffs((int)m) - 1) * 16u;
                         m &= m - 1;
-                        *dst++ = (unsigned short)off;
+                        __stcg(dst++, (unsigned short)off);             // the list lives in L2: written and read once per chunk
                     }
                     if (wl == DW - 1)
-                        for (int p = total; p < (int)(nq * 4); p++) run[p] = (unsigned short)(CH * 16);      // row CH: nothing passes
-                    for (unsigned i = wl; i < nq; i += DW) qblk[qbase + i] = (unsigned)b;
+                        for (int p = total; p < (int)(nq * 4); p++) __stcg(run + p, (unsigned short)(CH * 16));      // row CH: nothing passes
+                    for (unsigned i = wl; i < nq; i += DW) __stcg(qblk + qbase + i, (unsigned)b);
                 }
             }
             __syncthreads();
@@ -496,15 +505,15 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                 const unsigned lt_mask = (1u << lane) - 1u;
                 const uint2 *qo2 = reinterpret_cast<const uint2 *>(qoff);
                 uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-                if (qlo + lane < qhi) { const uint2 o = qo2[qlo + lane]; nxt = make_uint4(o.x, o.y, qblk[qlo + lane], 0u); }
+                if (qlo + lane < qhi) { const uint2 o = __ldcg(qo2 + qlo + lane); nxt = make_uint4(o.x, o.y, __ldcg(qblk + qlo + lane), 0u); }
 #pragma unroll 1
                 for (unsigned base = qlo; base < qhi; base += 32) {
                     const int nq = (int)min(32u, qhi - base);
                     sq[lane] = nxt;
                     __syncwarp();
                     if (base + 32 + lane < qhi) {                                   // next batch, under this one's work
-                        const uint2 o = qo2[base + 32 + lane];
-                        nxt = make_uint4(o.x, o.y, qblk[base + 32 + lane], 0u);
+                        const uint2 o = __ldcg(qo2 + base + 32 + lane);
+                        nxt = make_uint4(o.x, o.y, __ldcg(qblk + base + 32 + lane), 0u);
                     }
                     int j = 0;
                     uint4 e = bp_lds128_ordered(sq_s);

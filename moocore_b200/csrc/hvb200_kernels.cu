@@ -2810,7 +2810,8 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
         }
     }
     if (dp->fused) {
-        const size_t need = (size_t)dp->grid * 2 * d * kBpThreads * bp_R_of(d);
+        const size_t ch = (size_t)kBpThreads * bp_R_of(d);
+        const size_t need = (size_t)dp->grid * ((size_t)d * ch + (size_t)d * ch / 2);      // r FP64 + winv FP32 per direction
         if (dp->gen_scratch_cap < need) {
             cudaFree(dp->gen_scratch);
             dp->gen_scratch = nullptr; dp->gen_scratch_cap = 0;

@@ -104,6 +104,7 @@ def test_resolve_rejects_gaps_and_bad_heads():
 def test_layout_partitions_the_expected_stream():
     # short streams keep contiguous sample ranges
     assert mc_segment_layout(1000, 5, 4, 0) is None
+    assert mc_segment_layout(10**6, 5, 2, 0) is None                 # cfg2: 2.5e6 pairs per rank, below the 2^26 threshold
     assert mc_segment_layout(10**9, 50, 1, 0) is None
     N, d, world = 10**9, 50, 8
     lay = [mc_segment_layout(N, d, world, g) for g in range(world)]

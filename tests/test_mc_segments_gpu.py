@@ -56,7 +56,8 @@ def test_pair_range_shards_reproduce_the_sequential_stream(d, seed):
         assert abs(tot - (hi + lo)) <= 1e-12 * abs(hi + lo)
 
 
-def test_layout_sized_segments_and_many_cut_points():
+def test_layout_sized_segments_and_many_cut_points(monkeypatch):
+    monkeypatch.setenv("HVB200_MC_SEGMENT_MIN", str(1 << 20))       # the library's default threshold is 2^26 pairs per rank
     # the library's own layout (ranges of >= 2^20 pairs), and cuts at every offset of a 40-pair window: all 16 incoming
     # skip states that occur in the stream are exercised
     d, n, seed = 4, 30, 42

@@ -288,8 +288,12 @@ def test_multi_gpu_single_process_matches_single(mb):
         from moocore_b200 import _api
         assert _api._load().hvb200_multi_last_exchange() == 1       # the partial sums went through ncclAllGather
         c = mb.hv_approx(x, ref=ref, nsamples=300_000, seed=42, method="DZ2019-MC")
-        # long enough for the shards to own pair ranges of the MT19937 stream (hvb200_mc_segment_layout) ...
-        e = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=42, method="DZ2019-MC")
+        # the shards own pair ranges of the MT19937 stream (hvb200_mc_segment_layout; threshold lowered to this size) ...
+        os.environ["HVB200_MC_SEGMENT_MIN"] = str(1 << 20)
+        try:
+            e = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=42, method="DZ2019-MC")
+        finally:
+            del os.environ["HVB200_MC_SEGMENT_MIN"]
         os.environ["HVB200_MC_SHARD"] = "prefix"         # ... and the same estimate from contiguous sample ranges
         try:
             f = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=42, method="DZ2019-MC")
