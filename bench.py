@@ -336,6 +336,9 @@ def run_ours(args, rank, local_rank, world):
     single = None
     if d <= 31:
         barrier()
+        # the other ranks wait on the rendezvous store (a host-side wait): an NCCL barrier would park a spinning kernel on
+        # their GPUs, exactly the GPUs rank 0's threads are about to use (measured: 40 ms instead of 14 ms per cfg3 call)
+        store = dist.distributed_c10d._get_default_store() if world > 1 else None
         if rank == 0:
             os.environ["HVB200_NGPUS"] = str(world)
             try:
@@ -356,6 +359,11 @@ def run_ours(args, rank, local_rank, world):
                 single = {"value": None, "error": str(e)}
             finally:
                 os.environ.pop("HVB200_NGPUS", None)
+                if store is not None:
+                    store.set("hvb200_single_process_leg_done", "1")
+        elif store is not None:
+            import datetime
+            store.wait(["hvb200_single_process_leg_done"], datetime.timedelta(seconds=3600))
         barrier()
 
     # ---------------- roofline + cpu baseline (rank 0) ----------------
@@ -422,8 +430,10 @@ def run_ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config), "kernel": {1: "exact", 2: "screen", 3: "dpx", 4: "pruned"}.get(plan.stats()["kernel"], "?"),
                        "npoints_after_filter": npts, "parallelism": (f"block-cyclic direction blocks of {shard_block(N, world)} x{world}" if cyclic else f"direction-range x{world}"),
-                       "l2": "point set (0.8 MB) is L2/shared-memory resident by design; the per-batch direction "
-                             "buffer (2 GiB) exceeds L2, no flush needed",
+                       "l2": "no flush: the point set (8 n d bytes, 0.8 MB at cfg3) is L2-resident by design (every CTA re-reads "
+                             "its keys each chunk: that is the algorithm, not a warm-cache artefact), the directions are "
+                             "generated inside the kernel (DZ2019-HW) or streamed through a batch buffer larger than L2 (MC), "
+                             "and the kernel is issue-bound (DRAM < 0.5 % of peak in the ncu capture)",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "estimate": estimate, "estimate_e2e": est_e2e, "rel_error_vs_reference": reference_rel_error(args.config, estimate),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes + ref.nbytes + maxi.nbytes),

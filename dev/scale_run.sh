@@ -18,8 +18,8 @@ done
 # the reference's C symbol from one process, HVB200_NGPUS = 1..n (no torch), with NCCL's own log
 for cfg in $cfgs; do
   [ $cfg = cfg5 ] && continue          # the drop-in symbols stop at d = 31 like the reference
-  reps=5; [ $cfg = cfg4 ] && reps=2
-  NCCL_DEBUG=INFO NCCL_DEBUG_FILE=$out/${tag}_chost_${cfg}_nccl.%h.%p.log python dev/multi_gpu_c_host.py --config $cfg --reps $reps \
+  reps=5; ks=""; [ $cfg = cfg4 ] && { reps=2; ks="--ngpus $n"; }       # cfg4 on one GPU is 10 s per call: only the N-GPU row
+  NCCL_DEBUG=INFO NCCL_DEBUG_FILE=$out/${tag}_chost_${cfg}_nccl.%h.%p.log python dev/multi_gpu_c_host.py --config $cfg --reps $reps $ks \
       --json $out/${tag}_chost_${cfg}_n$n.json > $out/${tag}_chost_${cfg}_n$n.log 2>&1
   tail -4 $out/${tag}_chost_${cfg}_n$n.log | cut -c1-400
 done
