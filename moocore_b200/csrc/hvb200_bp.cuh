@@ -84,6 +84,7 @@ struct BpArgs {
     int gen_ntab;
     double *gen_scratch;      // [grid]{[D][CH] FP64 r, [D][CH] FP32 winv rounded down} = 12 D CH bytes per CTA
     ull *capped_counter;
+    int early_out;            // phase C may end a quad between threshold planes (d >= 24); HVB200_BP_EARLYOUT=0 switches it off
 };
 
 // shared-memory carve-up, used by the kernel and by the host to size the launch.
@@ -109,7 +110,7 @@ __host__ __device__ inline BpSmem bp_smem_layout(int D, int R, int seg_blocks, i
     s.best = o; o += (size_t)CH * 8;
     s.piv = o;  o += ((size_t)n_piv * D * 4 + 15) & ~(size_t)15;
     s.list = o; o += (size_t)(kBpThreads / 32) * 32 * 16;         // per warp: 32 staged quads of the CTA's pair list
-    s.bar = o;  o += 64;             // mbarrier, counters, per-warp hit counts
+    s.bar = o;  o += 128;            // mbarrier, counters, per-warp hit counts, per-warp early-out state
     s.red = o;  o += 8 * 8;
     s.total = o;
     return s;
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
     ull *bar = reinterpret_cast<ull *>(smem_raw + L.bar);
     unsigned *ctr = reinterpret_cast<unsigned *>(bar + 1);                   // [1] next block of phase C, [2], [3] next chunk (alternating)
     unsigned *hcnt = ctr + 4;                                                // [8] hit entries of each warp's list
+    unsigned *eost = hcnt + 8;                                               // [8] early-out state of each warp: quads seen | hits << 16 | on << 31
     double *red = reinterpret_cast<double *>(smem_raw + L.red);
     const int mstride = L.mask_stride;
 
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
     unsigned short *qoff = reinterpret_cast<unsigned short *>(a.quads + (size_t)blockIdx.x * qcap);
     unsigned *qblk = reinterpret_cast<unsigned *>(qoff + qcap * 4);
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); ctr[1] = 0; }
+    if (tid < kBpThreads / 32) eost[tid] = a.early_out ? 0x80000000u : 0u;
     // every warp appends to its own eighth of the CTA's hit list: the count is a warp-uniform register, no atomics
     constexpr unsigned WCAP = kBpHitCap / (kBpThreads / 32);
     uint2 *hits = a.hits + (size_t)blockIdx.x * kBpHitCap;
@@ -497,6 +500,9 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
             unsigned hcount = 0;                                                   // entries in this warp's hit list
             {
                 const unsigned nquads = ctr[1];
+                // early-out state of this warp (it outlives segments and chunks: parked in shared memory between phases)
+                unsigned eo_cnt = eost[warp] & 0xffffu, eo_hit = (eost[warp] >> 16) & 0x7fffu;
+                bool eo_on = (eost[warp] >> 31) != 0u;
                 const unsigned qlo = (unsigned)((ull)nquads * (unsigned)warp / (kBpThreads / 32));
                 const unsigned qhi = (unsigned)((ull)nquads * (unsigned)(warp + 1) / (kBpThreads / 32));
                 unsigned tb_s = (unsigned)__cvta_generic_to_shared(thr4);
@@ -537,18 +543,43 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
 #pragma unroll
                             for (int u = 0; u < 4; u++) ad[u] = tb_s + off[u];
                             unsigned m16[4] = {0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu};
+                            // Many objectives (d >= 24: three planes or more): a point that fails one objective stays out
+                            // (the running minimum keeps its sign), and at d = 50 a block bound prunes little — 73 % of the
+                            // blocks survive phase B at cfg5 — so nearly every quad dies long before its last plane.  From the
+                            // second plane on a vote ends the quad when none of its 128 (point, direction) pairs is alive.
+                            // Where the block bounds already prune well (fronts) the vote never fires and costs 2-4 %: every
+                            // warp watches how often it does over windows of 64 quads, drops it below one quad in four and
+                            // probes again every 16th window.
+                            constexpr bool kEarlyOut = Q >= 3;
+                            const bool try_out = kEarlyOut && eo_on;
+                            bool live = true;
 #pragma unroll
                             for (int q = 0; q < Q; q++) {
-                                uint4 t[4];
+                                if (!kEarlyOut || live) {
+                                    uint4 t[4];
 #pragma unroll
-                                for (int u = 0; u < 4; u++) t[u] = bp_lds128(ad[u] + q * CHP * 16);
+                                    for (int u = 0; u < 4; u++) t[u] = bp_lds128(ad[u] + q * CHP * 16);
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    m16[u] = __viaddmin_s16x2(kw[4 * q + 0], t[u].x, m16[u]);
-                                    m16[u] = __viaddmin_s16x2(kw[4 * q + 1], t[u].y, m16[u]);
-                                    m16[u] = __viaddmin_s16x2(kw[4 * q + 2], t[u].z, m16[u]);
-                                    m16[u] = __viaddmin_s16x2(kw[4 * q + 3], t[u].w, m16[u]);
+                                    for (int u = 0; u < 4; u++) {
+                                        m16[u] = __viaddmin_s16x2(kw[4 * q + 0], t[u].x, m16[u]);
+                                        m16[u] = __viaddmin_s16x2(kw[4 * q + 1], t[u].y, m16[u]);
+                                        m16[u] = __viaddmin_s16x2(kw[4 * q + 2], t[u].z, m16[u]);
+                                        m16[u] = __viaddmin_s16x2(kw[4 * q + 3], t[u].w, m16[u]);
+                                    }
+                                    if constexpr (kEarlyOut) {
+                                        if (try_out && q >= 1 && (q + 1 < Q || TW > 0))
+                                            live = __any_sync(0xffffffffu, ((m16[0] & 0x80008000u) == 0u) | ((m16[1] & 0x80008000u) == 0u) |
+                                                                           ((m16[2] & 0x80008000u) == 0u) | ((m16[3] & 0x80008000u) == 0u));
+                                    }
                                 }
+                            }
+                            if constexpr (kEarlyOut) {
+                                eo_hit += live ? 0u : 1u;
+                                if ((++eo_cnt & 63u) == 0u) {
+                                    eo_on = a.early_out && (eo_on ? eo_hit >= 16u : ((eo_cnt >> 6) & 15u) == 0u);
+                                    eo_hit = 0u;
+                                }
+                                if (!live) { e = e_next; continue; }
                             }
                             if constexpr (TW == 1) {
                                 unsigned t[4];
@@ -605,6 +636,7 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
                     }
                     __syncwarp();                 // the staged quads are overwritten by the next batch
                 }
+                if constexpr (Q >= 3) { if (lane == 0) eost[warp] = (eo_cnt & 0xffffu) | (eo_hit << 16) | (eo_on ? 0x80000000u : 0u); }
             }
             if (lane == 0) hcnt[warp] = min(hcount, WCAP);
             __syncthreads();

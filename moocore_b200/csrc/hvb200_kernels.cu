@@ -3097,6 +3097,10 @@ static int bp_fill_args(DevPlan *dp, BpArgs &ka, uint64_t count, ull n_chunks)
     ka.capped_counter = dp->counters;
     ka.hits = dp->bp_hits;
     ka.quads = dp->bp_quads;
+    {
+        const char *e = getenv("HVB200_BP_EARLYOUT");
+        ka.early_out = !(e && e[0] == '0');
+    }
     for (int k = 0; k < HVB200_MAXD; k++) {
         ka.qscale[k] = k < d ? dp->bp_qscale[k] : 0.0;
         ka.qlos[k] = k < d ? dp->bp_qlos[k] : 0.0;
