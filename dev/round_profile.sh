@@ -8,6 +8,7 @@ mkdir -p $out
 if [ "$2" != notest ]; then
   timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_gputests.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_gputests.log
 fi
+python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> $out/${tag}_smoke.log
 python bench.py --steps 5 --warmup 3 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_reference_arm.json 2>> $out/${tag}_bench_n1.err
 python bench.py --steps 2 --warmup 3 --kernel exact > $out/${tag}_bench_n1_exact_kernel.json 2>> $out/${tag}_bench_n1.err

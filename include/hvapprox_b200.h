@@ -130,7 +130,8 @@ MOOCORE_API int hvb200_plan_mc_segment_scan(hvb200_plan *plan, uint32_t seed, ui
                                             hvb200_mc_segment *out);
 MOOCORE_API int hvb200_mc_segments_resolve(const hvb200_mc_segment *segs, int world, dimension_t nobjs,
                                            uint_fast32_t nsamples, hvb200_mc_start *starts);
-/* one-shot: applies to the next DZ2019-MC run / sample_values call of the plan */
+/* one-shot: applies to the NEXT run / sample_values call of the plan if that is a DZ2019-MC run with the device generator,
+ * and is dropped by any other run */
 MOOCORE_API int hvb200_plan_set_mc_start(hvb200_plan *plan, uint64_t pair, uint64_t discard);
 
 /* (double)(c_d * (sum / (long double)nsamples)), c/hvapprox.c:256-257,691-692,863-864; the

@@ -418,6 +418,9 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
        (kept as an independent cross-check of the device generator) */
     const char *mc_env = getenv("HVB200_MC");
     int mc_on_device = !(mc_env && !strcmp(mc_env, "host"));
+    /* hvb200_plan_set_mc_start is one-shot: it applies to this run (if it is a device-generated DZ2019-MC run) and to no other */
+    const int mc_seek = plan->mc_seek && method == HVB200_METHOD_MC && mc_on_device;
+    plan->mc_seek = 0;
     uint64_t batch = 0;
     uint64_t want = i1 - i0 ? i1 - i0 : 1;
     if ((values_out || dirs_out) && want > (1u << 22)) want = 1u << 22;
@@ -450,10 +453,9 @@ static int run_range_ex(hvb200_plan *plan, int method, uint64_t nsamples, uint32
     } else if (method == HVB200_METHOD_MC && mc_on_device) {
         /* the stream is sequential: skip the normals of samples [0, i0) */
         int rc;
-        if (plan->mc_seek) {
+        if (mc_seek) {
             /* a shard that owns a pair range of the stream (hvb200_plan_set_mc_start): jump there, then drop the
                normals in front of its first whole sample */
-            plan->mc_seek = 0;
             rc = hvb200cu_mc_begin_at(plan, seed, plan->mc_pair);
             if (rc == 0) rc = hvb200cu_mc_skip(plan, plan->mc_discard);
         } else {

@@ -94,3 +94,19 @@ def test_segment_scan_errors():
     with mb.Plan(x, np.full(d, 1.1), False) as plan:
         with pytest.raises(RuntimeError):
             plan.mc_segment_scan(1, 0, 100)            # shorter than the head window
+
+
+def test_set_mc_start_is_one_shot():
+    d, N, seed = 3, 200_000, 5
+    x = hvcases.front("sphere", 25, d, 2)
+    with mb.Plan(x, np.full(d, 1.1), False) as plan:
+        want = plan.sample_values("DZ2019-MC", N, seed, 0, 1000)
+        segs = [plan.mc_segment_scan(seed, 0, 100_000), plan.mc_segment_scan(seed, 100_000, MC_OPEN_END)]
+        pair, discard, i0, i1 = mc_segments_resolve(segs, d, N)[1]
+        tail = plan.sample_values("DZ2019-MC", N, seed, i0, 500)
+        plan.set_mc_start(pair, discard)
+        assert np.array_equal(plan.sample_values("DZ2019-MC", N, seed, i0, 500), tail)        # used once ...
+        assert np.array_equal(plan.sample_values("DZ2019-MC", N, seed, 0, 1000), want)        # ... and gone
+        plan.set_mc_start(pair, discard)
+        plan.run("DZ2019-HW", N, 0, 0, 1000)                                                  # any other run drops it
+        assert np.array_equal(plan.sample_values("DZ2019-MC", N, seed, 0, 1000), want)
