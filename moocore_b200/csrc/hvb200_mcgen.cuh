@@ -161,9 +161,12 @@ __device__ __forceinline__ double pair_to_unit(unsigned w0, unsigned w1)
     const int a = (int)(w0 >> 5), b = (int)(w1 >> 6);
     return (a * 67108864.0 + b) / 9007199254740992.0;
 }
+// emit codes: 0 = no normal, 1 = normal, 2 = tail loop beyond the skip tables, 3 = the accept/reject comparison of a slow
+// path is a near-tie (its two sides agree to tie_eps relative: CUDA's log1p/exp and glibc's may then decide differently,
+// SURVEY H3) — 2 and 3 stop the device generator when the attempt is real, and the host generator takes over.
 __global__ void __launch_bounds__(256) k_zig_classify(const unsigned *__restrict__ words, ull npairs,
                                                       unsigned char *__restrict__ Lout, unsigned char *__restrict__ emit,
-                                                      double *__restrict__ val, ull *__restrict__ ftab, ull *scalars)
+                                                      double *__restrict__ val, ull *__restrict__ ftab, ull *scalars, double tie_eps)
 {
     // the 256-layer tables are indexed by random bits: constant memory would serialise the 32 lanes of a warp
     __shared__ double s_wi[256], s_fi[256];
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(256) k_zig_classify(const unsigned *__restrict
                 if (a + 1 >= npairs) { L = 0; em = 0; break; }          // needs pairs beyond this batch
                 const double xx = -INV_R * log1p(-pair_to_unit(words[2 * a], words[2 * a + 1]));
                 const double yy = -log1p(-pair_to_unit(words[2 * a + 2], words[2 * a + 3]));
+                if (fabs((yy + yy) - xx * xx) <= tie_eps * (xx * xx)) { L = 1 + 2 * (t + 1); em = 3; break; }
                 if (yy + yy > xx * xx) {
                     v = ((mag >> 8) & 1) ? -(R + xx) : R + xx;
                     L = 1 + 2 * (t + 1);
@@ -204,7 +208,8 @@ __global__ void __launch_bounds__(256) k_zig_classify(const unsigned *__restrict
                 const double u = pair_to_unit(words[2 * j + 2], words[2 * j + 3]);
                 const double f_hi = s_fi[layer - 1], f_lo = s_fi[layer];
                 L = 2;
-                em = ((f_hi - f_lo) * u + f_lo < exp(-0.5 * x * x)) ? 1 : 0;
+                const double lhs = (f_hi - f_lo) * u + f_lo, rhs = exp(-0.5 * x * x);
+                em = fabs(lhs - rhs) <= tie_eps * rhs ? 3 : (lhs < rhs ? 1 : 0);
             }
         }
     }
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(256) k_zig_flags(const ull *__restrict__ fscan
     if (j >= npairs) return;
     const bool start = (j == 0) || ((fscan[j - 1] & 15ull) == 0);      // skip counter before pair j, from s = 0
     // a tail loop longer than the skip tables express (1.5e-12 per pair) only matters when an attempt really starts here
-    if (start && emit[j] == 2) atomicOr(&scalars[2], 1ull);
+    if (start && emit[j] >= 2) atomicOr(&scalars[2], emit[j] == 2 ? 1ull : 2ull);
     eflag[j] = (start && emit[j] == 1) ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256) k_zig_scatter(const unsigned *__restrict__ eflag, const unsigned *__restrict__ epos,
@@ -466,7 +471,11 @@ static int mcgen_fill_classify(struct hvb200_plan *plan, DevPlan *dp, McGen *g, 
     const unsigned grid = (unsigned)((P + 255) / 256);
     const int b = span_begin(dp, 1);
     CUDA_TRY(cudaMemsetAsync(g->scalars, 0, 4 * sizeof(ull), dp->stream));
-    k_zig_classify<<<grid, 256, 0, dp->stream>>>(g->words, P, g->L, g->emit, g->val, g->ftab, g->scalars);
+    // near-tie band of the slow paths' comparisons: 8 ulp (CUDA's and glibc's log1p / exp are each within 1 ulp of the
+    // true value, the expressions around them add a few roundings); HVB200_MC_TIE_EPS widens it to exercise the fallback
+    double tie_eps = 8.0 * 2.220446049250313e-16;
+    if (const char *e = getenv("HVB200_MC_TIE_EPS")) { const double v = atof(e); if (v > 0.0) tie_eps = v; }
+    k_zig_classify<<<grid, 256, 0, dp->stream>>>(g->words, P, g->L, g->emit, g->val, g->ftab, g->scalars, tie_eps);
     CUDA_TRY(cub::DeviceScan::InclusiveScan(g->cub_tmp, g->cub_tmp_bytes, g->ftab, g->fscan, SkipCompose(), (int)P, dp->stream));
     k_zig_flags<<<grid, 256, 0, dp->stream>>>(g->fscan, g->emit, P, g->eflag, g->scalars);
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(g->cub_tmp, g->cub_tmp_bytes, g->eflag, g->epos, (int)P, dp->stream));
@@ -501,7 +510,8 @@ static int mcgen_read_scalars(DevPlan *dp, McGen *g)
     CUDA_TRY(cudaMemcpyAsync(g->scalars_host, g->scalars, 4 * sizeof(ull), cudaMemcpyDeviceToHost, dp->stream));
     CUDA_TRY(cudaStreamSynchronize(dp->stream));
     if (g->scalars_host[2] || getenv("HVB200_MC_FORCE_TAIL_OVERFLOW")) {
-        hvb200_set_error("ziggurat tail loop longer than %d pairs (device limit)", kZigMaxL);
+        if (g->scalars_host[2] & 2ull) hvb200_set_error("ziggurat accept/reject near-tie: the host generator decides");
+        else hvb200_set_error("ziggurat tail loop longer than %d pairs (device limit)", kZigMaxL);
         return 2;                       // the caller continues this run with the host generator
     }
     return 0;
@@ -568,7 +578,7 @@ static int mcgen_scan_segment(struct hvb200_plan *plan, DevPlan *dp, McGen *g, u
         if (pos[lo] == pos[hi]) break;
         const int p = pos[lo];
         if (p >= kMcHead - kZigMaxL || hL[p] == 0) { hvb200_set_error("MC segment: the 16 parses did not merge within %d pairs", kMcHead); return 3; }
-        if (hE[p] == 2) { hvb200_set_error("ziggurat tail loop longer than %d pairs (device limit)", kZigMaxL); return 2; }
+        if (hE[p] >= 2) { hvb200_set_error("ziggurat tail loop beyond the device tables or accept/reject near-tie"); return 2; }
         // every parse standing at p takes the same step
         for (int s = 0; s < 16; s++) if (pos[s] == p) { pos[s] = p + hL[p]; cnt[s] += hE[p] == 1; }
     }

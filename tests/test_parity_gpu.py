@@ -323,6 +323,27 @@ def test_mc_device_stream_bit_exact_across_batches(mb, oracle, seed):
         assert np.array_equal(got, want), (seed, i0)
 
 
+def test_mc_near_tie_decisions_go_to_the_host_generator(mb, monkeypatch):
+    """an accept/reject comparison of the ziggurat's slow paths (c/rng.c:84-97) whose two sides agree to a few ulp
+    could be decided differently by CUDA's and glibc's exp / log1p; such attempts are flagged and the run continues with the
+    host generator.  With the band widened to 1e-3 the fallback really happens — and the values do not change."""
+    x, ref, maxi = hvcases.config_inputs("cfg2")
+    with mb.Plan(x, ref, maxi) as plan:
+        dev = plan.sample_values("DZ2019-MC", 1_000_000, 9, 0, 400_000)
+        monkeypatch.setenv("HVB200_MC_TIE_EPS", "1e-3")
+        got = plan.sample_values("DZ2019-MC", 1_000_000, 9, 0, 400_000)
+        st = plan.stats()
+        assert st["h2d_bytes"] > 0, "the widened band must have sent the run to the host generator"
+        monkeypatch.delenv("HVB200_MC_TIE_EPS")
+        monkeypatch.setenv("HVB200_MC", "host")
+        host = plan.sample_values("DZ2019-MC", 1_000_000, 9, 0, 400_000)
+        assert np.array_equal(got, host)                 # the fallback IS the host stream
+        # device vs host: the same accept/reject decisions everywhere (a different one would shift every later sample);
+        # a tail value may differ in its last bits where CUDA's log1p and this box's glibc round differently
+        bad = np.flatnonzero(dev != host)
+        assert bad.size <= 40 and np.all(np.abs(dev[bad] - host[bad]) <= 1e-13 * np.abs(host[bad])), (bad.size, bad[:5])
+
+
 def test_mc_device_equals_host_generator(mb, monkeypatch):
     x, ref, maxi = hvcases.config_inputs("cfg2")
     a = mb.hv_approx(x, ref=ref, nsamples=1_300_000, seed=7, method="DZ2019-MC")
