@@ -1287,6 +1287,7 @@ double hvb200_hv_approx_multi(int method, const double *data, size_t npoints, di
                 /* a tail loop beyond the device tables, or parses that did not merge (both ~1e-12 per pair): fall back to
                    contiguous sample ranges, where the run itself switches to the host generator if it has to */
                 for (int g = 0; g < ndevices; g++) {
+                    if (!jobs[g].plan) continue;             /* no plan: that shard's failure stands and is reported */
                     jobs[g].rc = 0; jobs[g].err[0] = 0;
                     jobs[g].start.pair = 0; jobs[g].start.discard = jobs[g].i0 * (uint64_t)nobjs;
                     jobs[g].start.i0 = jobs[g].i0; jobs[g].start.i1 = jobs[g].i1;

@@ -60,9 +60,16 @@ def mc_shard_start(plan, nsamples: int, seed: int, rank: int, world: int, group=
         lay = _api.mc_segment_layout(nsamples, plan.nobj, world, rank)
     if lay is None:
         return shard_range(nsamples, rank, world)
-    seg = plan.mc_segment_scan(seed, lay[0], lay[1])
-    words = gather_words(seg.to_list(), group=group, device=device)
+    try:
+        mine = plan.mc_segment_scan(seed, lay[0], lay[1]).to_list()
+    except RuntimeError:
+        # a tail loop beyond the device tables or a near-tie decision in this rank's range (~1e-12 per pair): every rank
+        # still takes part in the exchange, sees the marker and falls back to sample ranges together
+        mine = [lay[0], lay[1], _api.MC_OPEN_END] + [0] * 18
+    words = gather_words(mine, group=group, device=device)
     segs = [_api.McSegment.from_list(words[g * _api.McSegment.WORDS:(g + 1) * _api.McSegment.WORDS]) for g in range(world)]
+    if any(sg.merge == _api.MC_OPEN_END for sg in segs):
+        return shard_range(nsamples, rank, world)
     pair, discard, i0, i1 = _api.mc_segments_resolve(segs, plan.nobj, nsamples)[rank]
     plan.set_mc_start(pair, discard)
     return i0, i1

@@ -145,3 +145,44 @@ def test_gather_words_two_ranks_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert "OK" in res.stdout
+
+
+WORKER_FALLBACK = r'''
+import os, sys
+import torch.distributed as dist
+sys.path.insert(0, ROOT)
+from moocore_b200 import _api
+from moocore_b200.sharding import mc_shard_start, shard_range
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+N, d = 10**9, 50
+
+class FakePlan:                     # the exchange protocol without a GPU: rank 1's scan fails
+    empty = False
+    nobj = d
+    def mc_segment_scan(self, seed, pair0, npairs):
+        if rank == 1:
+            raise RuntimeError("forced: tail loop beyond the device tables")
+        seg = _api.McSegment(pair0, npairs, 15, (_api.ctypes.c_uint64 * 16)(*([0] * 16)), 1000, 0)
+        return seg
+    def set_mc_start(self, pair, discard):
+        raise AssertionError("no rank may start from a pair range when one scan failed")
+
+assert _api.mc_segment_layout(N, d, world, rank) is not None
+got = mc_shard_start(FakePlan(), N, 42, rank, world)
+assert got == shard_range(N, rank, world), got
+if rank == 0:
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+def test_failed_scan_sends_every_rank_to_sample_ranges(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text("ROOT = %r\n" % ROOT + WORKER_FALLBACK)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 40), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "OK" in res.stdout
