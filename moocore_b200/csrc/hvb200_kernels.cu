@@ -2756,7 +2756,13 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
     else if (plan->kernel == HVB200_KERNEL_AUTO) {
         if (dp->n < 256) mode = MODE_EXACT;
         else if (d > 32) mode = MODE_BP;
-        else if (dp->n >= 512 && (dp->bp_ready || plan->run_samples >= (uint64_t)65536 * (uint64_t)d)) mode = MODE_BP;
+        // Round 2: the preparation runs on the device (0.2-0.4 ms of kernels), so whole calls — plan creation from host
+        // buffers + one run — are faster with the pruned kernel from n*d ~ 16 K coordinates on whatever the run's length
+        // (dev/auto_choice.py, pruned / DPX call time at 16 K ... 1 M directions: n=2000,d=10 0.90 ... 0.58; n=5000,d=10
+        // 0.89 ... 0.45; n=2000,d=30 0.27 ... 0.33; n=20000,d=20 0.51 ... 0.34; n=1e5,d=3 0.67 ... 0.22), while small sets
+        // (n=1000,d=5: 1.12 ... 0.67) still need ~65 K*d directions to earn it back.
+        else if (dp->n >= 512 && (dp->bp_ready || plan->run_samples >= (uint64_t)65536 * (uint64_t)d ||
+                                  (uint64_t)dp->n * (uint64_t)d >= 16384)) mode = MODE_BP;
     }
     if (mode == MODE_BP && dp->n / 32 + 64 >= ((size_t)1 << kBpPtBits)) mode = MODE_DPX;   // hit entries hold 23-bit granule (32-point) indices
     if (d > 32 && mode != MODE_BP) mode = MODE_EXACT;
