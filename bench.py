@@ -313,28 +313,30 @@ def run_ours(args, rank, local_rank, world):
         flat = gather_partials(hilo, device=dev)
         return mb.hv_approx_finalize(d, N, flat)
 
-    e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        est_e2e = step_e2e()
-    e1.record()
-    barrier()
-    e2e_s = e0.elapsed_time(e1) / 1e3
-    t2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_s = t2.item()
-    e2e_value = units_per_step * e2e_steps / e2e_s / 1e9
+    e2e_steps = max(1, min(args.steps, 3)) if args.e2e_steps < 0 else args.e2e_steps
+    est_e2e, e2e_value = None, None
+    if e2e_steps > 0:
+        step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            est_e2e = step_e2e()
+        e1.record()
+        barrier()
+        e2e_s = e0.elapsed_time(e1) / 1e3
+        t2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_s = t2.item()
+        e2e_value = units_per_step * e2e_steps / e2e_s / 1e9
 
     # ---------------- single-process leg: ONE call of the reference's own C symbol, all N GPUs from one process ----------------
     # What a Python/R caller of the drop-in gets: hv_approx_hua_wang / hv_approx_normal (c/hvapprox.h:16-28) with
     # HVB200_NGPUS=N — host threads per GPU and one ncclAllGather inside the library, no torchrun.  Rank 0 makes the
     # calls, the other ranks wait at the barrier with their GPUs idle.  Host wall clock around the call.
     single = None
-    if d <= 31:
+    if d <= 31 and e2e_steps > 0:
         barrier()
         # the other ranks wait on the rendezvous store (a host-side wait): an NCCL barrier would park a spinning kernel on
         # their GPUs, exactly the GPUs rank 0's threads are about to use (measured: 40 ms instead of 14 ms per cfg3 call)
@@ -460,6 +462,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg3", choices=list(hvcases.CONFIGS))
     ap.add_argument("--kernel", default="auto", choices=["auto", "exact", "screen", "dpx", "pruned"])
+    ap.add_argument("--e2e-steps", type=int, default=-1,
+                    help="steps of the end-to-end legs (default min(steps, 3); 0 skips them: side lines of the long configs)")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":
