@@ -5,8 +5,9 @@
 
 One "step" = one complete DZ2019-HW estimate of BASELINE.json's metric config
 (d=10, n=10 000 points on a spherical front, nsamples=1e8), sharded over the N ranks by
-contiguous direction-index ranges (strong scaling; one process per GPU under torchrun, one
-all-gather of 16 bytes per rank).  Prints ONE JSON line on rank 0.
+block-cyclic direction blocks (strong scaling; one process per GPU under torchrun, one
+all-gather of 16 bytes per rank).  --config cfg1..cfg5 runs the other BASELINE configs (DZ2019-MC
+configs shard by pair ranges of the MT19937 stream).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -431,7 +432,9 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config), "kernel": {1: "exact", 2: "screen", 3: "dpx", 4: "pruned"}.get(plan.stats()["kernel"], "?"),
-                       "npoints_after_filter": npts, "parallelism": (f"block-cyclic direction blocks of {shard_block(N, world)} x{world}" if cyclic else f"direction-range x{world}"),
+                       "npoints_after_filter": npts, "parallelism": (f"block-cyclic direction blocks of {shard_block(N, world)} x{world}" if cyclic else
+                                       (f"pair ranges of the MT19937 stream x{world} (no rank parses a prefix)" if world > 1 and method == "DZ2019-MC"
+                                        else f"direction-range x{world}")),
                        "l2": "no flush: the point set (8 n d bytes, 0.8 MB at cfg3) is L2-resident by design (every CTA re-reads "
                              "its keys each chunk: that is the algorithm, not a warm-cache artefact), the directions are "
                              "generated inside the kernel (DZ2019-HW) or streamed through a batch buffer larger than L2 (MC), "
