@@ -69,8 +69,8 @@ struct BpArgs {
     double *values;
     ull *slow_counter;
     uint2 *hits;              // [grid][kBpHitCap] hit lists: {direction of the chunk, point} per candidate
-    uint4 *quads;             // [grid][seg_blocks * CH / 4] the CTA's list of surviving (direction, block) pairs, four
-                              // directions of one block per entry (L2 resident)
+    uint4 *quads;             // [grid]{[seg_blocks * CH / 4] x 8 bytes of row offsets, then x 4 bytes of block indices}: the CTA's
+                              // list of surviving (direction, block) pairs, four directions of one block per entry (L2 resident)
     double qscale[HVB200_MAXD], qlos[HVB200_MAXD];
     // GEN = true (DZ2019-HW sums): the CTA generates the directions of its chunk itself (hw_direction) into a private
     // scratch block [2D][CH] (objective-major: coalesced for the lane = direction phases), which stays in L2 — there is
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(kBpThreads, (D <= 16 ? HVB200_BP_MINB : 2)) k_
     uint4 *sq = reinterpret_cast<uint4 *>(smem_raw + L.list) + warp * 32;                          // this warp's staged quads
     // the CTA's pair list: per quad four 16-bit threshold-row offsets, and the quad's block
     const size_t qcap = (size_t)a.seg_blocks * (CH / 4);
-    unsigned short *qoff = reinterpret_cast<unsigned short *>(a.quads + (size_t)blockIdx.x * qcap);
-    unsigned *qblk = reinterpret_cast<unsigned *>(qoff + qcap * 4);
+    unsigned short *qoff = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(a.quads) + (size_t)blockIdx.x * qcap * 12);
+    unsigned *qblk = reinterpret_cast<unsigned *>(qoff + qcap * 4);          // 8 + 4 bytes per quad
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); ctr[1] = 0; }
     if (tid < kBpThreads / 32) eost[tid] = a.early_out ? 0x80000000u : 0u;
     // every warp appends to its own eighth of the CTA's hit list: the count is a warp-uniform register, no atomics

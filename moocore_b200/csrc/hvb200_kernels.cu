@@ -2806,12 +2806,12 @@ extern "C" int hvb200cu_run_begin(struct hvb200_plan *plan, void *stream, uint64
         dp->bp_hits_cap = (size_t)dp->grid * kBpHitCap;
     }
     if (mode == MODE_BP) {
-        // worst case: every direction of a chunk survives in every block of a segment
-        const size_t need = (size_t)dp->grid * (size_t)dp->bp_seg_blocks * (size_t)(kBpThreads * bp_R_of(d) / 4);
+        // worst case: every direction of a chunk survives in every block of a segment; 12 bytes per quad
+        const size_t need = (size_t)dp->grid * (size_t)dp->bp_seg_blocks * (size_t)(kBpThreads * bp_R_of(d) / 4) * 12;
         if (dp->bp_quads_cap < need) {
             cudaFree(dp->bp_quads);
             dp->bp_quads = nullptr; dp->bp_quads_cap = 0;
-            CUDA_TRY(cudaMalloc(&dp->bp_quads, need * sizeof(uint4)));
+            CUDA_TRY(cudaMalloc(&dp->bp_quads, need));
             dp->bp_quads_cap = need;
         }
     }
