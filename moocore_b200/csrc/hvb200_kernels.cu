@@ -3078,6 +3078,18 @@ extern "C" int hvb200cu_read_dirs(struct hvb200_plan *plan, uint64_t count, doub
     return 0;
 }
 
+// Grid of a k_maxmin_bp launch.  Long runs take every resident CTA and let the dynamic chunk hand-out even things out; a
+// short run (default-sized calls: 262 144 directions are 512 chunks for 444 resident CTAs) would leave most of the GPU
+// idle while a few CTAs work on a second chunk, so it gets ceil(chunks / rounds) CTAs: every CTA the same number of chunks.
+static unsigned bp_grid_for(const DevPlan *dp, ull n_chunks)
+{
+    const ull full = (ull)dp->grid;
+    if (n_chunks <= full) return (unsigned)(n_chunks ? n_chunks : 1);
+    const ull rounds = (n_chunks + full - 1) / full;
+    if (rounds > 3) return (unsigned)full;
+    return (unsigned)((n_chunks + rounds - 1) / rounds);
+}
+
 // the arguments of k_maxmin_bp that do not depend on where the directions come from
 static int bp_fill_args(DevPlan *dp, BpArgs &ka, uint64_t count, ull n_chunks)
 {
@@ -3131,7 +3143,7 @@ extern "C" int hvb200cu_maxmin_hw_fused(struct hvb200_plan *plan, const hvb200_h
     const ull chunk = (ull)kBpThreads * bp_R_of(d);
     const ull n_chunks = (count + chunk - 1) / chunk;
     if (n_chunks > 0xfffffff0ull) { hvb200_set_error("internal: too many chunks for one launch"); return -1; }
-    const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks);
+    const unsigned grid = bp_grid_for(dp, n_chunks);
     BpArgs ka;
     const int b = span_begin(dp, 0);
     if (bp_fill_args(dp, ka, count, n_chunks)) return -1;
@@ -3181,7 +3193,7 @@ extern "C" int hvb200cu_maxmin(struct hvb200_plan *plan, uint64_t count, double 
     const ull chunk = bp ? (ull)kBpThreads * bp_R_of(d)
                          : (ull)kConsumerThreads * (dpx ? dp->kR : (dp->kernel_used == MODE_EXACT ? dp->R_exact : dp->R));
     const ull n_chunks = (count + chunk - 1) / chunk;
-    const unsigned grid = (unsigned)std::min<ull>((ull)dp->grid, n_chunks ? n_chunks : 1);
+    const unsigned grid = bp ? bp_grid_for(dp, n_chunks) : (unsigned)std::min<ull>((ull)dp->grid, n_chunks ? n_chunks : 1);
     const int b = span_begin(dp, 0);
     if (bp) {
         BpArgs ka;

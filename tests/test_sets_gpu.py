@@ -54,15 +54,20 @@ def test_sets_data_cumsizes_layout_and_high_d(mb):
 
 def test_sets_amortise_the_per_call_cost(mb):
     sets = [hvcases.front("sphere", 100, 3, i) for i in range(200)]
-    mb.hv_approx_sets(sets[:2], 1.1, nsamples=100_000, method="DZ2019-HW")       # warm-up
-    t0 = time.perf_counter()
-    a = mb.hv_approx_sets(sets, 1.1, nsamples=100_000, method="DZ2019-HW")
-    t1 = time.perf_counter()
-    b = [mb.hv_approx(s, ref=1.1, nsamples=100_000, method="DZ2019-HW") for s in sets]
-    t2 = time.perf_counter()
+    mb.hv_approx_sets(sets, 1.1, nsamples=100_000, method="DZ2019-HW")           # warm-up: buffers of the full size
+    mb.hv_approx(sets[0], ref=1.1, nsamples=100_000, method="DZ2019-HW")
+    batched, looped = [], []
+    for _ in range(3):               # best of three: one-off allocations and a noisy host must not decide the comparison
+        t0 = time.perf_counter()
+        a = mb.hv_approx_sets(sets, 1.1, nsamples=100_000, method="DZ2019-HW")
+        t1 = time.perf_counter()
+        b = [mb.hv_approx(s, ref=1.1, nsamples=100_000, method="DZ2019-HW") for s in sets]
+        t2 = time.perf_counter()
+        batched.append(t1 - t0)
+        looped.append(t2 - t1)
     assert np.allclose(a, b, rtol=1e-13, atol=0)
-    print("batched %.2f ms, looped %.2f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1)))
-    assert t1 - t0 < t2 - t1
+    print("batched %.2f ms, looped %.2f ms" % (1e3 * min(batched), 1e3 * min(looped)))
+    assert min(batched) < min(looped)
 
 
 def test_rphi_direction_cache_is_transparent(mb, monkeypatch):
