@@ -1688,7 +1688,10 @@ static constexpr KernelCfg cfg_for(int D)
     //             R  G  minb staged
     if (D <= 5)  return {2, 4, 2, true};
     if (D <= 12) return {3, 2, 2, false};
-    if (D <= 24) return {1, 2, 2, true};
+    if (D <= 22) return {1, 2, 2, true};
+    // 23, 24: one CTA per SM as well (d = 23, n = 2000: EXACT 6.09 -> 3.38 ms per 4e5 directions, SCREEN 10.9 -> 3.26); below,
+    // two CTAs with their 100-330 bytes of spills are faster (d = 17, 18, 20: 2-30 % slower with one)
+    if (D <= 24) return {1, 2, 1, true};
     // 25..32: one CTA per SM (255 registers).  With two, r[D] and the thresholds spilled 650-900 bytes per thread and the
     // textbook loop ran at half the speed (d = 30, n = 2000: EXACT 9.16 -> 4.05 ms per 4e5 directions, DPX 4.07 -> 3.15)
     if (D <= 32) return {1, 2, 1, false};
@@ -1739,7 +1742,7 @@ static constexpr DpxCfg dpx_cfg_for(int D)
     if (D <= 8)  return {4, 4, 3};
     if (D <= 12) return {4, 4, 2};
     if (D <= 20) return {3, 4, 2};
-    if (D <= 24) return {2, (D % 2) ? 4 : 2, 2};
+    if (D <= 24) return {2, (D % 2) ? 4 : 2, 2};      // (d = 23: 1.86 ms with two CTAs per SM, 1.98 with one)
     return {2, (D % 2) ? 4 : 2, 1};
 }
 typedef void (*dpx_fn)(const DpxArgs);
